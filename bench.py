@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the full ColorHandPose3DNetwork.inference pipeline on synthetic 320x320 batches.
+
+  python bench.py --gpus N --steps K --warmup W            # our sm_100a path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement of the TF1 reference (oracle)
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the full pipeline (HandSegNet -> mask/crop ->
+PoseNet2D -> PosePrior/Viewpoint lifting -> x8 up-sampling -> key-point arg-max) over one batch of
+`--batch` synthetic images PER GPU (weak scaling; BASELINE config 4 shards 32 images per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE = 142.258408192          # conv + FC FLOPs of the full pipeline (SURVEY.md 8a.1 / arch.conv_flops_per_image)
+METRIC = "images/sec full pipeline 320x320"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"tflops_burst": float(d["bf16_tflops"]), "tflops_sustained": float(d["bf16_tflops_sustained"]),
+                    "hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+        except Exception:
+            pass
+    return {"tflops_burst": 1590.0, "tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            names = {getattr(N, k): k for k in dir(N) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+            while not self.stop_flag:
+                self.sm.append(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM))
+                try:
+                    mask = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if isinstance(bit, int) and bit and (mask & bit) == bit and bin(bit).count("1") == 1:
+                        self.reasons.add(nm.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+                time.sleep(0.05)
+        except Exception as e:  # NVML unavailable: report that instead of clocks
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        r = sorted(x for x in self.reasons if x not in ("GpuIdle", "None", "ApplicationsClocksSetting"))
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": r, "samples": len(self.sm)}
+
+
+def cpu_reference_throughput(n_images, H, W, seconds_cap=40.0):
+    """Times the oracle (CPU restatement of the TF1 graph; the reference itself needs TensorFlow 1.3, which cannot be
+    installed here) on all host cores.  Returns (images/s, cores, sample description)."""
+    import torch
+    from hand3d_b200 import weights as Wt
+    from oracle import hand3d_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wd = Wt.synthetic_weights(0)
+    hs = Wt.synthetic_hand_side(1, seed=2)
+    done, t0 = 0, time.perf_counter()
+    O.inference(Wt.synthetic_images(1, H, W, seed=99), hs, wd, literal_mask=True)   # warm-up (thread pools, oneDNN primitives)
+    t0 = time.perf_counter()
+    for i in range(n_images):
+        O.inference(Wt.synthetic_images(1, H, W, seed=100 + i), hs, wd, literal_mask=True)
+        done += 1
+        if time.perf_counter() - t0 > seconds_cap:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, cores, "%d x [1,%d,%d,3] images, oracle inference() with the literal 32-pass 21x21 dilation, torch %d threads" % (
+        done, H, W, torch.get_num_threads())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    sample = ""
+    cores = os.cpu_count() or 1
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_reference_throughput(args.ref_images, args.height, args.width, seconds_cap=20.0)
+        if i >= args.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * args.ref_images / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full ColorHandPose3DNetwork.inference %dx%d, CPU restatement of the TF1 reference (oracle/); "
+                               "TensorFlow 1.3 is not installable" % (args.height, args.width), "images_per_step": args.ref_images},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hand3d_b200 import runtime, weights as Wt
+    from hand3d_b200.distributed import gather_records, pack_records
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device -- hand3d_b200 has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, H, W = args.batch, args.height, args.width
+
+    ctx = runtime.Context(local_rank, precision=args.precision)
+    ctx.load_weights(Wt.synthetic_weights(0))
+    # synthetic inputs: NBUF different batches per rank (rotated every step so that inputs > L2 never repeat back to back)
+    NBUF = 4
+    host_imgs = [torch.from_numpy(Wt.synthetic_images(B, H, W, seed=1000 + 17 * rank + i)).pin_memory() for i in range(NBUF)]
+    host_hs = [torch.from_numpy(Wt.synthetic_hand_side(B, seed=2000 + 17 * rank + i)).pin_memory() for i in range(NBUF)]
+    dev_imgs = [t.to(dev) for t in host_imgs]
+    dev_hs = [t.to(dev) for t in host_hs]
+
+    def step_device(i):
+        r = ctx.pipeline(dev_imgs[i % NBUF], dev_hs[i % NBUF], True, outputs="keypoints")
+        rec = pack_records(r["keypoint_coord3d"], r["keypoints_uv"], r["center"], r["scale_crop"])
+        return gather_records(rec) if world > 1 else rec
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+
+    # ---- timed region (device-resident inputs)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_device(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2.0)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * B * args.steps / (ms / 1000.0)
+
+    # ---- end-to-end: pinned host -> device copy of the step's inputs and device -> host read of the gathered key-point records
+    out_host = torch.empty((world * B, 108), dtype=torch.float32).pin_memory()
+    stage_img = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    stage_hs = torch.empty((B, 2), dtype=torch.float32, device=dev)
+
+    def step_e2e(i):
+        stage_img.copy_(host_imgs[i % NBUF], non_blocking=True)
+        stage_hs.copy_(host_hs[i % NBUF], non_blocking=True)
+        r = ctx.pipeline(stage_img, stage_hs, True, outputs="keypoints")
+        rec = pack_records(r["keypoint_coord3d"], r["keypoints_uv"], r["center"], r["scale_crop"])
+        if world > 1:
+            rec = gather_records(rec)
+        out_host.copy_(rec, non_blocking=True)
+
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    f1.record()
+    barrier()
+    t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) / 1000.0)
+    h2d = B * H * W * 3 * 4 + B * 2 * 4
+    d2h = world * B * 108 * 4
+
+    # ---- per-kernel-class timing (CUDA events around every launch; separate pass so it does not perturb `value`)
+    prof_steps = min(3, args.steps)
+    ctx.profile_begin()
+    for i in range(prof_steps):
+        ctx.pipeline(dev_imgs[i % NBUF], dev_hs[i % NBUF], True, outputs="keypoints")
+    prof = ctx.profile_end()
+    peaks = measured_peaks()
+    roof = None
+    dominant = "tc_conv" if prof["tc_conv"]["launches"] else "direct_conv"
+    d = prof[dominant]
+    if d["ms"] > 0:
+        achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
+        peak = peaks["tflops_sustained"] if dominant == "tc_conv" else 75.0
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all layers)" if dominant == "tc_conv" else "conv_direct_kernel (fp32 FFMA)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peaks["source"] + (", bf16 sustained" if dominant == "tc_conv" else ", nominal fp32 FFMA"),
+                "launches_per_step": d["launches"] // prof_steps, "ms_per_step": d["ms"] / prof_steps,
+                "mma_passes": 3 if args.precision in ("bf16x3", "fp16x3") else 1,
+                "share_of_step": (d["ms"] / prof_steps) / (ms / args.steps),
+                "by_class_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items()}}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_reference_throughput(args.cpu_images, H, W, seconds_cap=25.0)
+            cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16x3": "bf16 hi/lo split x3 MMA passes, fp32 accumulate (fp32 parity, 1e-3)",
+                      "fp16x3": "fp16 hi/lo split x3 MMA passes, fp32 accumulate (fp32 parity, 1e-3)",
+                      "fp16": "fp16 (1e-2 path)", "bf16": "bf16", "fp32_ffma": "f32"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "full ColorHandPose3DNetwork.inference (HandSegNet+PoseNet2D+PosePrior/Viewpoint, %dx%d input, 256x256 crop), "
+                                   "%d images per GPU per step (BASELINE config 4 shard)" % (H, W, B),
+                       "global_batch": world * B, "precision": args.precision, "parallelism": "dp%d" % world,
+                       "l2": "inputs rotate over %d distinct batches per rank (%.0f MB > L2); activations per step %.1f GB" % (
+                           NBUF, NBUF * B * H * W * 12 / 1e6, B * 0.312),
+                       "collective": "all_gather of 432 B/image key-point records (NCCL)" if world > 1 else "none (single GPU)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "tflops_algorithmic": value * GFLOP_PER_IMAGE / 1e3,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--height", type=int, default=320)
+    ap.add_argument("--width", type=int, default=320)
+    ap.add_argument("--precision", default=os.environ.get("H3D_PRECISION", "bf16x3"), choices=["bf16x3", "fp16x3", "fp16", "bf16", "fp32_ffma"])
+    ap.add_argument("--cpu-images", type=int, default=6, help="bounded CPU-baseline sample (images)")
+    ap.add_argument("--ref-images", type=int, default=2, help="--impl reference: images per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

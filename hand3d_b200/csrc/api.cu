@@ -1,0 +1,948 @@
+// C ABI (include/hand3d_b200.h): context, weight loading / packing, workspace layout, the fixed layer
+// schedules of HandSegNet / PoseNet2D / PosePrior / ViewpointNet and the full pipeline.
+#include <cstdarg>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace h3d {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return H3D_ENODEVICE;
+    return H3D_ECUDA;
+}
+
+// ------------------------------------------------------------------------------------------ layer tables
+struct LayerSpec { const char* name; int k, stride, cin, cout, leaky; };
+
+static const LayerSpec kHandSeg[] = {
+    {"conv1_1", 3, 1, 3, 64, 1},    {"conv1_2", 3, 1, 64, 64, 1},   {"conv2_1", 3, 1, 64, 128, 1},  {"conv2_2", 3, 1, 128, 128, 1},
+    {"conv3_1", 3, 1, 128, 256, 1}, {"conv3_2", 3, 1, 256, 256, 1}, {"conv3_3", 3, 1, 256, 256, 1}, {"conv3_4", 3, 1, 256, 256, 1},
+    {"conv4_1", 3, 1, 256, 512, 1}, {"conv4_2", 3, 1, 512, 512, 1}, {"conv4_3", 3, 1, 512, 512, 1}, {"conv4_4", 3, 1, 512, 512, 1},
+    {"conv5_1", 3, 1, 512, 512, 1}, {"conv5_2", 3, 1, 512, 128, 1}, {"conv6_1", 1, 1, 128, 512, 1}, {"conv6_2", 1, 1, 512, 2, 0}};
+static const LayerSpec kPoseTrunk[] = {
+    {"conv1_1", 3, 1, 3, 64, 1},    {"conv1_2", 3, 1, 64, 64, 1},   {"conv2_1", 3, 1, 64, 128, 1},  {"conv2_2", 3, 1, 128, 128, 1},
+    {"conv3_1", 3, 1, 128, 256, 1}, {"conv3_2", 3, 1, 256, 256, 1}, {"conv3_3", 3, 1, 256, 256, 1}, {"conv3_4", 3, 1, 256, 256, 1},
+    {"conv4_1", 3, 1, 256, 512, 1}, {"conv4_2", 3, 1, 512, 512, 1}, {"conv4_3", 3, 1, 512, 256, 1}, {"conv4_4", 3, 1, 256, 256, 1},
+    {"conv4_5", 3, 1, 256, 256, 1}, {"conv4_6", 3, 1, 256, 256, 1}, {"conv4_7", 3, 1, 256, 128, 1}};
+static const LayerSpec kPosePrior[] = {{"conv_pose_0_1", 3, 1, 21, 32, 1},  {"conv_pose_0_2", 3, 2, 32, 32, 1},
+                                       {"conv_pose_1_1", 3, 1, 32, 64, 1},  {"conv_pose_1_2", 3, 2, 64, 64, 1},
+                                       {"conv_pose_2_1", 3, 1, 64, 128, 1}, {"conv_pose_2_2", 3, 2, 128, 128, 1}};
+static const LayerSpec kViewpoint[] = {{"conv_vp_0_1", 3, 1, 21, 64, 1},   {"conv_vp_0_2", 3, 2, 64, 64, 1},
+                                       {"conv_vp_1_1", 3, 1, 64, 128, 1},  {"conv_vp_1_2", 3, 2, 128, 128, 1},
+                                       {"conv_vp_2_1", 3, 1, 128, 256, 1}, {"conv_vp_2_2", 3, 2, 256, 256, 1}};
+
+struct VarShape { int nd; int64_t s[4]; };
+static std::map<std::string, VarShape> build_known_vars() {
+    std::map<std::string, VarShape> m;
+    auto conv = [&](const std::string& scope, const LayerSpec& l) {
+        m[scope + "/" + l.name + "/weights"] = {4, {l.k, l.k, l.cin, l.cout}};
+        m[scope + "/" + l.name + "/biases"] = {1, {l.cout, 0, 0, 0}};
+    };
+    auto fc = [&](const std::string& scope, const char* n, int in, int out) {
+        m[scope + "/" + n + "/weights"] = {2, {in, out, 0, 0}};
+        m[scope + "/" + n + "/biases"] = {1, {out, 0, 0, 0}};
+    };
+    for (auto& l : kHandSeg) conv("HandSegNet", l);
+    for (auto& l : kPoseTrunk) conv("PoseNet2D", l);
+    conv("PoseNet2D", {"conv5_1", 1, 1, 128, 512, 1});
+    conv("PoseNet2D", {"conv5_2", 1, 1, 512, 21, 0});
+    for (int u = 6; u <= 7; ++u) {
+        char nm[16];
+        for (int i = 1; i <= 7; ++i) {
+            snprintf(nm, sizeof(nm), "conv%d_%d", u, i);
+            const int k = i <= 5 ? 7 : 1, cin = i == 1 ? 149 : 128, cout = i == 7 ? 21 : 128;
+            m[std::string("PoseNet2D/") + nm + "/weights"] = {4, {k, k, cin, cout}};
+            m[std::string("PoseNet2D/") + nm + "/biases"] = {1, {cout, 0, 0, 0}};
+        }
+    }
+    for (auto& l : kPosePrior) conv("PosePrior", l);
+    fc("PosePrior", "fc_rel0", 2050, 512); fc("PosePrior", "fc_rel1", 512, 512); fc("PosePrior", "fc_xyz", 512, 63);
+    fc("PosePrior", "fc_bottleneck", 512, 30);
+    for (auto& l : kViewpoint) conv("ViewpointNet", l);
+    fc("ViewpointNet", "fc_vp0", 4098, 256); fc("ViewpointNet", "fc_vp1", 256, 128);
+    fc("ViewpointNet", "fc_vp_ux", 128, 1); fc("ViewpointNet", "fc_vp_uy", 128, 1); fc("ViewpointNet", "fc_vp_uz", 128, 1);
+    return m;
+}
+static const std::map<std::string, VarShape>& known_vars() {
+    static const std::map<std::string, VarShape> m = build_known_vars();
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------ context
+struct HostTensor { std::vector<float> data; std::vector<int64_t> shape; };
+struct PackedW { Split w; float* bias = nullptr; int Cin_pad = 0, Cout_pad = 0; };
+
+struct Arena {   // bump allocator over the caller-owned workspace (base == nullptr -> size query)
+    char* base = nullptr; int64_t off = 0;
+    template <typename T> T* alloc(int64_t n) {
+        off = align_up(off, 1024);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += n * (int64_t)sizeof(T);
+        return p;
+    }
+};
+
+struct Ext {   // pointers that change per call (everything else is baked into the plan)
+    const float* in = nullptr;
+    float* out = nullptr;
+    float* out2 = nullptr;
+    float* out3 = nullptr;
+    const float* hand_side = nullptr;
+};
+using StepFn = std::function<int(const Ext&, cudaStream_t)>;
+
+enum StepKind { KIND_TC = 0, KIND_DIRECT = 1, KIND_FC = 2, KIND_OTHER = 3, KIND_COUNT = 4 };
+
+struct StagePlan {
+    std::vector<StepFn> steps;
+    std::vector<int> launches;          // kernels per step
+    std::vector<int> kinds;             // StepKind per step (profiling)
+    std::vector<int64_t> step_flops;    // algorithmic FLOPs per step
+    std::vector<TcConvPlan*> tc;
+    int B = 0, H = 0, W = 0, variant = -1;
+    int64_t flops = 0;
+    ~StagePlan() { for (auto* p : tc) tc_conv_plan_destroy(p); }
+};
+
+}  // namespace h3d
+
+using namespace h3d;
+
+struct h3d_ctx {
+    int device = 0;
+    int precision = H3D_PREC_BF16X3;
+    int64_t launches = 0;
+    std::map<std::string, HostTensor> host_w;
+    std::map<std::string, float*> dev_w;          // raw fp32 copies (HWIO / [in,out] / [C]) for the CUDA-core kernels
+    std::map<std::string, PackedW> packed;        // key = name|half|perm
+    float* vp_head_w = nullptr; float* vp_head_b = nullptr;   // fused fc_vp_ux/uy/uz [128,3]
+    char* ws = nullptr; int64_t ws_bytes = 0;
+    std::unique_ptr<StagePlan> seg, pose, lift;
+    // persistent buffers inside the workspace (laid out by layout())
+    struct Layout {
+        int B = 0, H = 0, W = 0;
+        float *hand_scoremap, *image_crop, *kp_scoremap, *center, *scale, *crop_size, *coord3d;
+        int32_t* kp_uv;
+        void *seg_scratch, *argmax_scratch;
+        float *seg_low, *s[3];
+        int64_t seg_off, pose_off, lift_off, total;
+    } lay;
+    void drop_plans() { seg.reset(); pose.reset(); lift.reset(); }
+    // optional per-kernel-class timing (CUDA events on the launch stream around every plan step)
+    bool profiling = false;
+    struct ProfRec { cudaEvent_t a, b; int kind; int64_t flops; };
+    std::vector<ProfRec> prof;
+};
+
+namespace h3d {
+
+static bool is_tc(int precision) { return precision != H3D_PREC_FP32_FFMA; }
+static int passes_of(int precision) { return (precision == H3D_PREC_BF16X3 || precision == H3D_PREC_FP16X3) ? 3 : 1; }
+static Half16 half_of(int precision) { return (precision == H3D_PREC_FP16X3 || precision == H3D_PREC_FP16) ? Half16::FP16 : Half16::BF16; }
+
+static uint16_t host_h16(float v, Half16 t) {
+    if (t == Half16::FP16) { __half h = __float2half_rn(v); uint16_t b; memcpy(&b, &h, 2); return b; }
+    __nv_bfloat16 h = __float2bfloat16_rn(v); uint16_t b; memcpy(&b, &h, 2); return b;
+}
+static float host_f32(uint16_t b, Half16 t) {
+    if (t == Half16::FP16) { __half h; memcpy(&h, &b, 2); return __half2float(h); }
+    uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f;
+}
+
+// Pack HWIO fp32 -> K-major [Cout_pad][kh][kw][Cin_pad] hi/lo planes.  perm[j] = source input channel of
+// packed channel j (or -1 for zero padding); empty perm = identity.
+static int pack_conv_weights(const float* w, const float* bias, int k, int Cin, int Cout, int Cin_pad, int Cout_pad,
+                             const std::vector<int>& perm, Half16 t, bool want_lo, PackedW* out) {
+    const int64_t Ktot = (int64_t)k * k * Cin_pad;
+    std::vector<uint16_t> hi((size_t)Cout_pad * Ktot, 0), lo;
+    if (want_lo) lo.assign((size_t)Cout_pad * Ktot, 0);
+    for (int co = 0; co < Cout; ++co)
+        for (int tap = 0; tap < k * k; ++tap)
+            for (int cj = 0; cj < Cin_pad; ++cj) {
+                const int ci = perm.empty() ? (cj < Cin ? cj : -1) : perm[cj];
+                if (ci < 0) continue;
+                const float v = w[((int64_t)tap * Cin + ci) * Cout + co];
+                const uint16_t h = host_h16(v, t);
+                const int64_t idx = (int64_t)co * Ktot + (int64_t)tap * Cin_pad + cj;
+                hi[idx] = h;
+                if (want_lo) lo[idx] = host_h16(v - host_f32(h, t), t);
+            }
+    std::vector<float> b((size_t)Cout_pad, 0.f);
+    for (int co = 0; co < Cout; ++co) b[co] = bias[co];
+    H3D_CUDA(cudaMalloc(&out->w.hi, hi.size() * 2));
+    H3D_CUDA(cudaMemcpy(out->w.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+    if (want_lo) {
+        H3D_CUDA(cudaMalloc(&out->w.lo, lo.size() * 2));
+        H3D_CUDA(cudaMemcpy(out->w.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    }
+    H3D_CUDA(cudaMalloc(&out->bias, b.size() * 4));
+    H3D_CUDA(cudaMemcpy(out->bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    out->Cin_pad = Cin_pad; out->Cout_pad = Cout_pad;
+    return H3D_OK;
+}
+
+static void free_packed(PackedW& p) {
+    if (p.w.hi) cudaFree(p.w.hi);
+    if (p.w.lo) cudaFree(p.w.lo);
+    if (p.bias) cudaFree(p.bias);
+    p = PackedW();
+}
+
+static int get_packed(h3d_ctx* ctx, const std::string& scope, const LayerSpec& l, int Cin_pad, const std::vector<int>& perm,
+                      const PackedW** out) {
+    const Half16 t = half_of(ctx->precision);
+    const bool lo = passes_of(ctx->precision) == 3;
+    const std::string key = scope + "/" + l.name + (t == Half16::FP16 ? "|h" : "|b") + (lo ? "3" : "1");
+    auto it = ctx->packed.find(key);
+    if (it == ctx->packed.end()) {
+        auto wi = ctx->host_w.find(scope + "/" + l.name + "/weights"), bi = ctx->host_w.find(scope + "/" + l.name + "/biases");
+        if (wi == ctx->host_w.end() || bi == ctx->host_w.end()) { set_error("weights for %s/%s not loaded", scope.c_str(), l.name); return H3D_EWEIGHTS; }
+        PackedW p;
+        int rc = pack_conv_weights(wi->second.data.data(), bi->second.data.data(), l.k, l.cin, l.cout, Cin_pad, (int)align_up(l.cout, 64), perm, t, lo, &p);
+        if (rc) return rc;
+        it = ctx->packed.emplace(key, p).first;
+    }
+    *out = &it->second;
+    return H3D_OK;
+}
+
+static int dev_weight(h3d_ctx* ctx, const std::string& name, const float** out) {
+    auto it = ctx->dev_w.find(name);
+    if (it == ctx->dev_w.end()) { set_error("weights %s not loaded", name.c_str()); return H3D_EWEIGHTS; }
+    *out = it->second;
+    return H3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------ workspace layout
+static int64_t slot_elems_seg(int B, int H, int W) { return (int64_t)B * H * W * 64; }
+
+static void layout(h3d_ctx::Layout& L, char* base, int B, int H, int W) {
+    Arena a; a.base = base;
+    L.B = B; L.H = H; L.W = W;
+    L.hand_scoremap = a.alloc<float>((int64_t)B * H * W * 2);
+    L.image_crop = a.alloc<float>((int64_t)B * 256 * 256 * 3);
+    L.kp_scoremap = a.alloc<float>((int64_t)B * 256 * 256 * 21);
+    L.center = a.alloc<float>(B * 2); L.scale = a.alloc<float>(B); L.crop_size = a.alloc<float>(B);
+    L.coord3d = a.alloc<float>(B * 63);
+    L.kp_uv = a.alloc<int32_t>(B * 42);
+    L.seg_scratch = a.alloc<char>(seg_scratch_bytes(B, H, W));
+    L.argmax_scratch = a.alloc<char>(argmax_scratch_bytes(B, 21));
+    L.seg_low = a.alloc<float>((int64_t)B * (H / 8) * (W / 8) * 2);
+    const int Hc = std::max(H, 256), Wc = std::max(W, 256);   // PoseNet may also be called stand-alone on HxW crops
+    for (int i = 0; i < 3; ++i) L.s[i] = a.alloc<float>((int64_t)B * (Hc / 8) * (Wc / 8) * 21);
+    a.off = align_up(a.off, 1024); L.seg_off = a.off;
+    a.off += 2 * align_up(slot_elems_seg(B, H, W) * 4, 1024) + 4096;
+    a.off = align_up(a.off, 1024); L.pose_off = a.off;
+    a.off += 2 * align_up((int64_t)B * Hc * Wc * 64 * 4, 1024) + 2 * align_up((int64_t)B * (Hc / 8) * (Wc / 8) * 192 * 4, 1024) +
+             align_up((int64_t)B * (Hc / 8) * (Wc / 8) * 512 * 4, 1024) + 8192;
+    a.off = align_up(a.off, 1024); L.lift_off = a.off;
+    a.off += 2 * align_up((int64_t)B * 32 * 32 * 64 * 4, 1024) + 4 * align_up((int64_t)B * 4100 * 4, 1024) + 16384;
+    L.total = align_up(a.off, 1024);
+}
+
+static int ensure_layout(h3d_ctx* ctx, int B, int H, int W) {
+    h3d_ctx::Layout probe;
+    layout(probe, nullptr, B, H, W);
+    if (!ctx->ws || ctx->ws_bytes < probe.total) {
+        set_error("workspace too small: need %lld bytes for B=%d H=%d W=%d, have %lld (call h3d_workspace_bytes / h3d_set_workspace)",
+                  (long long)probe.total, B, H, W, (long long)ctx->ws_bytes);
+        return H3D_EWORKSPACE;
+    }
+    if (ctx->lay.B != B || ctx->lay.H != H || ctx->lay.W != W || ctx->lay.hand_scoremap != (float*)ctx->ws) {
+        ctx->drop_plans();
+        layout(ctx->lay, ctx->ws, B, H, W);
+    }
+    return H3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------ step builders
+struct Act {   // an activation tensor living in the workspace
+    float* f = nullptr;   // fp32 view
+    Split s;              // split view (tensor-core modes)
+    int C = 0;            // channel stride
+};
+static Act slot_view(char* p, int64_t elems, int C, bool split, bool lo) {
+    Act a; a.C = C;
+    if (split) { a.s.hi = (uint16_t*)p; a.s.lo = lo ? (uint16_t*)(p + align_up(elems * 2, 1024)) : nullptr; }
+    else a.f = (float*)p;
+    return a;
+}
+
+static void tag(StagePlan* pl, int kind, int64_t flops) {
+    while (pl->kinds.size() + 1 < pl->launches.size()) { pl->kinds.push_back(KIND_OTHER); pl->step_flops.push_back(0); }
+    pl->kinds.push_back(kind); pl->step_flops.push_back(flops);
+}
+
+static int add_direct(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec& l, int B, int H, int W,
+                      const float* x /*null -> Ext.in*/, int Cin_total, int cin_off, float* y, int Cout_total, int cout_off,
+                      Split ys, int Cs_total, int cs_off) {
+    const float *w, *b;
+    int rc;
+    if ((rc = dev_weight(ctx, scope + "/" + l.name + "/weights", &w))) return rc;
+    if ((rc = dev_weight(ctx, scope + "/" + l.name + "/biases", &b))) return rc;
+    DirectConvArgs a;
+    a.x = x; a.Cin_total = Cin_total; a.cin_off = cin_off; a.w = w; a.bias = b; a.y = y; a.Cout_total = Cout_total; a.cout_off = cout_off;
+    a.ys = ys; a.Cs_total = Cs_total; a.cs_off = cs_off; a.half = half_of(ctx->precision);
+    a.B = B; a.H = H; a.W = W; a.Cin = l.cin; a.Cout = l.cout; a.k = l.k; a.stride = l.stride; a.leaky = l.leaky;
+    pl->steps.push_back([a](const Ext& e, cudaStream_t s) {
+        DirectConvArgs aa = a;
+        if (!aa.x) aa.x = e.in;
+        return launch_conv_direct(aa, s);
+    });
+    pl->launches.push_back(1);
+    const int64_t fl = 2ll * B * ceil_div(H, l.stride) * ceil_div(W, l.stride) * l.k * l.k * l.cin * l.cout;
+    pl->flops += fl;
+    tag(pl, KIND_DIRECT, fl);
+    return H3D_OK;
+}
+
+static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec& l, int B, int H, int W, Split x,
+                  int Cin_total, int Cin_pad, const std::vector<int>& perm, Split y, int Cy_total, int cy_off, float* yf,
+                  int Cyf_total, int cyf_off) {
+    const PackedW* pw;
+    int rc = get_packed(ctx, scope, l, Cin_pad, perm, &pw);
+    if (rc) return rc;
+    TcConvDesc d;
+    d.x = x; d.Cin_total = Cin_total; d.Cin_pad = Cin_pad; d.w = pw->w; d.bias = pw->bias; d.Cout = l.cout; d.Cout_pad = pw->Cout_pad;
+    d.y = y; d.Cy_total = Cy_total; d.cy_off = cy_off; d.yf = yf; d.Cyf_total = Cyf_total; d.cyf_off = cyf_off;
+    d.B = B; d.H = H; d.W = W; d.k = l.k; d.leaky = l.leaky; d.passes = passes_of(ctx->precision); d.half = half_of(ctx->precision);
+    TcConvPlan* tp = tc_conv_plan_create(d);
+    if (!tp) return H3D_ECUDA;
+    pl->tc.push_back(tp);
+    pl->steps.push_back([tp](const Ext&, cudaStream_t s) { return tc_conv_launch(tp, s); });
+    pl->launches.push_back(1);
+    const int64_t fl = 2ll * B * H * W * l.k * l.k * l.cin * l.cout;
+    pl->flops += fl;
+    tag(pl, KIND_TC, fl);
+    return H3D_OK;
+}
+
+// VGG-style trunk shared by HandSegNet and PoseNet2D: conv layers [0, n) of `layers` with 2x2 pools after
+// conv1_2 / conv2_2 / conv3_4; ping-pongs between two workspace slots.  Returns the final activation.
+static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec* layers, int n, int B, int H, int W,
+                       char* slot0, char* slot1, int64_t slot_elems, Act* last, int* Hout, int* Wout, Act* final_override,
+                       int final_c_off) {
+    const bool tc = is_tc(ctx->precision), lo = passes_of(ctx->precision) == 3;
+    const Half16 half = half_of(ctx->precision);
+    char* slots[2] = {slot0, slot1};
+    int cur = 0;
+    Act in;   // empty -> external fp32 input
+    int h = H, w = W, rc;
+    for (int i = 0; i < n; ++i) {
+        const LayerSpec& l = layers[i];
+        const bool last_layer = (i == n - 1) && final_override;
+        Act out = last_layer ? *final_override : slot_view(slots[cur], slot_elems, l.cout, tc, lo);
+        const bool use_tc = tc && l.cin % 64 == 0 && l.cout % 64 == 0 && l.stride == 1;
+        const int c_off = last_layer ? final_c_off : 0;
+        if (use_tc) {
+            rc = add_tc(ctx, pl, scope, l, B, h, w, in.s, in.C, l.cin, {}, out.s, out.C, c_off, nullptr, 0, 0);
+        } else if (tc) {   // first layer (Cin = 3): CUDA-core conv writing the split planes directly
+            rc = add_direct(ctx, pl, scope, l, B, h, w, in.f, i == 0 ? l.cin : in.C, 0, nullptr, 0, 0, out.s, out.C, c_off);
+        } else {
+            rc = add_direct(ctx, pl, scope, l, B, h, w, in.f, i == 0 ? l.cin : in.C, 0, out.f, out.C, c_off, Split(), 0, 0);
+        }
+        if (rc) return rc;
+        in = out; cur ^= 1;
+        if (!strcmp(l.name, "conv1_2") || !strcmp(l.name, "conv2_2") || !strcmp(l.name, "conv3_4")) {
+            Act pooled = slot_view(slots[cur], slot_elems, l.cout, tc, lo);
+            const Act src = in;
+            const int hh = h, ww = w, cc = l.cout;
+            if (tc) pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_maxpool_split(src.s, pooled.s, B, hh, ww, cc, half, s); });
+            else pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_maxpool_f32(src.f, pooled.f, B, hh, ww, cc, s); });
+            pl->launches.push_back(1);
+            in = pooled; cur ^= 1; h /= 2; w /= 2;
+        }
+    }
+    *last = in; *Hout = h; *Wout = w;
+    return H3D_OK;
+}
+
+static int build_handsegnet(h3d_ctx* ctx, int B, int H, int W) {
+    H3D_REQUIRE(H % 8 == 0 && W % 8 == 0, "HandSegNet: H and W must be multiples of 8 (got %dx%d)", H, W);
+    auto pl = std::make_unique<StagePlan>();
+    pl->B = B; pl->H = H; pl->W = W;
+    const bool tc = is_tc(ctx->precision);
+    char* r = ctx->ws + ctx->lay.seg_off;
+    const int64_t se = slot_elems_seg(B, H, W);
+    char* slot0 = r; char* slot1 = r + align_up(se * 4, 1024);
+    Act last; int h, w, rc;
+    if ((rc = build_trunk(ctx, pl.get(), "HandSegNet", kHandSeg, 14, B, H, W, slot0, slot1, se, &last, &h, &w, nullptr, 0))) return rc;
+    // conv6_1 (1x1, 128 -> 512, leaky) -> fp32; conv6_2 (1x1, 512 -> 2, linear) on CUDA cores
+    char* other = (last.f ? (char*)last.f : (char*)last.s.hi) == slot0 ? slot1 : slot0;
+    float* f512 = (float*)other;
+    if (tc) rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.s, last.C, 128, {}, Split(), 0, 0, f512, 512, 0);
+    else rc = add_direct(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.f, last.C, 0, f512, 512, 0, Split(), 0, 0);
+    if (rc) return rc;
+    float* low = ctx->lay.seg_low;
+    if ((rc = add_direct(ctx, pl.get(), "HandSegNet", kHandSeg[15], B, h, w, f512, 512, 0, low, 2, 0, Split(), 0, 0))) return rc;
+    pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_resize_bilinear_tf1(low, e.out, B, h, w, 2, H, W, s); });
+    pl->launches.push_back(1);
+    ctx->seg = std::move(pl);
+    return H3D_OK;
+}
+
+static int build_posenet(h3d_ctx* ctx, int B, int Hc, int Wc) {
+    H3D_REQUIRE(Hc % 8 == 0 && Wc % 8 == 0, "PoseNet2D: crop height/width must be multiples of 8 (got %dx%d)", Hc, Wc);
+    H3D_REQUIRE(Hc <= std::max(ctx->lay.H, 256) && Wc <= std::max(ctx->lay.W, 256), "PoseNet2D: crop %dx%d exceeds the workspace layout", Hc, Wc);
+    auto pl = std::make_unique<StagePlan>();
+    pl->B = B; pl->H = Hc; pl->W = Wc;
+    const bool tc = is_tc(ctx->precision), lo = passes_of(ctx->precision) == 3;
+    const int h8 = Hc / 8, w8 = Wc / 8;
+    const int LH = std::max(ctx->lay.H, 256), LW = std::max(ctx->lay.W, 256);
+    char* r = ctx->ws + ctx->lay.pose_off;
+    const int64_t se = (int64_t)B * Hc * Wc * 64;
+    char* slot0 = r; r += align_up((int64_t)B * LH * LW * 64 * 4, 1024);
+    char* slot1 = r; r += align_up((int64_t)B * LH * LW * 64 * 4, 1024);
+    char* cbuf = r; r += 2 * align_up((int64_t)B * (LH / 8) * (LW / 8) * 192 * 4, 1024);
+    float* f512 = (float*)r;
+    const int64_t pix = (int64_t)B * h8 * w8;
+    int rc, h, w;
+    Act last;
+    // concat buffer: tensor-core modes = split planes [pix,192] ordered (encoding 0..127 | scoremap 128..148 | zero pad);
+    // fp32 mode = [pix,149] in the reference order (scoremap 0..20 | encoding 21..148)   (nets/...:210)
+    Act cb;
+    if (tc) { cb.C = 192; cb.s.hi = (uint16_t*)cbuf; cb.s.lo = lo ? (uint16_t*)(cbuf + align_up(pix * 192 * 2, 1024)) : nullptr; }
+    else { cb.C = 149; cb.f = (float*)cbuf; }
+    if (tc) {
+        uint16_t* hi = cb.s.hi; uint16_t* lop = cb.s.lo; const size_t bytes = (size_t)pix * 192 * 2;
+        pl->steps.push_back([=](const Ext&, cudaStream_t s) {   // zero the padding channels (and everything else) once per call
+            H3D_CUDA(cudaMemsetAsync(hi, 0, bytes, s));
+            if (lop) H3D_CUDA(cudaMemsetAsync(lop, 0, bytes, s));
+            return H3D_OK;
+        });
+        pl->launches.push_back(0);
+    }
+    if ((rc = build_trunk(ctx, pl.get(), "PoseNet2D", kPoseTrunk, 15, B, Hc, Wc, slot0, slot1, se, &last, &h, &w, &cb, tc ? 0 : 21))) return rc;
+    float** S = ctx->lay.s;
+    const Half16 half = half_of(ctx->precision);
+    auto head = [&](const char* n6, const char* n7, int cin6, float* sm_out, bool feed_back, const Act& in6) -> int {
+        // 1x1 conv (cin6 -> 512 or 128, leaky) then 1x1 conv (-> 21, linear); score-map also fed back into the concat buffer
+        LayerSpec l6{n6, 1, 1, 128, cin6, 1}, l7{n7, 1, 1, cin6, 21, 0};
+        int rc2;
+        if (tc) rc2 = add_tc(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.s, in6.C, 128, {}, Split(), 0, 0, f512, cin6, 0);
+        else rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.f, in6.C, in6.f == cb.f ? 21 : 0, f512, cin6, 0, Split(), 0, 0);
+        if (rc2) return rc2;
+        if (tc) rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l7, B, h, w, f512, cin6, 0, sm_out, 21, 0, feed_back ? cb.s : Split(), 192, 128);
+        else rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l7, B, h, w, f512, cin6, 0, sm_out, 21, 0, Split(), 0, 0);
+        if (rc2) return rc2;
+        if (!tc && feed_back) {
+            float* dst = cb.f;
+            pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_copy_channels(sm_out, dst, pix, 21, 149, 0, s); });
+            pl->launches.push_back(1);
+        }
+        return H3D_OK;
+    };
+    if ((rc = head("conv5_1", "conv5_2", 512, S[0], true, cb))) return rc;
+    std::vector<int> perm(192, -1);
+    for (int j = 0; j < 128; ++j) perm[j] = 21 + j;
+    for (int j = 0; j < 21; ++j) perm[128 + j] = j;
+    char* slots[2] = {slot0, slot1};
+    for (int u = 6; u <= 7; ++u) {
+        char nm[7][16];
+        for (int i = 0; i < 7; ++i) snprintf(nm[i], 16, "conv%d_%d", u, i + 1);
+        Act in = cb;
+        for (int i = 0; i < 5; ++i) {
+            LayerSpec l{nm[i], 7, 1, i == 0 ? 149 : 128, 128, 1};
+            Act out = slot_view(slots[i & 1], pix * 128, 128, tc, lo);
+            if (tc) rc = add_tc(ctx, pl.get(), "PoseNet2D", l, B, h, w, in.s, in.C, i == 0 ? 192 : 128, i == 0 ? perm : std::vector<int>(), out.s, 128, 0, nullptr, 0, 0);
+            else rc = add_direct(ctx, pl.get(), "PoseNet2D", l, B, h, w, in.f, in.C, 0, out.f, 128, 0, Split(), 0, 0);
+            if (rc) return rc;
+            in = out;
+        }
+        if ((rc = head(nm[5], nm[6], 128, S[u - 5], u == 6, in))) return rc;
+    }
+    (void)half;
+    ctx->pose = std::move(pl);
+    return H3D_OK;
+}
+
+static int ensure_vp_heads(h3d_ctx* ctx) {
+    if (ctx->vp_head_w) return H3D_OK;
+    const char* nm[3] = {"ViewpointNet/fc_vp_ux", "ViewpointNet/fc_vp_uy", "ViewpointNet/fc_vp_uz"};
+    std::vector<float> w(128 * 3), b(3);
+    for (int j = 0; j < 3; ++j) {
+        auto wi = ctx->host_w.find(std::string(nm[j]) + "/weights"), bi = ctx->host_w.find(std::string(nm[j]) + "/biases");
+        if (wi == ctx->host_w.end() || bi == ctx->host_w.end()) { set_error("weights %s not loaded", nm[j]); return H3D_EWEIGHTS; }
+        for (int i = 0; i < 128; ++i) w[i * 3 + j] = wi->second.data[i];
+        b[j] = bi->second.data[0];
+    }
+    H3D_CUDA(cudaMalloc(&ctx->vp_head_w, w.size() * 4)); H3D_CUDA(cudaMalloc(&ctx->vp_head_b, b.size() * 4));
+    H3D_CUDA(cudaMemcpy(ctx->vp_head_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
+    H3D_CUDA(cudaMemcpy(ctx->vp_head_b, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    return H3D_OK;
+}
+
+static int add_fc(h3d_ctx* ctx, StagePlan* pl, const std::string& name, const float* x, float* y, int B, int in_f, int out_f, int leaky) {
+    const float *w, *b;
+    int rc;
+    if ((rc = dev_weight(ctx, name + "/weights", &w))) return rc;
+    if ((rc = dev_weight(ctx, name + "/biases", &b))) return rc;
+    pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_fc(x, w, b, y, B, in_f, out_f, leaky, in_f, s); });
+    pl->launches.push_back(1);
+    pl->flops += 2ll * B * in_f * out_f;
+    tag(pl, KIND_FC, 2ll * B * in_f * out_f);
+    return H3D_OK;
+}
+
+static int build_lifting(h3d_ctx* ctx, int B, int variant) {
+    auto pl = std::make_unique<StagePlan>();
+    pl->B = B; pl->variant = variant;
+    Arena a; a.base = ctx->ws + ctx->lay.lift_off;
+    float* bufA = a.alloc<float>((int64_t)B * 32 * 32 * 64);
+    float* bufB = a.alloc<float>((int64_t)B * 32 * 32 * 64);
+    float* xcat = a.alloc<float>((int64_t)B * 4100);
+    float* t1 = a.alloc<float>((int64_t)B * 512);
+    float* t2 = a.alloc<float>((int64_t)B * 512);
+    float* t3 = a.alloc<float>((int64_t)B * 64);
+    float* can = a.alloc<float>((int64_t)B * 63);
+    float* uxyz = a.alloc<float>((int64_t)B * 4);
+    int rc;
+    auto pyramid = [&](const std::string& scope, const LayerSpec* L) -> int {
+        int h = 32, w = 32;
+        float* bufs[2] = {bufA, bufB};
+        const float* in = nullptr; int cin_total = 21;
+        for (int i = 0; i < 6; ++i) {
+            float* out = bufs[i & 1];
+            int rc2 = add_direct(ctx, pl.get(), scope, L[i], B, h, w, in, cin_total, 0, out, L[i].cout, 0, Split(), 0, 0);
+            if (rc2) return rc2;
+            h = ceil_div(h, L[i].stride); w = ceil_div(w, L[i].stride);
+            in = out; cin_total = L[i].cout;
+        }
+        return H3D_OK;
+    };
+    // PosePrior (nets/ColorHandPose3DNetwork.py:249-272; bottleneck nets/PosePriorNetwork.py:113-116)
+    if ((rc = pyramid("PosePrior", kPosePrior))) return rc;
+    pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(bufB, e.hand_side, xcat, B, 2048, s); });
+    pl->launches.push_back(1);
+    if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_rel0", xcat, t1, B, 2050, 512, 1))) return rc;
+    if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_rel1", t1, t2, B, 512, 512, 1))) return rc;
+    const bool bott = variant == H3D_VARIANT_BOTTLENECK;
+    auto xyz = ctx->host_w.find("PosePrior/fc_xyz/weights");
+    if (xyz == ctx->host_w.end()) { set_error("weights PosePrior/fc_xyz not loaded"); return H3D_EWEIGHTS; }
+    const int xyz_in = (int)xyz->second.shape[0];
+    if (bott) {
+        H3D_REQUIRE(xyz_in == 30, "bottleneck variant needs PosePrior/fc_xyz/weights of shape [30,63]");
+        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_bottleneck", t2, t3, B, 512, 30, 0))) return rc;
+        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", t3, can, B, 30, 63, 0))) return rc;
+    } else {
+        H3D_REQUIRE(xyz_in == 512, "PosePrior/fc_xyz/weights must have shape [512,63] for this variant");
+        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", t2, can, B, 512, 63, 0))) return rc;
+    }
+    if (variant == H3D_VARIANT_PROPOSED) {
+        // ViewpointNet (nets/ColorHandPose3DNetwork.py:274-309) + Rodrigues / flip / rotate (:239-247,311-334)
+        if ((rc = ensure_vp_heads(ctx))) return rc;
+        if ((rc = pyramid("ViewpointNet", kViewpoint))) return rc;
+        pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(bufB, e.hand_side, xcat, B, 4096, s); });
+        pl->launches.push_back(1);
+        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp0", xcat, t1, B, 4098, 256, 1))) return rc;
+        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp1", t1, t2, B, 256, 128, 1))) return rc;
+        const float* hw = ctx->vp_head_w; const float* hb = ctx->vp_head_b;
+        pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_fc(t2, hw, hb, uxyz, B, 128, 3, 0, 128, s); });
+        pl->launches.push_back(1);
+        pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
+            if (e.out2) H3D_CUDA(cudaMemcpyAsync(e.out2, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
+            return launch_rotate_canonical(can, uxyz, e.hand_side, B, e.out3, e.out, s);
+        });
+        pl->launches.push_back(1);
+    } else {
+        pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
+            H3D_CUDA(cudaMemcpyAsync(e.out, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
+            if (e.out2) H3D_CUDA(cudaMemcpyAsync(e.out2, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
+            return H3D_OK;
+        });
+        pl->launches.push_back(0);
+    }
+    ctx->lift = std::move(pl);
+    return H3D_OK;
+}
+
+static int run_plan(h3d_ctx* ctx, StagePlan* pl, const Ext& e, cudaStream_t s) {
+    for (size_t i = 0; i < pl->steps.size(); ++i) {
+        h3d_ctx::ProfRec pr;
+        const bool prof = ctx->profiling && pl->launches[i] > 0;
+        if (prof) {
+            H3D_CUDA(cudaEventCreate(&pr.a)); H3D_CUDA(cudaEventCreate(&pr.b));
+            pr.kind = i < pl->kinds.size() ? pl->kinds[i] : KIND_OTHER;
+            pr.flops = i < pl->step_flops.size() ? pl->step_flops[i] : 0;
+            H3D_CUDA(cudaEventRecord(pr.a, s));
+        }
+        int rc = pl->steps[i](e, s);
+        if (rc) return rc;
+        if (prof) { H3D_CUDA(cudaEventRecord(pr.b, s)); ctx->prof.push_back(pr); }
+        ctx->launches += pl->launches[i];
+    }
+    return H3D_OK;
+}
+
+static int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s): hand3d_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return H3D_ENODEVICE;
+    }
+    return H3D_OK;
+}
+
+}  // namespace h3d
+
+// =============================================================================================== C ABI
+extern "C" {
+
+const char* h3d_last_error(void) { return g_err; }
+int h3d_version(void) { return 100; }
+
+int h3d_device_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return p.major == 10 ? 1 : 0;
+}
+
+int h3d_create(h3d_ctx** out, int device) {
+    H3D_REQUIRE(out != nullptr, "h3d_create: out is NULL");
+    int rc = check_device();
+    if (rc) return rc;
+    cudaDeviceProp p;
+    H3D_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) {
+        set_error("device %d (%s) has compute capability %d.%d; hand3d_b200 is built for sm_100a only", device, p.name, p.major, p.minor);
+        return H3D_ENODEVICE;
+    }
+    H3D_CUDA(cudaSetDevice(device));
+    h3d_ctx* c = new h3d_ctx();
+    c->device = device;
+    memset(&c->lay, 0, sizeof(c->lay));
+    *out = c;
+    return H3D_OK;
+}
+
+int h3d_destroy(h3d_ctx* ctx) {
+    if (!ctx) return H3D_OK;
+    ctx->drop_plans();
+    for (auto& kv : ctx->dev_w) cudaFree(kv.second);
+    for (auto& kv : ctx->packed) free_packed(kv.second);
+    if (ctx->vp_head_w) cudaFree(ctx->vp_head_w);
+    if (ctx->vp_head_b) cudaFree(ctx->vp_head_b);
+    delete ctx;
+    return H3D_OK;
+}
+
+int h3d_set_precision(h3d_ctx* ctx, int precision) {
+    H3D_REQUIRE(ctx && precision >= H3D_PREC_FP32_FFMA && precision <= H3D_PREC_BF16, "h3d_set_precision: bad argument");
+    if (precision != ctx->precision) { ctx->precision = precision; ctx->drop_plans(); }
+    return H3D_OK;
+}
+int h3d_get_precision(const h3d_ctx* ctx) { return ctx ? ctx->precision : H3D_EINVAL; }
+int64_t h3d_launch_count(const h3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int h3d_profile_begin(h3d_ctx* ctx) {
+    H3D_REQUIRE(ctx != nullptr, "h3d_profile_begin: ctx is NULL");
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    ctx->prof.clear();
+    ctx->profiling = true;
+    return H3D_OK;
+}
+
+int h3d_profile_end(h3d_ctx* ctx, double* ms_by_kind, int64_t* flops_by_kind, int64_t* launches_by_kind) {
+    H3D_REQUIRE(ctx && ms_by_kind && flops_by_kind && launches_by_kind, "h3d_profile_end: bad argument");
+    ctx->profiling = false;
+    for (int k = 0; k < KIND_COUNT; ++k) { ms_by_kind[k] = 0; flops_by_kind[k] = 0; launches_by_kind[k] = 0; }
+    H3D_CUDA(cudaDeviceSynchronize());
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        H3D_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_by_kind[r.kind] += ms; flops_by_kind[r.kind] += r.flops; launches_by_kind[r.kind] += 1;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    return H3D_OK;
+}
+
+int h3d_load_weight(h3d_ctx* ctx, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+    H3D_REQUIRE(ctx && name && host_data && shape && ndim >= 1 && ndim <= 4, "h3d_load_weight: bad argument");
+    auto it = known_vars().find(name);
+    if (it == known_vars().end()) { set_error("Unknown variable name: %s", name); return H3D_EWEIGHTS; }
+    VarShape vs = it->second;
+    const std::string nm(name);
+    bool ok = vs.nd == ndim;
+    for (int i = 0; ok && i < ndim; ++i) ok = vs.s[i] == shape[i];
+    if (!ok && nm == "PosePrior/fc_xyz/weights" && ndim == 2 && shape[0] == 30 && shape[1] == 63) ok = true;   // bottleneck variant
+    if (!ok) { set_error("Shape mismatch for variable %s", name); return H3D_EWEIGHTS; }
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    if (nm.find("/fc_") != std::string::npos) {   // tf.check_numerics (utils/general.py:122,127)
+        for (int64_t i = 0; i < n; ++i)
+            if (!std::isfinite(host_data[i])) { set_error("check_numerics: %s contains NaN/Inf", name); return H3D_EWEIGHTS; }
+    }
+    HostTensor t;
+    t.data.assign(host_data, host_data + n);
+    t.shape.assign(shape, shape + ndim);
+    float* d = nullptr;
+    H3D_CUDA(cudaSetDevice(ctx->device));
+    H3D_CUDA(cudaMalloc(&d, (size_t)n * 4));
+    H3D_CUDA(cudaMemcpy(d, host_data, (size_t)n * 4, cudaMemcpyHostToDevice));
+    auto old = ctx->dev_w.find(nm);
+    if (old != ctx->dev_w.end()) cudaFree(old->second);
+    ctx->dev_w[nm] = d;
+    ctx->host_w[nm] = std::move(t);
+    // invalidate everything derived from this variable
+    const std::string layer = nm.substr(0, nm.rfind('/'));
+    for (auto pit = ctx->packed.begin(); pit != ctx->packed.end();) {
+        if (pit->first.compare(0, layer.size() + 1, layer + "|") == 0) { free_packed(pit->second); pit = ctx->packed.erase(pit); }
+        else ++pit;
+    }
+    if (nm.find("fc_vp_u") != std::string::npos && ctx->vp_head_w) {
+        cudaFree(ctx->vp_head_w); cudaFree(ctx->vp_head_b); ctx->vp_head_w = ctx->vp_head_b = nullptr;
+    }
+    ctx->drop_plans();
+    return H3D_OK;
+}
+
+int h3d_scope_ready(const h3d_ctx* ctx, const char* scope) {
+    if (!ctx || !scope) return 0;
+    const std::string pre = std::string(scope) + "/";
+    int found = 0;
+    for (auto& kv : known_vars()) {
+        if (kv.first.compare(0, pre.size(), pre) != 0) continue;
+        if (kv.first.find("fc_bottleneck") != std::string::npos) continue;
+        ++found;
+        if (!ctx->host_w.count(kv.first)) return 0;
+    }
+    return found > 0;
+}
+
+int64_t h3d_workspace_bytes(const h3d_ctx* ctx, int B, int H, int W) {
+    if (!ctx || B <= 0 || H <= 0 || W <= 0) return H3D_EINVAL;
+    h3d_ctx::Layout L;
+    layout(L, nullptr, B, H, W);
+    return L.total;
+}
+
+int h3d_set_workspace(h3d_ctx* ctx, void* dev_ptr, int64_t bytes) {
+    H3D_REQUIRE(ctx != nullptr, "h3d_set_workspace: ctx is NULL");
+    H3D_REQUIRE(((uintptr_t)dev_ptr & 1023) == 0, "h3d_set_workspace: pointer must be 1024-byte aligned");
+    ctx->drop_plans();
+    memset(&ctx->lay, 0, sizeof(ctx->lay));
+    ctx->ws = (char*)dev_ptr; ctx->ws_bytes = bytes;
+    return H3D_OK;
+}
+
+int h3d_handsegnet_forward(h3d_ctx* ctx, const float* image, int B, int H, int W, float* logits, void* stream) {
+    H3D_REQUIRE(ctx && image && logits && B > 0, "h3d_handsegnet_forward: bad argument");
+    int rc;
+    if ((rc = ensure_layout(ctx, std::max(B, ctx->lay.B), std::max(H, ctx->lay.H), std::max(W, ctx->lay.W)))) return rc;
+    if (!ctx->seg || ctx->seg->B != B || ctx->seg->H != H || ctx->seg->W != W)
+        if ((rc = build_handsegnet(ctx, B, H, W))) return rc;
+    Ext e; e.in = image; e.out = logits;
+    return run_plan(ctx, ctx->seg.get(), e, (cudaStream_t)stream);
+}
+
+int h3d_posenet_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, int Wc, float* s0, float* s1, float* s2, void* stream) {
+    H3D_REQUIRE(ctx && image_crop && B > 0, "h3d_posenet_forward: bad argument");
+    int rc;
+    if ((rc = ensure_layout(ctx, std::max(B, ctx->lay.B), std::max(Hc, ctx->lay.H), std::max(Wc, ctx->lay.W)))) return rc;
+    if (!ctx->pose || ctx->pose->B != B || ctx->pose->H != Hc || ctx->pose->W != Wc)
+        if ((rc = build_posenet(ctx, B, Hc, Wc))) return rc;
+    Ext e; e.in = image_crop;
+    if ((rc = run_plan(ctx, ctx->pose.get(), e, (cudaStream_t)stream))) return rc;
+    float* outs[3] = {s0, s1, s2};
+    const size_t bytes = (size_t)B * (Hc / 8) * (Wc / 8) * 21 * 4;
+    for (int i = 0; i < 3; ++i)
+        if (outs[i]) H3D_CUDA(cudaMemcpyAsync(outs[i], ctx->lay.s[i], bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return H3D_OK;
+}
+
+int h3d_lifting_forward(h3d_ctx* ctx, const float* scoremap32, const float* hand_side, int B, int variant,
+                        float* coord_xyz_rel_normed, float* coord_can, float* rot_mat, void* stream) {
+    H3D_REQUIRE(ctx && scoremap32 && hand_side && coord_xyz_rel_normed && B > 0, "h3d_lifting_forward: bad argument");
+    H3D_REQUIRE(variant >= H3D_VARIANT_DIRECT && variant <= H3D_VARIANT_PROPOSED, "h3d_lifting_forward: unknown variant");
+    int rc;
+    if ((rc = ensure_layout(ctx, std::max(B, ctx->lay.B), std::max(8, ctx->lay.H), std::max(8, ctx->lay.W)))) return rc;
+    if (!ctx->lift || ctx->lift->B != B || ctx->lift->variant != variant)
+        if ((rc = build_lifting(ctx, B, variant))) return rc;
+    Ext e; e.in = scoremap32; e.hand_side = hand_side; e.out = coord_xyz_rel_normed; e.out2 = coord_can; e.out3 = rot_mat;
+    return run_plan(ctx, ctx->lift.get(), e, (cudaStream_t)stream);
+}
+
+int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_side, int B, int H, int W, int with_pose3d,
+                         const float* force_center, const float* force_scale, float* hand_scoremap, float* image_crop,
+                         float* scale_crop, float* center, float* keypoints_scoremap, float* keypoint_coord3d,
+                         int32_t* keypoints_uv, uint8_t* hand_mask, void* stream) {
+    H3D_REQUIRE(ctx && image && B > 0, "h3d_pipeline_forward: bad argument");
+    H3D_REQUIRE(!with_pose3d || (hand_side && keypoint_coord3d), "h3d_pipeline_forward: hand_side / keypoint_coord3d required with pose3d");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = ensure_layout(ctx, B, H, W))) return rc;
+    h3d_ctx::Layout& L = ctx->lay;
+    float* seg = hand_scoremap ? hand_scoremap : L.hand_scoremap;
+    float* crop = image_crop ? image_crop : L.image_crop;
+    float* kps = keypoints_scoremap ? keypoints_scoremap : L.kp_scoremap;
+    float* cen = center ? center : L.center;
+    float* scl = scale_crop ? scale_crop : L.scale;
+    // HandSegNet (nets/...:78-79)
+    if ((rc = h3d_handsegnet_forward(ctx, image, B, H, W, seg, stream))) return rc;
+    // single_obj_scoremap + calc_center_bb + scale (nets/...:82-85)
+    int nl = 0;
+    if ((rc = launch_seg_postprocess(seg, B, H, W, L.seg_scratch, hand_mask, nullptr, cen, L.crop_size, scl, s, &nl))) return rc;
+    ctx->launches += nl;
+    if (force_center) H3D_CUDA(cudaMemcpyAsync(cen, force_center, (size_t)B * 8, cudaMemcpyDeviceToDevice, s));
+    if (force_scale) H3D_CUDA(cudaMemcpyAsync(scl, force_scale, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+    // crop_image_from_xy (nets/...:86)
+    if ((rc = launch_crop_image(image, cen, scl, crop, B, H, W, 3, 256, s))) return rc;
+    ctx->launches += 1;
+    // PoseNet2D (nets/...:89-90)
+    if ((rc = h3d_posenet_forward(ctx, crop, B, 256, 256, nullptr, nullptr, nullptr, stream))) return rc;
+    // PosePrior + ViewpointNet on the 32x32 map (nets/...:93)
+    if (with_pose3d)
+        if ((rc = h3d_lifting_forward(ctx, L.s[2], hand_side, B, H3D_VARIANT_PROPOSED, keypoint_coord3d, nullptr, nullptr, stream))) return rc;
+    // x8 up-sampling (nets/...:96-97) and detect_keypoints (utils/general.py:331-344)
+    if ((rc = launch_resize_bilinear_tf1(L.s[2], kps, B, 32, 32, 21, 256, 256, s))) return rc;
+    ctx->launches += 1;
+    if (keypoints_uv) {
+        nl = 0;
+        if ((rc = launch_detect_keypoints(kps, B, 256, 256, 21, L.argmax_scratch, keypoints_uv, s, &nl))) return rc;
+        ctx->launches += nl;
+    }
+    return H3D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- operators
+#define H3D_OP_PROLOGUE(ctx)                              \
+    H3D_REQUIRE((ctx) != nullptr, "ctx is NULL");         \
+    cudaStream_t s = (cudaStream_t)stream;
+
+int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const float* bias, float* y, int B, int H, int W, int Cin,
+                   int Cout, int ksize, int stride, int leaky, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    DirectConvArgs a;
+    a.x = x; a.Cin_total = Cin; a.cin_off = 0; a.w = w_hwio; a.bias = bias; a.y = y; a.Cout_total = Cout; a.cout_off = 0;
+    a.ys = Split(); a.Cs_total = 0; a.cs_off = 0; a.half = Half16::BF16;
+    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = ksize; a.stride = stride; a.leaky = leaky;
+    int rc = launch_conv_direct(a, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+
+int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y, int B, int H, int W,
+                  int Cin, int Cout, int ksize, int leaky, int precision, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(precision >= H3D_PREC_BF16X3 && precision <= H3D_PREC_BF16, "h3d_conv2d_tc: precision must be a tensor-core mode");
+    const Half16 half = half_of(precision);
+    const int passes = passes_of(precision);
+    const int Cin_pad = (int)align_up(Cin, 64), Cout_pad = (int)align_up(Cout, 64);
+    PackedW pw;
+    int rc = pack_conv_weights(host_w_hwio, host_bias, ksize, Cin, Cout, Cin_pad, Cout_pad, {}, half, passes == 3, &pw);
+    if (rc) return rc;
+    const int64_t rows = (int64_t)B * H * W;
+    Split xs, ys;
+    TcConvPlan* tp = nullptr;
+    auto cleanup = [&]() {
+        if (xs.hi) cudaFree(xs.hi); if (xs.lo) cudaFree(xs.lo); if (ys.hi) cudaFree(ys.hi); if (ys.lo) cudaFree(ys.lo);
+        if (tp) tc_conv_plan_destroy(tp);
+        free_packed(pw);
+    };
+    auto fail = [&](int code) { cleanup(); return code; };
+    if (cudaMalloc(&xs.hi, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.hi, rows * Cout_pad * 2) != cudaSuccess ||
+        (passes == 3 && (cudaMalloc(&xs.lo, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.lo, rows * Cout_pad * 2) != cudaSuccess))) {
+        set_error("h3d_conv2d_tc: out of device memory");
+        return fail(H3D_ECUDA);
+    }
+    if ((rc = launch_f32_to_split(x, xs, rows, Cin, Cin_pad, half, s))) return fail(rc);
+    TcConvDesc d;
+    d.x = xs; d.Cin_total = Cin_pad; d.Cin_pad = Cin_pad; d.w = pw.w; d.bias = pw.bias; d.Cout = Cout; d.Cout_pad = Cout_pad;
+    d.y = ys; d.Cy_total = Cout_pad; d.cy_off = 0; d.yf = nullptr; d.Cyf_total = 0; d.cyf_off = 0;
+    d.B = B; d.H = H; d.W = W; d.k = ksize; d.leaky = leaky; d.passes = passes; d.half = half;
+    tp = tc_conv_plan_create(d);
+    if (!tp) return fail(H3D_ECUDA);
+    if ((rc = tc_conv_launch(tp, s))) return fail(rc);
+    if ((rc = launch_split_to_f32(ys, y, rows, Cout, Cout_pad, half, s))) return fail(rc);
+    ctx->launches += 3;
+    cudaError_t e = cudaStreamSynchronize(s);
+    cleanup();
+    if (e != cudaSuccess) return cuda_fail(e, "h3d_conv2d_tc sync", __FILE__, __LINE__);
+    return H3D_OK;
+}
+
+int h3d_maxpool2x2_f32(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    int rc = launch_maxpool_f32(x, y, B, H, W, C, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_fully_connected_f32(h3d_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int in_features,
+                            int out_features, int leaky, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    int rc = launch_fc(x, w, bias, y, B, in_features, out_features, leaky, in_features, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_resize_bilinear_tf1(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, int out_h, int out_w, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    int rc = launch_resize_bilinear_tf1(x, y, B, H, W, C, out_h, out_w, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_avgpool8(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    int rc = launch_avgpool8(x, y, B, H, W, C, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_seg_postprocess(h3d_ctx* ctx, const float* logits, int B, int H, int W, uint8_t* hand_mask, int32_t* max_loc, float* center,
+                        float* crop_size, float* scale_crop, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(logits && center && scale_crop, "h3d_seg_postprocess: logits, center and scale_crop are required");
+    void* scratch = nullptr;
+    H3D_CUDA(cudaMalloc(&scratch, seg_scratch_bytes(B, H, W)));
+    int nl = 0;
+    int rc = launch_seg_postprocess(logits, B, H, W, scratch, hand_mask, max_loc, center, crop_size, scale_crop, s, &nl);
+    ctx->launches += nl;
+    cudaStreamSynchronize(s);
+    cudaFree(scratch);
+    return rc;
+}
+int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float* center, const float* scale, float* image_crop, int B,
+                           int H, int W, int C, int crop_size, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    int rc = launch_crop_image(image, center, scale, image_crop, B, H, W, C, crop_size, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int C, int32_t* keypoints_uv, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    void* scratch = nullptr;
+    H3D_CUDA(cudaMalloc(&scratch, argmax_scratch_bytes(B, C)));
+    int nl = 0;
+    int rc = launch_detect_keypoints(scoremaps, B, H, W, C, scratch, keypoints_uv, s, &nl);
+    ctx->launches += nl;
+    cudaStreamSynchronize(s);
+    cudaFree(scratch);
+    return rc;
+}
+int h3d_rotate_canonical(h3d_ctx* ctx, const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot_mat,
+                         float* coord_out, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    int rc = launch_rotate_canonical(coord_can, uxyz, hand_side, B, rot_mat, coord_out, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+
+}  // extern "C"

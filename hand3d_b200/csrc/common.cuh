@@ -1,0 +1,122 @@
+// Shared declarations for the hand3d_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <algorithm>
+#include <cmath>
+#include <string>
+
+#include "../../include/hand3d_b200.h"
+
+namespace h3d {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define H3D_CUDA(expr)                                                     \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) return h3d::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define H3D_CHECK_LAUNCH() H3D_CUDA(cudaGetLastError())
+
+#define H3D_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            h3d::set_error(__VA_ARGS__);       \
+            return H3D_EINVAL;                 \
+        }                                      \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t align_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+constexpr float kNegSlope = 0.01f;  // utils/general.py:28
+
+// Activation tensors on the tensor-core path are stored as two 16-bit planes (hi, lo) with
+// x ~= hi + lo ("split" format); lo == nullptr in single-pass modes.
+struct Split {
+    uint16_t* hi = nullptr;
+    uint16_t* lo = nullptr;
+};
+
+enum class Half16 : int { BF16 = 0, FP16 = 1 };
+
+// ---------------------------------------------------------------- launch counter
+struct LaunchCounter {
+    int64_t n = 0;
+};
+
+// ---------------------------------------------------------------- kernels (elementwise.cu)
+int launch_resize_bilinear_tf1(const float* x, float* y, int B, int H, int W, int C, int oh, int ow, cudaStream_t s);
+int launch_maxpool_f32(const float* x, float* y, int B, int H, int W, int C, cudaStream_t s);
+int launch_maxpool_split(Split x, Split y, int B, int H, int W, int C, Half16 t, cudaStream_t s);
+int launch_avgpool8(const float* x, float* y, int B, int H, int W, int C, cudaStream_t s);
+int launch_f32_to_split(const float* x, Split y, int64_t rows, int C, int Cpad, Half16 t, cudaStream_t s);
+int launch_split_to_f32(Split x, float* y, int64_t rows, int C, int Cpad, Half16 t, cudaStream_t s);
+// seg post-process: scratch must hold seg_scratch_bytes(B,H,W) bytes (zeroed by the launcher).
+int64_t seg_scratch_bytes(int B, int H, int W);
+int launch_seg_postprocess(const float* logits, int B, int H, int W, void* scratch, uint8_t* hand_mask,
+                           int32_t* max_loc, float* center, float* crop_size, float* scale_crop, cudaStream_t s,
+                           int* n_launch);
+int launch_crop_image(const float* image, const float* center, const float* scale, float* out, int B, int H, int W,
+                      int C, int crop, cudaStream_t s);
+int64_t argmax_scratch_bytes(int B, int C);
+int launch_detect_keypoints(const float* sm, int B, int H, int W, int C, void* scratch, int32_t* uv, cudaStream_t s,
+                            int* n_launch);
+// dst[r, dst_off + c] = src[r, c] for c < C (fp32 channel copy into a wider NHWC tensor)
+int launch_copy_channels(const float* src, float* dst, int64_t rows, int C, int dst_total, int dst_off, cudaStream_t s);
+int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot,
+                            float* out, cudaStream_t s);
+
+// ---------------------------------------------------------------- kernels (conv_direct.cu)
+struct DirectConvArgs {
+    const float* x;       // [B,H,W,Cin_total] fp32, channels [cin_off, cin_off+Cin) are read
+    int Cin_total, cin_off;
+    const float* w;       // HWIO [k,k,Cin,Cout]
+    const float* bias;    // [Cout]
+    float* y;             // fp32 out (may be null) [B,Ho,Wo,Cout_total] at channel offset cout_off
+    int Cout_total, cout_off;
+    Split ys;             // optional split output [B,Ho,Wo,Cs_total] at channel offset cs_off
+    int Cs_total, cs_off;
+    Half16 half;
+    int B, H, W, Cin, Cout, k, stride, leaky;
+};
+int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s);
+int launch_fc(const float* x, const float* w, const float* bias, float* y, int B, int in_f, int out_f, int leaky,
+              int x_stride, cudaStream_t s);
+// gathers [conv_feat(b, :feat) , hand_side(b, :2)] -> xcat [B, feat+2]
+int launch_concat_handside(const float* feat, const float* hand_side, float* out, int B, int feat_n, cudaStream_t s);
+
+// ---------------------------------------------------------------- kernels (conv_tc.cu)
+struct TcConvPlan;  // opaque: tensor maps + launch geometry of one tensor-core conv layer
+struct TcConvDesc {
+    // input activations (split planes) [B,H,W,Cin_total]; channels [0,Cin_pad) are read (Cin_pad % 64 == 0)
+    Split x;
+    int Cin_total, Cin_pad;
+    // packed weights: [Cout_pad][k*k*Cin_pad] K-major 16-bit planes
+    Split w;
+    const float* bias;  // [Cout_pad] fp32
+    int Cout, Cout_pad;
+    // outputs: split planes at channel offset (16-byte aligned) and/or fp32
+    Split y;
+    int Cy_total, cy_off;
+    float* yf;
+    int Cyf_total, cyf_off;
+    int B, H, W, k, leaky;
+    int passes;  // 1 or 3
+    Half16 half;
+};
+TcConvPlan* tc_conv_plan_create(const TcConvDesc& d);   // nullptr on failure (h3d_last_error set)
+void tc_conv_plan_destroy(TcConvPlan* p);
+int tc_conv_launch(const TcConvPlan* p, cudaStream_t s);
+int64_t tc_conv_flops(const TcConvPlan* p);
+int tc_num_sms();
+
+}  // namespace h3d

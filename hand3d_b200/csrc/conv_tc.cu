@@ -1,0 +1,479 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (tf.nn.conv2d 'SAME' stride 1 + bias + leaky ReLU,
+// utils/general.py:36-59), im2col-free:
+//
+//   D[M = 128 output pixels, N = BN output channels] += A[M, K] * B[N, K]^T,   K = kh*kw*Cin
+//
+// * A is never materialised.  For filter tap (kh, kw) and 64-channel chunk c the A tile is the 4-D TMA
+//   box {64 ch, TW, TH, TB} of the NHWC activation tensor at (c, w0+kw-pad, h0+kh-pad, b0): TMA's
+//   out-of-bounds zero fill (negative / past-the-end coordinates) implements the 'SAME' zero padding
+//   and never leaks pixels across images.  The box lands in shared memory as 128 rows x 128 bytes with
+//   the 128-byte swizzle, which is exactly the canonical K-major SWIZZLE_128B UMMA operand layout.
+// * B tiles are 2-D TMA boxes {64, BN} of the pre-packed K-major weights [Cout][kh][kw][Cin].
+// * fp32 parity on 16-bit tensor cores: activations and weights are stored as two 16-bit planes
+//   x = hi + lo; each K block issues hi*hi + hi*lo + lo*hi (3 passes) into the same fp32 TMEM
+//   accumulator (dropped lo*lo term ~2^-18 relative for bf16, ~2^-24 for fp16).  PASSES == 1 is the
+//   plain 16-bit path (BASELINE config 5).
+// * Warp-specialised persistent CTAs: warp 4 = TMA producer, warp 5 = MMA issuer (+ TMEM alloc),
+//   warps 0-3 = epilogue (tcgen05.ld -> bias -> leaky ReLU -> hi/lo split or fp32 -> global).  Two TMEM
+//   accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+
+namespace h3d {
+
+namespace {
+
+constexpr int BM = 128;           // UMMA M (pixels per tile)
+constexpr int BK = 64;            // K elements per stage (= 128 bytes = one swizzle span)
+constexpr int UMMA_K = 16;
+constexpr int kNumEpilogueWarps = 4;
+constexpr int kThreads = 32 * (kNumEpilogueWarps + 2);
+constexpr int kSmemBudget = 227 * 1024 - 2048;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+__host__ __device__ constexpr int stage_bytes(int BN, int PASSES) { return (PASSES == 3 ? 2 : 1) * (A_TILE_BYTES + BN * BK * 2); }
+__host__ __device__ constexpr int num_stages(int BN, int PASSES) {
+    return kSmemBudget / stage_bytes(BN, PASSES) > 8 ? 8 : kSmemBudget / stage_bytes(BN, PASSES);
+}
+__host__ __device__ constexpr int tmem_cols(int BN) { return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512; }
+
+struct TcParams {
+    const float* bias;
+    uint16_t* y_hi; uint16_t* y_lo; int Cy_total, cy_off;
+    float* yf; int Cyf_total, cyf_off;
+    int B, H, W, k, pad, cin_chunks;
+    int TW, TH, TB, tiles_w, tiles_h, n_tiles, num_tiles;
+    int leaky;
+    int* err_flag;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {   // ~2 s
+            if (err_flag) atomicExch(err_flag, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version = 1, layout = SWIZZLE_128B (2).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format f32 (bit 4), a/b format (bits 7, 10:
+// 0 = f16, 1 = bf16), K-major A and B (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int N, bool fp16) {
+    return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_hi2(float a, float b) {
+    if (FP16) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h);
+}
+template <bool FP16>
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+    if (FP16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int BN, int PASSES, bool FP16>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+    constexpr int STAGES = num_stages(BN, PASSES);
+    constexpr int STAGE_BYTES = stage_bytes(BN, PASSES);
+    constexpr int B_TILE_BYTES = BN * BK * 2;
+    constexpr uint32_t IDESC = make_idesc(BN, FP16);
+    static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = p.k * p.k * p.cin_chunks;
+
+    if (warp == 4 && lane == 0) {
+        prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w_hi);
+        if (PASSES == 3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kNumEpilogueWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * p.TW - p.pad, h0 = th * p.TH - p.pad, b0 = tb * p.TB, n0 = nt * BN;
+                int kcol = 0;
+                for (int kh = 0; kh < p.k; ++kh) {
+                    for (int kw = 0; kw < p.k; ++kw) {
+                        for (int cc = 0; cc < p.cin_chunks; ++cc, kcol += BK) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+                            uint8_t* st = smem + stage * STAGE_BYTES;
+                            mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                            tma_load_4d(&map_x_hi, st, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                            tma_load_2d(&map_w_hi, st + (PASSES == 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
+                            if (PASSES == 3) {
+                                tma_load_4d(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                tma_load_2d(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
+                            }
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1, p.err_flag, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t a_hi = make_smem_desc(sa);
+                    const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
+                    const uint64_t b_hi = make_smem_desc(sa + (PASSES == 3 ? 2 : 1) * A_TILE_BYTES);
+                    const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < BK / UMMA_K; ++j) {
+                        const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);   // advance the start address by 32 B per K step
+                        tc_mma_f16(d_tmem, a_hi + koff, b_hi + koff, IDESC, (kb | j) != 0);
+                        if (PASSES == 3) {
+                            tc_mma_f16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
+                            tc_mma_f16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+                        }
+                    }
+                    tc_commit(&empty_bar[stage]);   // frees the smem stage once the MMAs above have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31) ================================
+        const int row = threadIdx.x;                       // 0..127 = tile row = TMEM lane
+        const int w_l = row % p.TW, h_l = (row / p.TW) % p.TH, b_l = row / (p.TW * p.TH);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+            const int w = tw * p.TW + w_l, h = th * p.TH + h_l, b = tb * p.TB + b_l, n0 = nt * BN;
+            const bool valid = (w < p.W) && (h < p.H) && (b < p.B);
+            const int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
+            mbar_wait(&tfull_bar[acc], (it >> 1) & 1, p.err_flag, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tc_ld_32x32b_x32(taddr + c0, v);
+                tc_wait_ld();
+                if (valid) {
+                    float f[32];
+                    const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bv = __ldg(bp + q);
+                        f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + bv.x;
+                        f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bv.y;
+                        f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bv.z;
+                        f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bv.w;
+                    }
+                    if (p.leaky) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], kNegSlope * f[q]);
+                    }
+                    if (p.yf) {
+                        float4* dst = reinterpret_cast<float4*>(p.yf + pix * p.Cyf_total + p.cyf_off + n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    }
+                    if (p.y_hi) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            hi[q] = pack_hi2<FP16>(f[2 * q], f[2 * q + 1]);
+                            if (PASSES == 3) {
+                                const float2 r = unpack2<FP16>(hi[q]);
+                                lo[q] = pack_hi2<FP16>(f[2 * q] - r.x, f[2 * q + 1] - r.y);
+                            }
+                        }
+                        const int64_t off = pix * p.Cy_total + p.cy_off + n0 + c0;
+                        uint4* dh = reinterpret_cast<uint4*>(p.y_hi + off);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                        if (PASSES == 3 && p.y_lo) {
+                            uint4* dl = reinterpret_cast<uint4*>(p.y_lo + off);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // this warp has drained its 32 lanes of the accumulator
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) {
+        set_error("cuTensorMapEncodeTiled not available (%s)", cudaGetErrorString(e));
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    return fn;
+}
+
+bool encode_act_map(CUtensorMap* m, const uint16_t* base, int C_total, int C_used, int W, int H, int B, int TW, int TH, int TB) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)C_used, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C_total * 2, (cuuint64_t)W * C_total * 2, (cuuint64_t)H * W * C_total * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return false; }
+    return true;
+}
+
+bool encode_w_map(CUtensorMap* m, const uint16_t* base, int Ktot, int Cout_pad, int BN) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return false; }
+    return true;
+}
+
+void choose_tile(int B, int H, int W, int* TW, int* TH, int* TB) {
+    static const int cand[][3] = {{16, 8, 1}, {8, 16, 1}, {32, 4, 1}, {4, 32, 1}, {64, 2, 1}, {128, 1, 1}, {8, 8, 2},
+                                  {16, 4, 2}, {4, 16, 2}, {8, 4, 4}, {4, 8, 4}, {4, 4, 8}, {8, 2, 8}, {2, 2, 32}, {1, 1, 128}};
+    int64_t best = -1;
+    for (auto& c : cand) {
+        const int64_t tiles = (int64_t)ceil_div(W, c[0]) * ceil_div(H, c[1]) * ceil_div(B, c[2]);
+        if (best < 0 || tiles < best) { best = tiles; *TW = c[0]; *TH = c[1]; *TB = c[2]; }
+    }
+}
+
+template <int BN, int PASSES, bool FP16>
+int launch_inst(const TcConvPlan* pl, cudaStream_t s);
+
+}  // namespace
+
+struct TcConvPlan {
+    TcConvDesc d;
+    CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo;
+    TcParams p;
+    int BN, grid;
+    int* err_flag;
+};
+
+int tc_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+namespace {
+template <int BN, int PASSES, bool FP16>
+int launch_inst(const TcConvPlan* pl, cudaStream_t s) {
+    constexpr int smem = num_stages(BN, PASSES) * stage_bytes(BN, PASSES) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static bool attr = false;
+    if (!attr) {
+        H3D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, PASSES, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    conv_tc_kernel<BN, PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+}  // namespace
+
+TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
+    if (d.Cin_pad % BK != 0 || d.Cout_pad % 64 != 0 || (d.k != 1 && d.k != 3 && d.k != 5 && d.k != 7) || (d.passes != 1 && d.passes != 3)) {
+        set_error("tc_conv: unsupported geometry (Cin_pad=%d Cout_pad=%d k=%d passes=%d)", d.Cin_pad, d.Cout_pad, d.k, d.passes);
+        return nullptr;
+    }
+    if (d.y.hi && ((d.Cy_total % 8) || (d.cy_off % 8))) { set_error("tc_conv: split output channel offset/stride must be multiples of 8"); return nullptr; }
+    if (d.yf && ((d.Cyf_total % 4) || (d.cyf_off % 4))) { set_error("tc_conv: fp32 output channel offset/stride must be multiples of 4"); return nullptr; }
+    if (d.passes == 3 && (!d.x.lo || !d.w.lo)) { set_error("tc_conv: 3-pass mode needs lo planes"); return nullptr; }
+    TcConvPlan* pl = new TcConvPlan();
+    pl->d = d;
+    int BN = d.Cout_pad % 128 == 0 ? 128 : 64;
+    if (const char* e = getenv("H3D_TC_BN")) {
+        const int v = atoi(e);
+        if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
+    }
+    pl->BN = BN;
+    int TW, TH, TB;
+    choose_tile(d.B, d.H, d.W, &TW, &TH, &TB);
+    TcParams& p = pl->p;
+    p.bias = d.bias;
+    p.y_hi = d.y.hi; p.y_lo = d.y.lo; p.Cy_total = d.Cy_total; p.cy_off = d.cy_off;
+    p.yf = d.yf; p.Cyf_total = d.Cyf_total; p.cyf_off = d.cyf_off;
+    p.B = d.B; p.H = d.H; p.W = d.W; p.k = d.k; p.pad = d.k / 2; p.cin_chunks = d.Cin_pad / BK;
+    p.TW = TW; p.TH = TH; p.TB = TB;
+    p.tiles_w = ceil_div(d.W, TW); p.tiles_h = ceil_div(d.H, TH);
+    const int tiles_b = ceil_div(d.B, TB);
+    p.n_tiles = d.Cout_pad / BN;
+    p.num_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
+    p.leaky = d.leaky;
+    p.err_flag = nullptr;
+    pl->grid = std::min(p.num_tiles, tc_num_sms());
+    const int Ktot = d.k * d.k * d.Cin_pad;
+    bool ok = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB) &&
+              encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, BN);
+    if (ok && d.passes == 3)
+        ok = encode_act_map(&pl->map_x_lo, d.x.lo, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB) &&
+             encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, BN);
+    if (ok && d.passes == 1) { pl->map_x_lo = pl->map_x_hi; pl->map_w_lo = pl->map_w_hi; }
+    if (!ok) { delete pl; return nullptr; }
+    return pl;
+}
+
+void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
+
+int64_t tc_conv_flops(const TcConvPlan* p) {
+    return 2ll * p->d.B * p->d.H * p->d.W * p->d.k * p->d.k * (int64_t)p->d.Cin_pad * p->d.Cout_pad;
+}
+
+int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
+    const bool fp16 = pl->d.half == Half16::FP16;
+    const int key = pl->BN * 10 + pl->d.passes;
+#define CASE(BN_, P_)                                                                  \
+    case BN_ * 10 + P_:                                                                \
+        return fp16 ? launch_inst<BN_, P_, true>(pl, s) : launch_inst<BN_, P_, false>(pl, s);
+    switch (key) {
+        CASE(64, 1) CASE(64, 3) CASE(128, 1) CASE(128, 3) CASE(256, 1) CASE(256, 3)
+    }
+#undef CASE
+    set_error("tc_conv: no kernel instance for BN=%d passes=%d", pl->BN, pl->d.passes);
+    return H3D_EINVAL;
+}
+
+}  // namespace h3d

@@ -1,0 +1,636 @@
+// HBM-bound kernels of the ColorHandPose3D forward pass: TF1-legacy bilinear resize, 2x2 max-pool,
+// 8x8 avg-pool, soft-max / round / arg-max + 32-pass geodesic mask growing + bounding box,
+// crop_and_resize, per-channel heat-map arg-max, Rodrigues / flip / rotate epilogue.
+//
+// All arithmetic that feeds a discrete decision or an interpolated output uses explicit
+// __fmul_rn/__fadd_rn/__fsub_rn so that nvcc cannot contract to FMA: the TF-1.3 CPU kernels the
+// oracle restates use separate multiply and add.
+#include "common.cuh"
+
+namespace h3d {
+
+__device__ __forceinline__ float lerp_tf(float a, float b, float t) {
+    // a + (b - a) * t  without FMA contraction (TF compute_lerp)
+    return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
+}
+
+// =============================================================================================
+// tf.image.resize_images bilinear, align_corners=False, legacy (nets/ColorHandPose3DNetwork.py:97,128,166)
+// One thread produces 4 consecutive floats of the flattened (ox, c) output row -> float4 stores.
+// =============================================================================================
+__global__ void resize_bilinear_tf1_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
+                                           int C, int oh, int ow, float hscale, float wscale) {
+    const int row_elems = ow * C;
+    const int vec_per_row = (row_elems + 3) >> 2;
+    const int64_t total = (int64_t)B * oh * vec_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec_per_row);
+        const int oy = (int)((i / vec_per_row) % oh);
+        const int b = (int)(i / ((int64_t)vec_per_row * oh));
+        const float in_y = __fmul_rn((float)oy, hscale);
+        const int y0 = (int)floorf(in_y);
+        const int y1 = min(y0 + 1, H - 1);
+        const float ly = __fsub_rn(in_y, (float)y0);
+        const float* r0 = x + ((int64_t)b * H + y0) * W * C;
+        const float* r1 = x + ((int64_t)b * H + y1) * W * C;
+        float out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = v * 4 + j;
+            if (e < row_elems) {
+                const int ox = e / C, c = e - ox * C;
+                const float in_x = __fmul_rn((float)ox, wscale);
+                const int x0 = (int)floorf(in_x);
+                const int x1 = min(x0 + 1, W - 1);
+                const float lx = __fsub_rn(in_x, (float)x0);
+                const float tl = __ldg(r0 + x0 * C + c), tr = __ldg(r0 + x1 * C + c);
+                const float bl = __ldg(r1 + x0 * C + c), br = __ldg(r1 + x1 * C + c);
+                const float top = lerp_tf(tl, tr, lx);
+                const float bot = lerp_tf(bl, br, lx);
+                out[j] = lerp_tf(top, bot, ly);
+            } else {
+                out[j] = 0.f;
+            }
+        }
+        float* dst = y + ((int64_t)b * oh + oy) * row_elems + v * 4;
+        if ((row_elems & 3) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (v * 4 + j < row_elems) dst[j] = out[j];
+        }
+    }
+}
+
+int launch_resize_bilinear_tf1(const float* x, float* y, int B, int H, int W, int C, int oh, int ow, cudaStream_t s) {
+    if (H == oh && W == ow) {  // TF returns the input unchanged when the size already matches
+        H3D_CUDA(cudaMemcpyAsync(y, x, (size_t)B * H * W * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return H3D_OK;
+    }
+    const float hscale = (float)H / (float)oh, wscale = (float)W / (float)ow;
+    const int64_t total = (int64_t)B * oh * ((ow * C + 3) / 4);
+    const int threads = 256;
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), 148 * 32);
+    resize_bilinear_tf1_kernel<<<blocks, threads, 0, s>>>(x, y, B, H, W, C, oh, ow, hscale, wscale);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
+// NetworkOps.max_pool 2x2/2 VALID (utils/general.py:62-65)
+// =============================================================================================
+__global__ void maxpool_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int C4 = C >> 2;
+    const int64_t total = (int64_t)B * Ho * Wo * C4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        const int ox = (int)((i / C4) % Wo);
+        const int oy = (int)((i / ((int64_t)C4 * Wo)) % Ho);
+        const int b = (int)(i / ((int64_t)C4 * Wo * Ho));
+        const float4* p = reinterpret_cast<const float4*>(x + (((int64_t)b * H + 2 * oy) * W + 2 * ox) * C) + c4;
+        const float4 a = __ldg(p), bq = __ldg(p + C4), c = __ldg(p + (int64_t)W * C4), d = __ldg(p + (int64_t)W * C4 + C4);
+        float4 r;
+        r.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(c.x, d.x));
+        r.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(c.y, d.y));
+        r.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(c.z, d.z));
+        r.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(c.w, d.w));
+        reinterpret_cast<float4*>(y)[i] = r;
+    }
+}
+
+__global__ void maxpool_f32_scalar_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int64_t total = (int64_t)B * Ho * Wo * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int ox = (int)((i / C) % Wo);
+        const int oy = (int)((i / ((int64_t)C * Wo)) % Ho);
+        const int b = (int)(i / ((int64_t)C * Wo * Ho));
+        const float* p = x + (((int64_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+        y[i] = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(int64_t)W * C], p[(int64_t)W * C + C]));
+    }
+}
+
+int launch_maxpool_f32(const float* x, float* y, int B, int H, int W, int C, cudaStream_t s) {
+    const int threads = 256;
+    if ((C & 3) == 0) {
+        const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (C / 4);
+        maxpool_f32_kernel<<<(int)std::min<int64_t>(ceil_div64(total, threads), 148 * 32), threads, 0, s>>>(x, y, B, H, W, C);
+    } else {
+        const int64_t total = (int64_t)B * (H / 2) * (W / 2) * C;
+        maxpool_f32_scalar_kernel<<<(int)std::min<int64_t>(ceil_div64(total, threads), 148 * 32), threads, 0, s>>>(x, y, B, H, W, C);
+    }
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+template <bool FP16>
+__device__ __forceinline__ float h16_to_f32(uint16_t v) {
+    if (FP16) return __half2float(__ushort_as_half(v));
+    return __uint_as_float((uint32_t)v << 16);
+}
+template <bool FP16>
+__device__ __forceinline__ uint16_t f32_to_h16(float v) {
+    if (FP16) return __half_as_ushort(__float2half_rn(v));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+
+// Split-format 2x2 max-pool: 8 channels (one uint4 per plane) per thread.  The arg-max element's
+// (hi, lo) pair is carried through unchanged, so the pooled value is exactly one of the inputs.
+template <bool FP16, bool HAS_LO>
+__global__ void maxpool_split_kernel(const uint4* __restrict__ xh, const uint4* __restrict__ xl, uint4* __restrict__ yh,
+                                     uint4* __restrict__ yl, int B, int H, int W, int C8) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int64_t total = (int64_t)B * Ho * Wo * C8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const int ox = (int)((i / C8) % Wo);
+        const int oy = (int)((i / ((int64_t)C8 * Wo)) % Ho);
+        const int b = (int)(i / ((int64_t)C8 * Wo * Ho));
+        const int64_t base = (((int64_t)b * H + 2 * oy) * W + 2 * ox) * C8 + c8;
+        const int64_t offs[4] = {0, C8, (int64_t)W * C8, (int64_t)W * C8 + C8};
+        uint16_t bh[8], bl[8];
+        float bv[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 vh = __ldg(xh + base + offs[q]);
+            uint4 vl = make_uint4(0, 0, 0, 0);
+            if (HAS_LO) vl = __ldg(xl + base + offs[q]);
+            const uint16_t* ph = reinterpret_cast<const uint16_t*>(&vh);
+            const uint16_t* pl = reinterpret_cast<const uint16_t*>(&vl);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = h16_to_f32<FP16>(ph[j]);
+                if (HAS_LO) v += h16_to_f32<FP16>(pl[j]);
+                if (q == 0 || v > bv[j]) { bv[j] = v; bh[j] = ph[j]; bl[j] = pl[j]; }
+            }
+        }
+        yh[i] = *reinterpret_cast<uint4*>(bh);
+        if (HAS_LO) yl[i] = *reinterpret_cast<uint4*>(bl);
+    }
+}
+
+int launch_maxpool_split(Split x, Split y, int B, int H, int W, int C, Half16 t, cudaStream_t s) {
+    H3D_REQUIRE((C & 7) == 0, "maxpool_split: C %% 8 != 0");
+    const int threads = 256;
+    const int64_t total = (int64_t)B * (H / 2) * (W / 2) * (C / 8);
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), 148 * 32);
+    const uint4 *xh = (const uint4*)x.hi, *xl = (const uint4*)x.lo;
+    uint4 *yh = (uint4*)y.hi, *yl = (uint4*)y.lo;
+    const bool lo = x.lo != nullptr;
+    if (t == Half16::FP16) {
+        if (lo) maxpool_split_kernel<true, true><<<blocks, threads, 0, s>>>(xh, xl, yh, yl, B, H, W, C / 8);
+        else maxpool_split_kernel<true, false><<<blocks, threads, 0, s>>>(xh, xl, yh, yl, B, H, W, C / 8);
+    } else {
+        if (lo) maxpool_split_kernel<false, true><<<blocks, threads, 0, s>>>(xh, xl, yh, yl, B, H, W, C / 8);
+        else maxpool_split_kernel<false, false><<<blocks, threads, 0, s>>>(xh, xl, yh, yl, B, H, W, C / 8);
+    }
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
+// tf.nn.avg_pool 8x8/8 (nets/PosePriorNetwork.py:61)
+// =============================================================================================
+__global__ void avgpool8_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+    const int Ho = H / 8, Wo = W / 8;
+    const int64_t total = (int64_t)B * Ho * Wo * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int ox = (int)((i / C) % Wo);
+        const int oy = (int)((i / ((int64_t)C * Wo)) % Ho);
+        const int b = (int)(i / ((int64_t)C * Wo * Ho));
+        const float* p = x + (((int64_t)b * H + 8 * oy) * W + 8 * ox) * C + c;
+        float acc = 0.f;
+        for (int dy = 0; dy < 8; ++dy)
+            for (int dx = 0; dx < 8; ++dx) acc += __ldg(p + ((int64_t)dy * W + dx) * C);
+        y[i] = acc / 64.0f;
+    }
+}
+
+int launch_avgpool8(const float* x, float* y, int B, int H, int W, int C, cudaStream_t s) {
+    H3D_REQUIRE(H % 8 == 0 && W % 8 == 0, "avgpool8: H, W must be multiples of 8");
+    const int64_t total = (int64_t)B * (H / 8) * (W / 8) * C;
+    avgpool8_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 148 * 32), 256, 0, s>>>(x, y, B, H, W, C);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
+// fp32 <-> split conversions (operator-level tensor-core entry point / tests)
+// =============================================================================================
+template <bool FP16>
+__global__ void f32_to_split_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                    int64_t rows, int C, int Cpad) {
+    const int64_t total = rows * Cpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cpad);
+        const int64_t r = i / Cpad;
+        const float v = c < C ? x[r * C + c] : 0.f;
+        const uint16_t h = f32_to_h16<FP16>(v);
+        hi[i] = h;
+        if (lo) lo[i] = f32_to_h16<FP16>(v - h16_to_f32<FP16>(h));
+    }
+}
+template <bool FP16>
+__global__ void split_to_f32_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, float* __restrict__ y,
+                                    int64_t rows, int C, int Cpad) {
+    const int64_t total = rows * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t r = i / C;
+        float v = h16_to_f32<FP16>(hi[r * Cpad + c]);
+        if (lo) v += h16_to_f32<FP16>(lo[r * Cpad + c]);
+        y[i] = v;
+    }
+}
+int launch_f32_to_split(const float* x, Split y, int64_t rows, int C, int Cpad, Half16 t, cudaStream_t s) {
+    const int blocks = (int)std::min<int64_t>(ceil_div64(rows * Cpad, 256), 148 * 32);
+    if (t == Half16::FP16) f32_to_split_kernel<true><<<blocks, 256, 0, s>>>(x, y.hi, y.lo, rows, C, Cpad);
+    else f32_to_split_kernel<false><<<blocks, 256, 0, s>>>(x, y.hi, y.lo, rows, C, Cpad);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+int launch_split_to_f32(Split x, float* y, int64_t rows, int C, int Cpad, Half16 t, cudaStream_t s) {
+    const int blocks = (int)std::min<int64_t>(ceil_div64(rows * C, 256), 148 * 32);
+    if (t == Half16::FP16) split_to_f32_kernel<true><<<blocks, 256, 0, s>>>(x.hi, x.lo, y, rows, C, Cpad);
+    else split_to_f32_kernel<false><<<blocks, 256, 0, s>>>(x.hi, x.lo, y, rows, C, Cpad);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+__global__ void copy_channels_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int C, int dst_total, int dst_off) {
+    const int64_t total = rows * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        dst[(i / C) * dst_total + dst_off + c] = src[i];
+    }
+}
+int launch_copy_channels(const float* src, float* dst, int64_t rows, int C, int dst_total, int dst_off, cudaStream_t s) {
+    copy_channels_kernel<<<(int)std::min<int64_t>(ceil_div64(rows * C, 256), 148 * 8), 256, 0, s>>>(src, dst, rows, C, dst_total, dst_off);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
+// single_obj_scoremap + calc_center_bb + crop scale (utils/general.py:233-328, nets/...:83-85)
+//
+// Kernel 1 (seg_prob_kernel): per pixel fg = softmax(l)[1] (Eigen form e * (1/sum)),
+//   det = round_half_even(fg) == 1  <=>  fg > 0.5, bit-packed with __ballot_sync (bit i of word w of
+//   row y <-> pixel x = 32 w + i), and per-image arg-max of fg with first-occurrence tie-break
+//   via a 64-bit (value bits, ~index) key reduced with warp shuffles and one atomicMax per block.
+// Kernel 2 (mask_grow_kernel): one CTA per image; det / obj bit masks live in shared memory;
+//   obj <- det AND dilate21x21(obj), exactly max(H,W)//10 passes (early exit once a pass changes
+//   nothing -- the fixed point is idempotent, so the result is identical); then the bounding box,
+//   centre, crop size and scale_crop = clip(256 / (1.25 size), 0.25, 5).
+// =============================================================================================
+struct SegScratch {
+    unsigned long long* key;  // [B]
+    uint32_t* det;            // [B][H][Ww]
+};
+
+__host__ __device__ inline int seg_words(int W) { return (W + 31) >> 5; }
+
+int64_t seg_scratch_bytes(int B, int H, int W) {
+    return align_up((int64_t)B * 8, 256) + align_up((int64_t)B * H * seg_words(W) * 4, 256);
+}
+
+__global__ void seg_prob_kernel(const float2* __restrict__ logits, int H, int W, int Ww, unsigned long long* __restrict__ key,
+                                uint32_t* __restrict__ det) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int words = H * Ww;
+    unsigned long long best = 0ull;
+    for (int wd = blockIdx.x * warps_per_block + (threadIdx.x >> 5); wd < words; wd += gridDim.x * warps_per_block) {
+        const int y = wd / Ww, xw = wd - y * Ww;
+        const int x = xw * 32 + lane;
+        bool bit = false;
+        if (x < W) {
+            const int idx = y * W + x;
+            const float2 l = __ldg(logits + (int64_t)b * H * W + idx);
+            const float m = fmaxf(l.x, l.y);
+            const float e0 = expf(__fsub_rn(l.x, m)), e1 = expf(__fsub_rn(l.y, m));
+            const float inv = __fdiv_rn(1.0f, __fadd_rn(e0, e1));
+            const float fg = __fmul_rn(e1, inv);
+            bit = fg > 0.5f;  // == (rint(fg) == 1) for fg in [0,1]
+            const unsigned long long k = ((unsigned long long)__float_as_uint(fg) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)idx);
+            best = k > best ? k : best;
+        }
+        const uint32_t word = __ballot_sync(0xFFFFFFFFu, bit);
+        if (lane == 0) det[(int64_t)b * words + wd] = word;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+        best = other > best ? other : best;
+    }
+    __shared__ unsigned long long sbest[32];
+    if (lane == 0) sbest[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < warps_per_block ? sbest[threadIdx.x] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            best = other > best ? other : best;
+        }
+        if (threadIdx.x == 0) atomicMax(key + b, best);
+    }
+}
+
+constexpr int kGrowThreads = 1024;
+constexpr int kMaxMaskWords = 512 * 16;  // H, W <= 512
+
+__global__ void __launch_bounds__(kGrowThreads, 1)
+mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ det_g, int H, int W, int Ww,
+                 int num_passes, uint8_t* __restrict__ hand_mask, int32_t* __restrict__ max_loc, float* __restrict__ center,
+                 float* __restrict__ crop_size, float* __restrict__ scale_crop) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* det = sm;                    // [H][Ww]
+    uint32_t* obj = sm + H * Ww;           // [H][Ww]
+    uint32_t* hor = sm + 2 * H * Ww;       // [H][Ww]
+    __shared__ int s_changed;
+    __shared__ int s_rmin, s_rmax, s_cmin, s_cmax;
+    const int b = blockIdx.x;
+    const int words = H * Ww;
+    const int tid = threadIdx.x;
+
+    const unsigned long long k = key[b];
+    const int seed_idx = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+    const int sy = seed_idx / W, sx = seed_idx - sy * W;
+    for (int i = tid; i < words; i += kGrowThreads) {
+        det[i] = det_g[(int64_t)b * words + i];
+        obj[i] = 0u;
+    }
+    if (tid == 0) {
+        s_rmin = 1 << 30; s_rmax = -1; s_cmin = 1 << 30; s_cmax = -1;
+        if (max_loc) { max_loc[2 * b] = sy; max_loc[2 * b + 1] = sx; }
+    }
+    __syncthreads();
+    if (tid == 0) obj[sy * Ww + (sx >> 5)] = 1u << (sx & 31);   // one-hot seed (utils/general.py:252-253)
+    __syncthreads();
+
+    for (int pass = 0; pass < num_passes; ++pass) {
+        if (tid == 0) s_changed = 0;
+        // horizontal OR over [-10, +10] pixels
+        for (int i = tid; i < words; i += kGrowThreads) {
+            const int xw = i % Ww;
+            const uint32_t cur = obj[i];
+            const uint32_t prev = xw > 0 ? obj[i - 1] : 0u;
+            const uint32_t next = xw + 1 < Ww ? obj[i + 1] : 0u;
+            uint32_t r = cur;
+#pragma unroll
+            for (int sft = 1; sft <= 10; ++sft) {
+                r |= __funnelshift_l(prev, cur, sft);   // pixel x - sft -> x
+                r |= __funnelshift_r(cur, next, sft);   // pixel x + sft -> x
+            }
+            hor[i] = r;
+        }
+        __syncthreads();
+        // vertical OR over [-10, +10] rows, AND with det
+        int changed = 0;
+        for (int i = tid; i < words; i += kGrowThreads) {
+            const int y = i / Ww;
+            const int y0 = max(y - 10, 0), y1 = min(y + 10, H - 1);
+            uint32_t r = 0u;
+            for (int yy = y0; yy <= y1; ++yy) r |= hor[i + (yy - y) * Ww];
+            r &= det[i];
+            changed |= (r != obj[i]);
+            // obj is only read through `hor` in this phase, so the in-place update is race-free
+            obj[i] = r;
+        }
+        if (changed) s_changed = 1;
+        __syncthreads();
+        const int any = s_changed;
+        __syncthreads();
+        if (!any) break;   // fixed point: remaining passes are no-ops
+    }
+
+    // bounding box (utils/general.py:294-300): X = row index, Y = column index
+    int rmin = 1 << 30, rmax = -1, cmin = 1 << 30, cmax = -1;
+    for (int i = tid; i < words; i += kGrowThreads) {
+        const uint32_t v = obj[i];
+        if (v) {
+            const int y = i / Ww, xw = i - y * Ww;
+            rmin = min(rmin, y); rmax = max(rmax, y);
+            cmin = min(cmin, xw * 32 + __ffs(v) - 1);
+            cmax = max(cmax, xw * 32 + 31 - __clz(v));
+        }
+    }
+    if (rmax >= 0) {
+        atomicMin(&s_rmin, rmin); atomicMax(&s_rmax, rmax);
+        atomicMin(&s_cmin, cmin); atomicMax(&s_cmax, cmax);
+    }
+    if (hand_mask) {
+        for (int i = tid; i < H * W; i += kGrowThreads) {
+            const int y = i / W, x = i - y * W;
+            hand_mask[(int64_t)b * H * W + i] = (obj[y * Ww + (x >> 5)] >> (x & 31)) & 1u;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float c0, c1, sz;
+        if (s_rmax < 0) {           // empty mask: the reference's written fallbacks (utils/general.py:311-312,319-320)
+            c0 = 160.0f; c1 = 160.0f; sz = 100.0f;
+        } else {
+            const float xmin = (float)s_rmin, xmax = (float)s_rmax, ymin = (float)s_cmin, ymax = (float)s_cmax;
+            c0 = __fmul_rn(0.5f, __fadd_rn(xmax, xmin));
+            c1 = __fmul_rn(0.5f, __fadd_rn(ymax, ymin));
+            sz = fmaxf(__fsub_rn(xmax, xmin), __fsub_rn(ymax, ymin));
+        }
+        center[2 * b] = c0; center[2 * b + 1] = c1;
+        if (crop_size) crop_size[b] = sz;
+        const float best = __fmul_rn(sz, 1.25f);                                   // nets/...:84
+        scale_crop[b] = fminf(fmaxf(__fdiv_rn(256.0f, best), 0.25f), 5.0f);         // nets/...:85 (size 0 -> inf -> 5)
+    }
+}
+
+int launch_seg_postprocess(const float* logits, int B, int H, int W, void* scratch, uint8_t* hand_mask, int32_t* max_loc,
+                           float* center, float* crop_size, float* scale_crop, cudaStream_t s, int* n_launch) {
+    H3D_REQUIRE(H <= 512 && W <= 512 && H > 0 && W > 0, "seg_postprocess: H, W must be in [1, 512]");
+    const int Ww = seg_words(W);
+    unsigned long long* key = (unsigned long long*)scratch;
+    uint32_t* det = (uint32_t*)((char*)scratch + align_up((int64_t)B * 8, 256));
+    H3D_CUDA(cudaMemsetAsync(key, 0, (size_t)B * 8, s));
+    const int words = H * Ww;
+    dim3 grid(std::min(ceil_div(words, 8), 64), B);
+    seg_prob_kernel<<<grid, 256, 0, s>>>((const float2*)logits, H, W, Ww, key, det);
+    H3D_CHECK_LAUNCH();
+    const size_t smem = (size_t)3 * words * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        H3D_CUDA(cudaFuncSetAttribute(mask_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kMaxMaskWords * 4));
+        attr_set = true;
+    }
+    const int num_passes = std::max(H, W) / (21 / 2);   // utils/general.py:256
+    mask_grow_kernel<<<B, kGrowThreads, smem, s>>>(key, det, H, W, Ww, num_passes, hand_mask, max_loc, center, crop_size,
+                                                   scale_crop);
+    H3D_CHECK_LAUNCH();
+    if (n_launch) *n_launch += 2;
+    return H3D_OK;
+}
+
+// =============================================================================================
+// crop_image_from_xy (utils/general.py:163-196) = box arithmetic + tf.image.crop_and_resize
+// (bilinear, extrapolation 0).  One thread per output pixel (all C channels, C <= 4).
+// =============================================================================================
+__global__ void crop_image_kernel(const float* __restrict__ image, const float* __restrict__ center,
+                                  const float* __restrict__ scale, float* __restrict__ out, int B, int H, int W, int C, int crop) {
+    const int64_t total = (int64_t)B * crop * crop;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % crop);
+        const int y = (int)((i / crop) % crop);
+        const int b = (int)(i / ((int64_t)crop * crop));
+        const float cs = (float)crop;
+        const float css = __fdiv_rn(cs, scale[b]);                       // :182
+        const float half = floorf(__fdiv_rn(css, 2.0f));                 // float '//' (:183,185)
+        const float y1 = __fsub_rn(center[2 * b], half), y2 = __fadd_rn(y1, css);
+        const float x1 = __fsub_rn(center[2 * b + 1], half), x2 = __fadd_rn(x1, css);
+        const float y1n = __fdiv_rn(y1, (float)H), y2n = __fdiv_rn(y2, (float)H);   // :187-190 (H, W -- not H-1)
+        const float x1n = __fdiv_rn(x1, (float)W), x2n = __fdiv_rn(x2, (float)W);
+        const float hm1 = (float)(H - 1), wm1 = (float)(W - 1);
+        const float hs = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(y2n, y1n), hm1), (float)(crop - 1)) : 0.f;
+        const float ws = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(x2n, x1n), wm1), (float)(crop - 1)) : 0.f;
+        const float in_y = crop > 1 ? __fadd_rn(__fmul_rn(y1n, hm1), __fmul_rn((float)y, hs))
+                                    : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1n, y2n)), hm1);
+        const float in_x = crop > 1 ? __fadd_rn(__fmul_rn(x1n, wm1), __fmul_rn((float)x, ws))
+                                    : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1n, x2n)), wm1);
+        float* dst = out + i * C;
+        const bool valid = !(in_y < 0.f || in_y > hm1) && !(in_x < 0.f || in_x > wm1);
+        if (!valid) {
+            for (int c = 0; c < C; ++c) dst[c] = 0.f;
+            continue;
+        }
+        const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
+        const int lef = (int)floorf(in_x), rig = (int)ceilf(in_x);
+        const float ly = __fsub_rn(in_y, (float)top), lx = __fsub_rn(in_x, (float)lef);
+        const float* img = image + (int64_t)b * H * W * C;
+        for (int c = 0; c < C; ++c) {
+            const float tl = __ldg(img + ((int64_t)top * W + lef) * C + c), tr = __ldg(img + ((int64_t)top * W + rig) * C + c);
+            const float bl = __ldg(img + ((int64_t)bot * W + lef) * C + c), br = __ldg(img + ((int64_t)bot * W + rig) * C + c);
+            dst[c] = lerp_tf(lerp_tf(tl, tr, lx), lerp_tf(bl, br, lx), ly);
+        }
+    }
+}
+
+int launch_crop_image(const float* image, const float* center, const float* scale, float* out, int B, int H, int W, int C,
+                      int crop, cudaStream_t s) {
+    const int64_t total = (int64_t)B * crop * crop;
+    crop_image_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 148 * 16), 256, 0, s>>>(image, center, scale, out, B, H,
+                                                                                             W, C, crop);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
+// detect_keypoints (utils/general.py:331-344), batched on device.  Thread (p, c) streams pixels
+// p, p+P, ... of channel c: consecutive threads read consecutive floats (NHWC), keys are reduced in
+// shared memory and merged with one 64-bit atomicMax per (block, channel).
+// =============================================================================================
+__device__ __forceinline__ uint32_t float_orderable(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+int64_t argmax_scratch_bytes(int B, int C) { return align_up((int64_t)B * C * 8, 256); }
+
+__global__ void heatmap_argmax_kernel(const float* __restrict__ sm, int HW, int C, int P, unsigned long long* __restrict__ key) {
+    extern __shared__ unsigned long long skey[];   // [P][C]
+    const int b = blockIdx.y;
+    const int t = threadIdx.x;
+    const int p_sub = t / C, c = t - p_sub * C;
+    unsigned long long best = 0ull;
+    if (p_sub < P) {
+        const float* base = sm + (int64_t)b * HW * C;
+        for (int p = blockIdx.x * P + p_sub; p < HW; p += gridDim.x * P) {
+            const float v = __ldg(base + (int64_t)p * C + c);
+            const unsigned long long k = ((unsigned long long)float_orderable(v) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
+            best = k > best ? k : best;
+        }
+        skey[p_sub * C + c] = best;
+    }
+    __syncthreads();
+    if (t < C) {
+        unsigned long long m = 0ull;
+        for (int q = 0; q < P; ++q) { const unsigned long long k = skey[q * C + t]; m = k > m ? k : m; }
+        atomicMax(key + (int64_t)b * C + t, m);
+    }
+}
+
+__global__ void argmax_decode_kernel(const unsigned long long* __restrict__ key, int n, int W, int32_t* __restrict__ uv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int idx = (int)(0xFFFFFFFFu - (uint32_t)(key[i] & 0xFFFFFFFFull));
+        uv[2 * i] = idx / W;       // v (row)
+        uv[2 * i + 1] = idx % W;   // u (col)
+    }
+}
+
+int launch_detect_keypoints(const float* sm, int B, int H, int W, int C, void* scratch, int32_t* uv, cudaStream_t s,
+                            int* n_launch) {
+    H3D_REQUIRE(C >= 1 && C <= 256, "detect_keypoints: C must be in [1,256]");
+    unsigned long long* key = (unsigned long long*)scratch;
+    H3D_CUDA(cudaMemsetAsync(key, 0, (size_t)B * C * 8, s));
+    const int P = std::max(1, 256 / C);
+    const int threads = P * C;
+    const int HW = H * W;
+    dim3 grid(std::max(1, std::min(ceil_div(HW, P * 16), 64)), B);
+    heatmap_argmax_kernel<<<grid, threads, (size_t)P * C * 8, s>>>(sm, HW, C, P, key);
+    H3D_CHECK_LAUNCH();
+    argmax_decode_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(key, B * C, W, uv);
+    H3D_CHECK_LAUNCH();
+    if (n_launch) *n_launch += 2;
+    return H3D_OK;
+}
+
+// =============================================================================================
+// _get_rot_mat + _flip_right_hand + batched matmul (nets/ColorHandPose3DNetwork.py:239-247,311-384)
+// =============================================================================================
+__global__ void rotate_canonical_kernel(const float* __restrict__ can, const float* __restrict__ uxyz,
+                                        const float* __restrict__ hand_side, int B, float* __restrict__ rot, float* __restrict__ out) {
+    const int b = blockIdx.x;
+    __shared__ float R[9];
+    if (threadIdx.x == 0) {
+        const float ux_b = uxyz[3 * b], uy_b = uxyz[3 * b + 1], uz_b = uxyz[3 * b + 2];
+        const float n2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux_b, ux_b), __fmul_rn(uy_b, uy_b)), __fmul_rn(uz_b, uz_b)), 1e-8f);
+        const float theta = sqrtf(n2);
+        const float st = sinf(theta), ct = cosf(theta);
+        const float one_ct = __fsub_rn(1.0f, ct);
+        const float nf = __fdiv_rn(1.0f, theta);
+        const float ux = __fmul_rn(ux_b, nf), uy = __fmul_rn(uy_b, nf), uz = __fmul_rn(uz_b, nf);
+#define M3(a, b_, c) __fmul_rn(__fmul_rn(a, b_), c)
+        R[0] = __fadd_rn(ct, M3(ux, ux, one_ct));
+        R[1] = __fsub_rn(M3(ux, uy, one_ct), __fmul_rn(uz, st));
+        R[2] = __fadd_rn(M3(ux, uz, one_ct), __fmul_rn(uy, st));
+        R[3] = __fadd_rn(M3(uy, ux, one_ct), __fmul_rn(uz, st));
+        R[4] = __fadd_rn(ct, M3(uy, uy, one_ct));
+        R[5] = __fsub_rn(M3(uy, uz, one_ct), __fmul_rn(ux, st));
+        R[6] = __fsub_rn(M3(uz, ux, one_ct), __fmul_rn(uy, st));
+        R[7] = __fadd_rn(M3(uz, uy, one_ct), __fmul_rn(ux, st));
+        R[8] = __fadd_rn(ct, M3(uz, uz, one_ct));
+#undef M3
+        if (rot)
+            for (int i = 0; i < 9; ++i) rot[9 * b + i] = R[i];
+    }
+    __syncthreads();
+    const bool right = hand_side[2 * b + 1] > hand_side[2 * b];   // argmax(hand_side,1)==1 (ties -> index 0)
+    for (int i = threadIdx.x; i < 63; i += blockDim.x) {
+        const int kp = i / 3, j = i - kp * 3;
+        const float cx = can[63 * b + 3 * kp], cy = can[63 * b + 3 * kp + 1];
+        float cz = can[63 * b + 3 * kp + 2];
+        if (right) cz = -cz;
+        out[63 * b + i] = cx * R[j] + cy * R[3 + j] + cz * R[6 + j];
+    }
+}
+
+int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot, float* out,
+                            cudaStream_t s) {
+    rotate_canonical_kernel<<<B, 64, 0, s>>>(coord_can, uxyz, hand_side, B, rot, out);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+}  // namespace h3d

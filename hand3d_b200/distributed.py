@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing: the pipeline is embarrassingly data parallel (every image is independent,
+utils/general.py:250,293 even loop per sample), so ranks shard the batch, replicate the weights and run
+with no communication; the only exchange is ONE all-gather of a fixed 432-byte per-image record
+(coord3d 21x3 f32 | key-points (row, col) 21x2 i32 | center 2 f32 | scale_crop 1 f32) -- SURVEY.md 8(e).
+The large score maps stay sharded on their owning GPU.  Backend-agnostic (NCCL on GPUs, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+RECORD_FLOATS = 63 + 42 + 2 + 1   # 108 x 4 B = 432 B per image
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of `total` images for `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_records(coord3d, keypoints_uv, center, scale_crop):
+    B = coord3d.shape[0]
+    uv_bits = keypoints_uv.reshape(B, 42).contiguous().view(torch.float32)    # bit-cast, gathered bitwise
+    return torch.cat([coord3d.reshape(B, 63), uv_bits, center.reshape(B, 2), scale_crop.reshape(B, 1)], dim=1).contiguous()
+
+
+def unpack_records(rec):
+    B = rec.shape[0]
+    return {
+        "keypoint_coord3d": rec[:, :63].reshape(B, 21, 3),
+        "keypoints_uv": rec[:, 63:105].contiguous().view(torch.int32).reshape(B, 21, 2),
+        "center": rec[:, 105:107],
+        "scale_crop": rec[:, 107:108],
+    }
+
+
+def gather_records(rec, group=None):
+    """all_gather of equally sized [B_local, 108] record tensors -> [world * B_local, 108], rank-major."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    return out
+
+
+def gather_ragged_records(rec, total: int, group=None):
+    """Same for shard_range() shards of unequal size: pads to the largest shard, gathers, strips the padding."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
+    mx = max(sizes)
+    pad = torch.zeros((mx, rec.shape[1]), dtype=rec.dtype, device=rec.device)
+    pad[: sizes[rank]] = rec
+    full = gather_records(pad, group).reshape(world, mx, rec.shape[1])
+    return torch.cat([full[r, : sizes[r]] for r in range(world)], dim=0)

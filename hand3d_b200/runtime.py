@@ -1,0 +1,282 @@
+"""Host-side runtime over the C ABI: one Context per CUDA device (weights, workspace, precision).
+
+Mirrors the role the default TF graph + tf.Session play in the reference (nets/ColorHandPose3DNetwork.py:34-59):
+`default_context()` is what `ColorHandPose3DNetwork.init()` loads the pickled variables into and what the
+static `inference_detection()` / `NetworkOps` helpers look their variables up in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PRECISIONS, VARIANTS
+
+
+def _ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_f32(t, name, ndim=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must live on a CUDA device (hand3d_b200 has no CPU path)" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32" % name)
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("%s must be %d-D, got %s" % (name, ndim, tuple(t.shape)))
+    return t.contiguous()
+
+
+class Context:
+    def __init__(self, device=None, precision="bf16x3"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("hand3d_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        h = C.c_void_p()
+        _lib.check(self.lib.h3d_create(C.byref(h), self.device.index), "h3d_create")
+        self.h = h
+        self._ws = None
+        self._ws_key = (0, 0, 0)
+        self.weights = {}
+        self.set_precision(precision)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.h3d_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- configuration -------------------------------------------------------------------
+    def set_precision(self, precision):
+        p = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        _lib.check(self.lib.h3d_set_precision(self.h, p), "h3d_set_precision")
+        self.precision = p
+
+    @property
+    def launch_count(self):
+        return int(self.lib.h3d_launch_count(self.h))
+
+    def profile_begin(self):
+        _lib.check(self.lib.h3d_profile_begin(self.h), "h3d_profile_begin")
+
+    def profile_end(self):
+        ms = (C.c_double * 4)(); fl = (C.c_int64 * 4)(); nl = (C.c_int64 * 4)()
+        _lib.check(self.lib.h3d_profile_end(self.h, ms, fl, nl), "h3d_profile_end")
+        names = ("tc_conv", "direct_conv", "fc", "other")
+        return {n: {"ms": ms[i], "flops": int(fl[i]), "launches": int(nl[i])} for i, n in enumerate(names)}
+
+    def load_weights(self, weight_dict):
+        for name, arr in weight_dict.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            rc = self.lib.h3d_load_weight(self.h, name.encode(), a.ctypes.data_as(C.c_void_p), shape, a.ndim)
+            if rc == _lib.EWEIGHTS:
+                raise ValueError(_lib.last_error())
+            _lib.check(rc, "h3d_load_weight(%s)" % name)
+            self.weights[name] = a
+
+    def scope_ready(self, scope):
+        return bool(self.lib.h3d_scope_ready(self.h, scope.encode()))
+
+    def dev_weight(self, name):
+        """fp32 device copy of a loaded variable (for the operator-level NetworkOps mirror)."""
+        cache = self.__dict__.setdefault("_dev_w", {})
+        if name not in cache:
+            if name not in self.weights:
+                raise ValueError("variable %s was not loaded" % name)
+            cache[name] = torch.from_numpy(self.weights[name]).to(self.device)
+        return cache[name]
+
+    def ensure_workspace(self, B, H, W):
+        kB, kH, kW = max(B, self._ws_key[0]), max(H, self._ws_key[1]), max(W, self._ws_key[2])
+        if (kB, kH, kW) == self._ws_key and self._ws is not None:
+            return
+        need = int(self.lib.h3d_workspace_bytes(self.h, kB, kH, kW))
+        if need < 0:
+            _lib.check(need, "h3d_workspace_bytes")
+        torch.cuda.synchronize(self.device)
+        self._ws = None
+        self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        base = (self._ws.data_ptr() + 1023) // 1024 * 1024
+        _lib.check(self.lib.h3d_set_workspace(self.h, C.c_void_p(base), need), "h3d_set_workspace")
+        self._ws_key = (kB, kH, kW)
+
+    # ---- stages ----------------------------------------------------------------------------
+    def handsegnet(self, image):
+        image = _chk_f32(image, "image", 4)
+        B, H, W, _ = image.shape
+        self.ensure_workspace(B, H, W)
+        out = torch.empty((B, H, W, 2), dtype=torch.float32, device=image.device)
+        _lib.check(self.lib.h3d_handsegnet_forward(self.h, _ptr(image), B, H, W, _ptr(out), _stream()), "h3d_handsegnet_forward")
+        return out
+
+    def posenet(self, image_crop):
+        image_crop = _chk_f32(image_crop, "image_crop", 4)
+        B, H, W, _ = image_crop.shape
+        self.ensure_workspace(B, H, W)
+        outs = [torch.empty((B, H // 8, W // 8, 21), dtype=torch.float32, device=image_crop.device) for _ in range(3)]
+        _lib.check(self.lib.h3d_posenet_forward(self.h, _ptr(image_crop), B, H, W, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
+                                                _stream()), "h3d_posenet_forward")
+        return outs
+
+    def lifting(self, scoremap32, hand_side, variant="proposed"):
+        scoremap32 = _chk_f32(scoremap32, "scoremap", 4)
+        hand_side = _chk_f32(hand_side, "hand_side", 2)
+        B = scoremap32.shape[0]
+        if tuple(scoremap32.shape[1:]) != (32, 32, 21):
+            raise ValueError("lifting expects a [B,32,32,21] score map, got %s" % (tuple(scoremap32.shape),))
+        self.ensure_workspace(B, 8, 8)
+        dev = scoremap32.device
+        out = torch.empty((B, 21, 3), dtype=torch.float32, device=dev)
+        can = torch.empty((B, 21, 3), dtype=torch.float32, device=dev)
+        v = VARIANTS[variant]
+        rot = torch.empty((B, 3, 3), dtype=torch.float32, device=dev) if variant == "proposed" else None
+        _lib.check(self.lib.h3d_lifting_forward(self.h, _ptr(scoremap32), _ptr(hand_side), B, v, _ptr(out), _ptr(can), _ptr(rot),
+                                                _stream()), "h3d_lifting_forward")
+        return out, can, rot
+
+    def pipeline(self, image, hand_side=None, with_pose3d=True, force_center=None, force_scale=None, want_mask=False,
+                 outputs="all"):
+        """ColorHandPose3DNetwork.inference / inference2d + detect_keypoints.  outputs="all" materialises the
+        reference's large tensors; outputs="keypoints" keeps them in the workspace (serving mode)."""
+        image = _chk_f32(image, "image", 4)
+        B, H, W, _ = image.shape
+        dev = image.device
+        if with_pose3d:
+            hand_side = _chk_f32(hand_side, "hand_side", 2)
+        self.ensure_workspace(B, H, W)
+        f32 = dict(dtype=torch.float32, device=dev)
+        big = outputs == "all"
+        r = {
+            "hand_scoremap": torch.empty((B, H, W, 2), **f32) if big else None,
+            "image_crop": torch.empty((B, 256, 256, 3), **f32) if big else None,
+            "scale_crop": torch.empty((B, 1), **f32),
+            "center": torch.empty((B, 2), **f32),
+            "keypoints_scoremap": torch.empty((B, 256, 256, 21), **f32) if big else None,
+            "keypoint_coord3d": torch.empty((B, 21, 3), **f32) if with_pose3d else None,
+            "keypoints_uv": torch.empty((B, 21, 2), dtype=torch.int32, device=dev),
+            "hand_mask": torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_mask else None,
+        }
+        fc = _chk_f32(force_center, "force_center") if force_center is not None else None
+        fs = _chk_f32(force_scale, "force_scale") if force_scale is not None else None
+        _lib.check(self.lib.h3d_pipeline_forward(
+            self.h, _ptr(image), _ptr(hand_side if with_pose3d else None), B, H, W, int(bool(with_pose3d)), _ptr(fc), _ptr(fs),
+            _ptr(r["hand_scoremap"]), _ptr(r["image_crop"]), _ptr(r["scale_crop"]), _ptr(r["center"]),
+            _ptr(r["keypoints_scoremap"]), _ptr(r["keypoint_coord3d"]), _ptr(r["keypoints_uv"]), _ptr(r["hand_mask"]),
+            _stream()), "h3d_pipeline_forward")
+        return r
+
+    # ---- operators ---------------------------------------------------------------------------
+    def conv2d(self, x, w, b, stride=1, leaky=False):
+        x = _chk_f32(x, "x", 4); w = _chk_f32(w, "w", 4); b = _chk_f32(b, "b", 1)
+        B, H, W, Cin = x.shape
+        k, _, _, Cout = w.shape
+        y = torch.empty((B, -(-H // stride), -(-W // stride), Cout), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.h3d_conv2d_f32(self.h, _ptr(x), _ptr(w), _ptr(b), _ptr(y), B, H, W, Cin, Cout, k, stride, int(leaky),
+                                           _stream()), "h3d_conv2d_f32")
+        return y
+
+    def conv2d_tc(self, x, w_host, b_host, leaky=False, precision="bf16x3"):
+        x = _chk_f32(x, "x", 4)
+        w = np.ascontiguousarray(w_host, np.float32); b = np.ascontiguousarray(b_host, np.float32)
+        B, H, W, Cin = x.shape
+        k, _, _, Cout = w.shape
+        y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.h3d_conv2d_tc(self.h, _ptr(x), w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), _ptr(y),
+                                          B, H, W, Cin, Cout, k, int(leaky), PRECISIONS[precision], _stream()), "h3d_conv2d_tc")
+        return y
+
+    def max_pool(self, x):
+        x = _chk_f32(x, "x", 4)
+        B, H, W, Cc = x.shape
+        y = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.h3d_maxpool2x2_f32(self.h, _ptr(x), _ptr(y), B, H, W, Cc, _stream()), "h3d_maxpool2x2_f32")
+        return y
+
+    def fully_connected(self, x, w, b, leaky=False):
+        x = _chk_f32(x, "x", 2); w = _chk_f32(w, "w", 2); b = _chk_f32(b, "b", 1)
+        y = torch.empty((x.shape[0], w.shape[1]), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.h3d_fully_connected_f32(self.h, _ptr(x), _ptr(w), _ptr(b), _ptr(y), x.shape[0], w.shape[0], w.shape[1],
+                                                    int(leaky), _stream()), "h3d_fully_connected_f32")
+        return y
+
+    def resize_bilinear(self, x, out_h, out_w):
+        x = _chk_f32(x, "x", 4)
+        B, H, W, Cc = x.shape
+        y = torch.empty((B, out_h, out_w, Cc), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.h3d_resize_bilinear_tf1(self.h, _ptr(x), _ptr(y), B, H, W, Cc, out_h, out_w, _stream()),
+                   "h3d_resize_bilinear_tf1")
+        return y
+
+    def avg_pool8(self, x):
+        x = _chk_f32(x, "x", 4)
+        B, H, W, Cc = x.shape
+        y = torch.empty((B, H // 8, W // 8, Cc), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.h3d_avgpool8(self.h, _ptr(x), _ptr(y), B, H, W, Cc, _stream()), "h3d_avgpool8")
+        return y
+
+    def seg_postprocess(self, logits):
+        logits = _chk_f32(logits, "scoremap", 4)
+        B, H, W, Cc = logits.shape
+        if Cc != 2:
+            raise ValueError("single_obj_scoremap kernel expects 2 classes (background, hand)")
+        dev = logits.device
+        mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        loc = torch.empty((B, 2), dtype=torch.int32, device=dev)
+        center = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        size = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        scale = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.h3d_seg_postprocess(self.h, _ptr(logits), B, H, W, _ptr(mask), _ptr(loc), _ptr(center), _ptr(size),
+                                                _ptr(scale), _stream()), "h3d_seg_postprocess")
+        return {"hand_mask": mask, "max_loc": loc, "center": center, "crop_size": size, "scale_crop": scale}
+
+    def crop_image_from_xy(self, image, center, crop_size, scale):
+        image = _chk_f32(image, "image", 4)
+        B, H, W, Cc = image.shape
+        center = _chk_f32(center.to(torch.float32).reshape(B, 2), "crop_location")
+        scale = _chk_f32(scale.to(torch.float32).reshape(-1).expand(B).contiguous(), "scale")
+        out = torch.empty((B, crop_size, crop_size, Cc), dtype=torch.float32, device=image.device)
+        _lib.check(self.lib.h3d_crop_image_from_xy(self.h, _ptr(image), _ptr(center), _ptr(scale), _ptr(out), B, H, W, Cc,
+                                                   int(crop_size), _stream()), "h3d_crop_image_from_xy")
+        return out
+
+    def detect_keypoints(self, scoremaps):
+        scoremaps = _chk_f32(scoremaps, "scoremaps", 4)
+        B, H, W, Cc = scoremaps.shape
+        uv = torch.empty((B, Cc, 2), dtype=torch.int32, device=scoremaps.device)
+        _lib.check(self.lib.h3d_detect_keypoints(self.h, _ptr(scoremaps), B, H, W, Cc, _ptr(uv), _stream()), "h3d_detect_keypoints")
+        return uv
+
+    def rotate_canonical(self, coord_can, uxyz, hand_side):
+        coord_can = _chk_f32(coord_can, "coord_can", 3); uxyz = _chk_f32(uxyz, "uxyz", 2); hand_side = _chk_f32(hand_side, "hand_side", 2)
+        B = coord_can.shape[0]
+        rot = torch.empty((B, 3, 3), dtype=torch.float32, device=coord_can.device)
+        out = torch.empty((B, 21, 3), dtype=torch.float32, device=coord_can.device)
+        _lib.check(self.lib.h3d_rotate_canonical(self.h, _ptr(coord_can), _ptr(uxyz), _ptr(hand_side), B, _ptr(rot), _ptr(out),
+                                                 _stream()), "h3d_rotate_canonical")
+        return rot, out
+
+
+_default = {}
+
+
+def default_context(device=None) -> Context:
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if idx not in _default:
+        _default[idx] = Context(idx)
+    return _default[idx]
+
+
+def reset_default_context():
+    _default.clear()

@@ -1,0 +1,157 @@
+/*
+ * hand3d_b200 -- C ABI of the B200-native ColorHandPose3D forward pass.
+ *
+ * The reference (lmb-freiburg/hand3d) has no FFI boundary: its hot path sits behind the Python API
+ * of nets/ColorHandPose3DNetwork.py / nets/PosePriorNetwork.py / utils/general.py and resolves to
+ * TensorFlow-1.3 library kernels.  This header is the boundary a maintainer binds instead (ctypes
+ * stub in INTEGRATION.md); every entry point cites the reference interface it replaces.
+ *
+ * Conventions:
+ *   - plain C, raw DEVICE pointers unless a parameter is named host_*, explicit sizes, NHWC fp32
+ *     tensors exactly as the reference lays them out;
+ *   - every call ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns at once;
+ *   - return 0 on success, negative H3D_E* on failure; h3d_last_error() gives a thread-local message;
+ *   - no allocation inside hot calls: the caller owns all tensors and the workspace arena;
+ *   - one h3d_ctx per device, used from one host thread at a time (one rank <-> one GPU);
+ *   - there is NO CPU fallback: without a usable sm_100a device every compute call fails with
+ *     H3D_ENODEVICE.
+ */
+#ifndef HAND3D_B200_H_
+#define HAND3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define H3D_API __attribute__((visibility("default")))
+#else
+#define H3D_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H3D_OK 0
+#define H3D_EINVAL (-1)     /* bad argument / shape                                   */
+#define H3D_ENODEVICE (-2)  /* no CUDA device, or not compute capability 10.x          */
+#define H3D_ECUDA (-3)      /* CUDA runtime / driver error (message in h3d_last_error) */
+#define H3D_EWEIGHTS (-4)   /* weights missing, unknown name, wrong shape, NaN/Inf     */
+#define H3D_EWORKSPACE (-5) /* workspace arena missing or too small                    */
+
+/* Arithmetic of the tensor-core convolution layers. */
+#define H3D_PREC_FP32_FFMA 0  /* all layers on CUDA cores in fp32 (validation yard-stick)             */
+#define H3D_PREC_BF16X3 1     /* tcgen05, bf16 hi/lo split, 3 MMA passes, fp32 accumulate (fp32 parity) */
+#define H3D_PREC_FP16X3 2     /* tcgen05, fp16 hi/lo split, 3 MMA passes, fp32 accumulate (fp32 parity) */
+#define H3D_PREC_FP16 3       /* tcgen05, fp16 single pass, fp32 accumulate (BASELINE config 5, 1e-2)   */
+#define H3D_PREC_BF16 4       /* tcgen05, bf16 single pass                                              */
+
+/* PosePriorNetwork variants (nets/PosePriorNetwork.py:64-93). */
+#define H3D_VARIANT_DIRECT 0
+#define H3D_VARIANT_BOTTLENECK 1
+#define H3D_VARIANT_PROPOSED 2
+
+typedef struct h3d_ctx h3d_ctx;
+
+H3D_API const char* h3d_last_error(void);
+H3D_API int h3d_version(void);
+/* 1 when a CUDA device with compute capability 10.x is visible, else 0 (never fails). */
+H3D_API int h3d_device_available(void);
+
+/* ---- context ----------------------------------------------------------------------------- */
+H3D_API int h3d_create(h3d_ctx** out, int device);
+H3D_API int h3d_destroy(h3d_ctx* ctx);
+H3D_API int h3d_set_precision(h3d_ctx* ctx, int precision);
+H3D_API int h3d_get_precision(const h3d_ctx* ctx);
+/* Number of kernels this library launched through `ctx` since creation (bench "gpu_launches"). */
+H3D_API int64_t h3d_launch_count(const h3d_ctx* ctx);
+
+/* Per-kernel-class device timing for bench.py's roofline: between begin and end every plan step is
+ * bracketed by CUDA events on its launch stream.  Classes: 0 = tcgen05 conv, 1 = CUDA-core conv,
+ * 2 = fully connected, 3 = other.  end() synchronises and fills three arrays of length 4. */
+H3D_API int h3d_profile_begin(h3d_ctx* ctx);
+H3D_API int h3d_profile_end(h3d_ctx* ctx, double* ms_by_kind, int64_t* flops_by_kind, int64_t* launches_by_kind);
+
+/* Replaces ColorHandPose3DNetwork.init / PosePriorNetwork.init (nets/ColorHandPose3DNetwork.py:34-59,
+ * nets/PosePriorNetwork.py:36-57): one call per pickled variable, `name` = "<scope>/<layer>/weights|biases",
+ * host_data = fp32 HWIO / [in,out] / [Cout] exactly as pickled.  Unknown names and wrong shapes fail
+ * (assign_from_values behaviour); FC weights/biases containing NaN/Inf fail (tf.check_numerics,
+ * utils/general.py:122,127).  Weights are packed once to the kernel layouts. */
+H3D_API int h3d_load_weight(h3d_ctx* ctx, const char* name, const float* host_data, const int64_t* shape, int ndim);
+/* 1 if every variable of `scope` ("HandSegNet", "PoseNet2D", "PosePrior", "ViewpointNet") is loaded. */
+H3D_API int h3d_scope_ready(const h3d_ctx* ctx, const char* scope);
+
+/* Workspace arena for the stage entry points (activations of one batch). */
+H3D_API int64_t h3d_workspace_bytes(const h3d_ctx* ctx, int B, int H, int W);
+H3D_API int h3d_set_workspace(h3d_ctx* ctx, void* dev_ptr, int64_t bytes);
+
+/* ---- stage entry points (fixed layer schedules) --------------------------------------------- */
+/* ColorHandPose3DNetwork.inference_detection (nets/ColorHandPose3DNetwork.py:131-168).
+ * image [B,H,W,3] -> logits [B,H,W,2] (already x8 bilinearly up-sampled, TF1 legacy resize). */
+H3D_API int h3d_handsegnet_forward(h3d_ctx* ctx, const float* image, int B, int H, int W, float* logits, void* stream);
+
+/* ColorHandPose3DNetwork.inference_pose2d (nets/ColorHandPose3DNetwork.py:170-219).
+ * image_crop [B,Hc,Wc,3] (Hc,Wc multiples of 8) -> s0,s1,s2 [B,Hc/8,Wc/8,21] (any may be NULL). */
+H3D_API int h3d_posenet_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, int Wc,
+                        float* s0, float* s1, float* s2, void* stream);
+
+/* ColorHandPose3DNetwork._inference_pose3d (nets/ColorHandPose3DNetwork.py:221-247) and the
+ * PosePriorNetwork variants (nets/PosePriorNetwork.py:64-93, H3D_VARIANT_*).
+ * scoremap [B,32,32,21], hand_side [B,2] -> coord_xyz_rel_normed [B,21,3]; optional coord_can [B,21,3],
+ * rot_mat [B,3,3] (NULL to skip; rot_mat is only written for H3D_VARIANT_PROPOSED). */
+H3D_API int h3d_lifting_forward(h3d_ctx* ctx, const float* scoremap32, const float* hand_side, int B, int variant,
+                        float* coord_xyz_rel_normed, float* coord_can, float* rot_mat, void* stream);
+
+/* ColorHandPose3DNetwork.inference / inference2d (nets/ColorHandPose3DNetwork.py:61-129), plus
+ * detect_keypoints (utils/general.py:331-344) on device.  with_pose3d == 0 -> inference2d (hand_side,
+ * keypoint_coord3d may be NULL).  force_center/force_scale non-NULL: teacher-forced crop parameters.
+ * Outputs (device, caller-owned, any of the large ones may be NULL to skip the copy-out):
+ *   hand_scoremap [B,H,W,2], image_crop [B,256,256,3], scale_crop [B,1], center [B,2],
+ *   keypoints_scoremap [B,256,256,21], keypoint_coord3d [B,21,3], keypoints_uv [B,21,2] int32 (row,col),
+ *   hand_mask [B,H,W] uint8 (optional). */
+H3D_API int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_side, int B, int H, int W,
+                         int with_pose3d, const float* force_center, const float* force_scale,
+                         float* hand_scoremap, float* image_crop, float* scale_crop, float* center,
+                         float* keypoints_scoremap, float* keypoint_coord3d, int32_t* keypoints_uv,
+                         uint8_t* hand_mask, void* stream);
+
+/* ---- operator entry points (utils/general.py) ------------------------------------------------- */
+/* NetworkOps.conv / conv_relu (utils/general.py:36-59): tf.nn.conv2d SAME + bias (+ leaky 0.01).
+ * fp32 CUDA-core kernel; x [B,H,W,Cin], w HWIO [k,k,Cin,Cout] (device), y [B,ceil(H/s),ceil(W/s),Cout]. */
+H3D_API int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const float* bias, float* y,
+                   int B, int H, int W, int Cin, int Cout, int ksize, int stride, int leaky, void* stream);
+/* Same op on the tcgen05 tensor-core path (stride 1, Cin and Cout multiples of 64 after internal padding;
+ * ksize in {1,3,7}); host_w_hwio / host_bias are HOST pointers (packed per call: test / tuning entry). */
+H3D_API int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y,
+                  int B, int H, int W, int Cin, int Cout, int ksize, int leaky, int precision, void* stream);
+/* NetworkOps.max_pool (utils/general.py:62-65): 2x2 / 2 VALID. */
+H3D_API int h3d_maxpool2x2_f32(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, void* stream);
+/* NetworkOps.fully_connected(_relu) (utils/general.py:113-136): y = x[B,in] @ w[in,out] + b. */
+H3D_API int h3d_fully_connected_f32(h3d_ctx* ctx, const float* x, const float* w, const float* bias, float* y,
+                            int B, int in_features, int out_features, int leaky, void* stream);
+/* tf.image.resize_images bilinear, align_corners=False, TF1 legacy (nets/...:97,128,166). */
+H3D_API int h3d_resize_bilinear_tf1(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C,
+                            int out_h, int out_w, void* stream);
+/* tf.nn.avg_pool 8x8/8 (nets/PosePriorNetwork.py:61). */
+H3D_API int h3d_avgpool8(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, void* stream);
+/* single_obj_scoremap + calc_center_bb + crop-scale glue (utils/general.py:233-328,
+ * nets/ColorHandPose3DNetwork.py:83-85).  logits [B,H,W,2] -> hand_mask [B,H,W] uint8 (optional),
+ * max_loc [B,2] int32 (optional, find_max_location), center [B,2], crop_size [B,1] (raw, optional),
+ * scale_crop [B,1].  H,W <= 512, W % 32 == 0 not required. */
+H3D_API int h3d_seg_postprocess(h3d_ctx* ctx, const float* logits, int B, int H, int W, uint8_t* hand_mask,
+                        int32_t* max_loc, float* center, float* crop_size, float* scale_crop, void* stream);
+/* crop_image_from_xy (utils/general.py:163-196) incl. tf.image.crop_and_resize bilinear/extrapolation 0. */
+H3D_API int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float* center, const float* scale,
+                           float* image_crop, int B, int H, int W, int C, int crop_size, void* stream);
+/* detect_keypoints (utils/general.py:331-344), batched: scoremaps [B,H,W,C] -> [B,C,2] int32 (row,col),
+ * first occurrence of the maximum in row-major order. */
+H3D_API int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int C,
+                         int32_t* keypoints_uv, void* stream);
+/* _get_rot_mat + _flip_right_hand + matmul (nets/ColorHandPose3DNetwork.py:239-247,311-384). */
+H3D_API int h3d_rotate_canonical(h3d_ctx* ctx, const float* coord_can, const float* uxyz, const float* hand_side,
+                         int B, float* rot_mat, float* coord_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAND3D_B200_H_ */

@@ -1,0 +1,27 @@
+#!/bin/bash
+# Runs on the GPU box (gpurun): every stage in its own process under a timeout, logs into gpurun_out/.
+# usage: scripts/gpu_check.sh [stage ...]   stages: ops tc pipe bench ncu
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+export PYTHONPATH=$PWD
+STAGES="${@:-ops tc pipe bench}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+for s in $STAGES; do
+  case $s in
+    ops)   timeout 600 python -m pytest tests/test_gpu_ops.py -q -m gpu --timeout 300 > gpurun_out/ops.log 2>&1; echo "ops rc=$?" ;;
+    tc)    timeout 900 python -m pytest tests/test_gpu_tc_conv.py -q -m gpu --timeout 300 > gpurun_out/tc.log 2>&1; echo "tc rc=$?" ;;
+    pipe)  timeout 1500 python -m pytest tests/test_gpu_pipeline.py -q -m gpu --timeout 600 > gpurun_out/pipe.log 2>&1; echo "pipe rc=$?" ;;
+    smoke) timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
+    bench) for p in ${BENCH_PRECS:-bf16x3 fp16 fp32_ffma}; do
+             timeout 900 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 --precision $p --no-cpu-baseline > gpurun_out/bench_$p.json 2> gpurun_out/bench_$p.err; echo "bench $p rc=$?"
+           done ;;
+    benchfull) timeout 1200 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "benchfull rc=$?" ;;
+    ref)   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?" ;;
+    ncu)   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+             python bench.py --steps 1 --warmup 3 --batch ${NCU_BATCH:-8} --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?" ;;
+    ncufull) timeout 1500 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-3} -o gpurun_out/prof_tc -f \
+             python bench.py --steps 1 --warmup 3 --batch ${NCU_BATCH:-8} --no-cpu-baseline > gpurun_out/ncufull.log 2>&1; echo "ncufull rc=$?" ;;
+  esac
+done
+tail -n 25 gpurun_out/*.log 2>/dev/null | tail -n 120
+cat gpurun_out/bench_*.json 2>/dev/null

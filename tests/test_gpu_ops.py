@@ -1,0 +1,161 @@
+"""GPU parity of the HBM-bound / CUDA-core operators against the oracle (through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hand3d_oracle as O
+from oracle import tf1_ops as T
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from hand3d_b200 import runtime
+    return runtime.default_context()
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _smooth_logits(rng, B, H, W, amp=3.0, bias=-1.0):
+    low = rng.normal(size=(B, H // 8, W // 8, 2)).astype(f32) * amp
+    low[..., 1] += bias
+    return T.resize_bilinear_tf1(low, H, W)
+
+
+@pytest.mark.parametrize("shape,out", [((2, 40, 40, 2), (320, 320)), ((2, 32, 32, 21), (256, 256)), ((1, 30, 40, 2), (240, 320)),
+                                       ((1, 12, 10, 3), (30, 17)), ((1, 48, 64, 5), (24, 32)), ((1, 8, 8, 1), (8, 8))])
+def test_resize_bilinear_bit_exact(ctx, shape, out):
+    x = np.random.default_rng(0).normal(size=shape).astype(f32)
+    y = ctx.resize_bilinear(_dev(x), *out).cpu().numpy()
+    np.testing.assert_array_equal(y, T.resize_bilinear_tf1(x, *out))
+
+
+@pytest.mark.parametrize("C", [64, 21])
+def test_maxpool(ctx, C):
+    x = np.random.default_rng(1).normal(size=(2, 16, 24, C)).astype(f32)
+    np.testing.assert_array_equal(ctx.max_pool(_dev(x)).cpu().numpy(), T.max_pool_2x2(x))
+
+
+def test_avgpool8(ctx):
+    x = np.random.default_rng(2).normal(size=(2, 256, 256, 21)).astype(f32)
+    np.testing.assert_allclose(ctx.avg_pool8(_dev(x)).cpu().numpy(), T.avg_pool_8x8(x), atol=1e-6)
+
+
+@pytest.mark.parametrize("H,W,seed", [(320, 320, 0), (240, 320, 1), (320, 320, 2), (64, 96, 3), (320, 320, 4)])
+def test_seg_postprocess_matches_oracle(ctx, H, W, seed):
+    rng = np.random.default_rng(seed)
+    B = 4
+    sm = _smooth_logits(rng, B, H, W, amp=2.0 + seed, bias=-1.5)
+    if seed == 4:
+        sm[1, ..., 1] = -50.0          # empty mask -> (160,160)/100 fallbacks
+        sm[2, ..., 1] = 50.0           # saturated soft-max: seed = first pixel, mask = everything
+    r = ctx.seg_postprocess(_dev(sm))
+    fg, det = O.seg_fg_det(sm)
+    mask = O.single_obj_scoremap(sm, literal=False)
+    center, _, size = O.calc_center_bb(mask)
+    np.testing.assert_array_equal(r["max_loc"].cpu().numpy(), O.find_max_location(fg))
+    np.testing.assert_array_equal(r["hand_mask"].cpu().numpy(), mask[..., 0].astype(np.uint8))
+    np.testing.assert_array_equal(r["center"].cpu().numpy(), center)
+    np.testing.assert_array_equal(r["crop_size"].cpu().numpy(), size)
+    np.testing.assert_array_equal(r["scale_crop"].cpu().numpy(), O.crop_scale(size))
+
+
+def test_seg_postprocess_needs_all_32_passes(ctx):
+    H = W = 320
+    sm = np.zeros((1, H, W, 2), f32); sm[..., 0] = 5.0
+    sm[0, 7, :, 1] = 10.0; sm[0, 7, 0, 1] = 11.0           # 1-px line: grows 10 px per pass
+    sm[0, 7:300, 319, 1] = 10.0                             # continues down the right edge: not fully reachable in 32 passes
+    r = ctx.seg_postprocess(_dev(sm))
+    mask = O.single_obj_scoremap(sm, literal=False)
+    np.testing.assert_array_equal(r["hand_mask"].cpu().numpy(), mask[..., 0].astype(np.uint8))
+    assert 0 < mask.sum() < (sm[..., 1] > 5).sum()          # the pass limit really truncated the growth
+
+
+@pytest.mark.parametrize("H,W", [(320, 320), (240, 320)])
+def test_crop_image_from_xy(ctx, H, W):
+    rng = np.random.default_rng(5)
+    B = 6
+    img = rng.uniform(-0.5, 0.5, size=(B, H, W, 3)).astype(f32)
+    center = np.stack([rng.uniform(-20, H + 20, B), rng.uniform(-20, W + 20, B)], 1).astype(f32)
+    scale = np.array([0.25, 0.64, 1.0, 2.048, 5.0, 1.7], f32).reshape(B, 1)
+    out = ctx.crop_image_from_xy(_dev(img), _dev(center), 256, _dev(scale)).cpu().numpy()
+    ref = O.crop_image_from_xy(img, center, 256, scale)
+    np.testing.assert_array_equal(out, ref)
+
+
+def test_detect_keypoints_first_occurrence(ctx):
+    rng = np.random.default_rng(6)
+    s = rng.normal(size=(3, 256, 256, 21)).astype(f32)
+    s[0, 10, 20, 3] = 9.0; s[0, 200, 5, 3] = 9.0          # duplicate maximum: the first one wins
+    s[1, :, :, 7] = -1.0                                   # constant map -> (0,0)
+    uv = ctx.detect_keypoints(_dev(s)).cpu().numpy()
+    for b in range(3):
+        np.testing.assert_array_equal(uv[b], O.detect_keypoints(s[b]).astype(np.int32))
+    from hand3d_b200.utils.general import detect_keypoints
+    kp = detect_keypoints(s[2])
+    assert kp.dtype == np.float64
+    np.testing.assert_array_equal(kp, O.detect_keypoints(s[2]))
+
+
+CONV_CASES = [  # B,H,W,Cin,Cout,k,stride
+    (2, 32, 32, 3, 64, 3, 1), (1, 17, 23, 21, 32, 3, 1), (2, 32, 32, 32, 32, 3, 2), (1, 16, 16, 64, 64, 3, 2),
+    (1, 8, 8, 128, 256, 3, 1), (2, 16, 16, 512, 2, 1, 1), (1, 16, 16, 128, 21, 1, 1), (1, 12, 12, 149, 128, 7, 1),
+    (1, 9, 7, 16, 8, 3, 2), (1, 40, 40, 64, 128, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_f32_vs_oracle(ctx, case):
+    B, H, W, Cin, Cout, k, s = case
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=(B, H, W, Cin)).astype(f32)
+    w = (rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(f32)
+    b = rng.normal(size=Cout).astype(f32)
+    for leaky in (False, True):
+        y = ctx.conv2d(_dev(x), _dev(w), _dev(b), stride=s, leaky=leaky).cpu().numpy()
+        ref = T.conv2d_same(x, w, b, s, np.float64)
+        if leaky:
+            ref = T.leaky_relu(ref)
+        np.testing.assert_allclose(y, ref, atol=2e-5, rtol=1e-5)
+
+
+def test_fully_connected(ctx):
+    rng = np.random.default_rng(8)
+    for B, i, o in [(3, 2050, 512), (33, 512, 63), (5, 128, 3), (1, 4098, 256)]:
+        x = rng.normal(size=(B, i)).astype(f32); w = (rng.normal(size=(i, o)) / np.sqrt(i)).astype(f32); b = rng.normal(size=o).astype(f32)
+        y = ctx.fully_connected(_dev(x), _dev(w), _dev(b), leaky=True).cpu().numpy()
+        ref = T.fully_connected(x, w, b, np.float64)
+        np.testing.assert_allclose(y, np.maximum(ref, 0.01 * ref), atol=2e-5, rtol=1e-5)
+
+
+def test_rotate_canonical(ctx):
+    rng = np.random.default_rng(9)
+    B = 7
+    can = rng.normal(size=(B, 21, 3)).astype(f32)
+    u = rng.normal(size=(B, 3)).astype(f32); u[0] = 0.0
+    hs = np.zeros((B, 2), f32); hs[np.arange(B), rng.integers(0, 2, B)] = 1
+    rot, out = ctx.rotate_canonical(_dev(can), _dev(u), _dev(hs))
+    R = O.get_rot_mat(u[:, 0:1], u[:, 1:2], u[:, 2:3])
+    np.testing.assert_allclose(rot.cpu().numpy(), R, atol=2e-6)
+    np.testing.assert_allclose(out.cpu().numpy(), np.matmul(O.flip_right_hand(can, hs), R), atol=1e-5)
+
+
+def test_network_ops_mirror(ctx):
+    """NetworkOps.conv_relu / max_pool / fully_connected_relu with tf-style variable scopes."""
+    from hand3d_b200 import weights as Wt
+    from hand3d_b200.utils.general import NetworkOps as ops, variable_scope
+    wd = Wt.synthetic_weights(0)
+    ctx.load_weights({k: v for k, v in wd.items() if k.startswith("PosePrior/")})
+    x = np.random.default_rng(10).normal(size=(2, 32, 32, 21)).astype(f32)
+    with variable_scope("PosePrior"):
+        y = ops.conv_relu(_dev(x), "conv_pose_0_1", kernel_size=3, stride=1, out_chan=32)
+        y = ops.conv_relu(y, "conv_pose_0_2", kernel_size=3, stride=2, out_chan=32)
+        p = ops.max_pool(y)
+    r = T.conv_relu(x, wd["PosePrior/conv_pose_0_1/weights"], wd["PosePrior/conv_pose_0_1/biases"], 1)
+    r = T.conv_relu(r, wd["PosePrior/conv_pose_0_2/weights"], wd["PosePrior/conv_pose_0_2/biases"], 2)
+    np.testing.assert_allclose(y.cpu().numpy(), r, atol=1e-5)
+    np.testing.assert_allclose(p.cpu().numpy(), T.max_pool_2x2(r), atol=1e-5)
