@@ -251,7 +251,8 @@ static void layout(h3d_ctx::Layout& L, char* base, int B, int H, int W) {
     a.off += 2 * align_up((int64_t)B * Hc * Wc * 64 * 4, 1024) + 2 * align_up((int64_t)B * (Hc / 8) * (Wc / 8) * 192 * 4, 1024) +
              align_up((int64_t)B * (Hc / 8) * (Wc / 8) * 512 * 4, 1024) + 8192;
     a.off = align_up(a.off, 1024); L.lift_off = a.off;
-    a.off += 2 * align_up((int64_t)B * 32 * 32 * 64 * 4, 1024) + 4 * align_up((int64_t)B * 4100 * 4, 1024) + 16384;
+    a.off += 2 * align_up((int64_t)B * 32 * 32 * 64 * 4, 1024) + 4 * align_up((int64_t)B * 4100 * 4, 1024) +
+             align_up(fc_scratch_floats(B, 4098, 512) * 4, 1024) + align_up(kConvSplitKScratchFloats * 4, 1024) + 16384;
     L.total = align_up(a.off, 1024);
 }
 
@@ -290,7 +291,7 @@ static void tag(StagePlan* pl, int kind, int64_t flops) {
 
 static int add_direct(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec& l, int B, int H, int W,
                       const float* x /*null -> Ext.in*/, int Cin_total, int cin_off, float* y, int Cout_total, int cout_off,
-                      Split ys, int Cs_total, int cs_off) {
+                      Split ys, int Cs_total, int cs_off, float* splitk_scratch = nullptr) {
     const float *w, *b;
     int rc;
     if ((rc = dev_weight(ctx, scope + "/" + l.name + "/weights", &w))) return rc;
@@ -299,6 +300,7 @@ static int add_direct(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, con
     a.x = x; a.Cin_total = Cin_total; a.cin_off = cin_off; a.w = w; a.bias = b; a.y = y; a.Cout_total = Cout_total; a.cout_off = cout_off;
     a.ys = ys; a.Cs_total = Cs_total; a.cs_off = cs_off; a.half = half_of(ctx->precision);
     a.B = B; a.H = H; a.W = W; a.Cin = l.cin; a.Cout = l.cout; a.k = l.k; a.stride = l.stride; a.leaky = l.leaky;
+    a.splitk_scratch = splitk_scratch; a.splitk_scratch_floats = splitk_scratch ? kConvSplitKScratchFloats : 0;
     pl->steps.push_back([a](const Ext& e, cudaStream_t s) {
         DirectConvArgs aa = a;
         if (!aa.x) aa.x = e.in;
@@ -313,7 +315,7 @@ static int add_direct(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, con
 
 static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec& l, int B, int H, int W, Split x,
                   int Cin_total, int Cin_pad, const std::vector<int>& perm, Split y, int Cy_total, int cy_off, float* yf,
-                  int Cyf_total, int cyf_off) {
+                  int Cyf_total, int cyf_off, int pool = 0) {
     const PackedW* pw;
     int rc = get_packed(ctx, scope, l, Cin_pad, perm, &pw);
     if (rc) return rc;
@@ -321,6 +323,7 @@ static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const L
     d.x = x; d.Cin_total = Cin_total; d.Cin_pad = Cin_pad; d.w = pw->w; d.bias = pw->bias; d.Cout = l.cout; d.Cout_pad = pw->Cout_pad;
     d.y = y; d.Cy_total = Cy_total; d.cy_off = cy_off; d.yf = yf; d.Cyf_total = Cyf_total; d.cyf_off = cyf_off;
     d.B = B; d.H = H; d.W = W; d.k = l.k; d.leaky = l.leaky; d.passes = passes_of(ctx->precision); d.half = half_of(ctx->precision);
+    d.pool = pool;
     TcConvPlan* tp = tc_conv_plan_create(d);
     if (!tp) return H3D_ECUDA;
     pl->tc.push_back(tp);
@@ -349,8 +352,10 @@ static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, co
         Act out = last_layer ? *final_override : slot_view(slots[cur], slot_elems, l.cout, tc, lo);
         const bool use_tc = tc && l.cin % 64 == 0 && l.cout % 64 == 0 && l.stride == 1;
         const int c_off = last_layer ? final_c_off : 0;
+        const bool pool_after = !strcmp(l.name, "conv1_2") || !strcmp(l.name, "conv2_2") || !strcmp(l.name, "conv3_4");
+        const bool fuse_pool = use_tc && pool_after && (h % 2 == 0) && (w % 2 == 0) && !getenv("H3D_NO_POOL_FUSION");
         if (use_tc) {
-            rc = add_tc(ctx, pl, scope, l, B, h, w, in.s, in.C, l.cin, {}, out.s, out.C, c_off, nullptr, 0, 0);
+            rc = add_tc(ctx, pl, scope, l, B, h, w, in.s, in.C, l.cin, {}, out.s, out.C, c_off, nullptr, 0, 0, fuse_pool ? 1 : 0);
         } else if (tc) {   // first layer (Cin = 3): CUDA-core conv writing the split planes directly
             rc = add_direct(ctx, pl, scope, l, B, h, w, in.f, i == 0 ? l.cin : in.C, 0, nullptr, 0, 0, out.s, out.C, c_off);
         } else {
@@ -358,7 +363,8 @@ static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, co
         }
         if (rc) return rc;
         in = out; cur ^= 1;
-        if (!strcmp(l.name, "conv1_2") || !strcmp(l.name, "conv2_2") || !strcmp(l.name, "conv3_4")) {
+        if (fuse_pool) { h /= 2; w /= 2; }
+        else if (pool_after) {
             Act pooled = slot_view(slots[cur], slot_elems, l.cout, tc, lo);
             const Act src = in;
             const int hh = h, ww = w, cc = l.cout;
@@ -487,13 +493,13 @@ static int ensure_vp_heads(h3d_ctx* ctx) {
     return H3D_OK;
 }
 
-static int add_fc(h3d_ctx* ctx, StagePlan* pl, const std::string& name, const float* x, float* y, int B, int in_f, int out_f, int leaky) {
+static int add_fc(h3d_ctx* ctx, StagePlan* pl, const std::string& name, const float* x, float* y, float* scratch, int B, int in_f, int out_f, int leaky) {
     const float *w, *b;
     int rc;
     if ((rc = dev_weight(ctx, name + "/weights", &w))) return rc;
     if ((rc = dev_weight(ctx, name + "/biases", &b))) return rc;
-    pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_fc(x, w, b, y, B, in_f, out_f, leaky, in_f, s); });
-    pl->launches.push_back(1);
+    pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_fc(x, w, b, y, scratch, B, in_f, out_f, leaky, in_f, s); });
+    pl->launches.push_back(2);
     pl->flops += 2ll * B * in_f * out_f;
     tag(pl, KIND_FC, 2ll * B * in_f * out_f);
     return H3D_OK;
@@ -511,6 +517,8 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
     float* t3 = a.alloc<float>((int64_t)B * 64);
     float* can = a.alloc<float>((int64_t)B * 63);
     float* uxyz = a.alloc<float>((int64_t)B * 4);
+    float* fcs = a.alloc<float>(fc_scratch_floats(B, 4098, 512));   // upper bound over all FC layers of the stage
+    float* cvs = a.alloc<float>(kConvSplitKScratchFloats);
     int rc;
     auto pyramid = [&](const std::string& scope, const LayerSpec* L) -> int {
         int h = 32, w = 32;
@@ -518,7 +526,7 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
         const float* in = nullptr; int cin_total = 21;
         for (int i = 0; i < 6; ++i) {
             float* out = bufs[i & 1];
-            int rc2 = add_direct(ctx, pl.get(), scope, L[i], B, h, w, in, cin_total, 0, out, L[i].cout, 0, Split(), 0, 0);
+            int rc2 = add_direct(ctx, pl.get(), scope, L[i], B, h, w, in, cin_total, 0, out, L[i].cout, 0, Split(), 0, 0, cvs);
             if (rc2) return rc2;
             h = ceil_div(h, L[i].stride); w = ceil_div(w, L[i].stride);
             in = out; cin_total = L[i].cout;
@@ -529,19 +537,19 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
     if ((rc = pyramid("PosePrior", kPosePrior))) return rc;
     pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(bufB, e.hand_side, xcat, B, 2048, s); });
     pl->launches.push_back(1);
-    if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_rel0", xcat, t1, B, 2050, 512, 1))) return rc;
-    if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_rel1", t1, t2, B, 512, 512, 1))) return rc;
+    if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_rel0", xcat, t1, fcs, B, 2050, 512, 1))) return rc;
+    if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_rel1", t1, t2, fcs, B, 512, 512, 1))) return rc;
     const bool bott = variant == H3D_VARIANT_BOTTLENECK;
     auto xyz = ctx->host_w.find("PosePrior/fc_xyz/weights");
     if (xyz == ctx->host_w.end()) { set_error("weights PosePrior/fc_xyz not loaded"); return H3D_EWEIGHTS; }
     const int xyz_in = (int)xyz->second.shape[0];
     if (bott) {
         H3D_REQUIRE(xyz_in == 30, "bottleneck variant needs PosePrior/fc_xyz/weights of shape [30,63]");
-        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_bottleneck", t2, t3, B, 512, 30, 0))) return rc;
-        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", t3, can, B, 30, 63, 0))) return rc;
+        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_bottleneck", t2, t3, fcs, B, 512, 30, 0))) return rc;
+        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", t3, can, fcs, B, 30, 63, 0))) return rc;
     } else {
         H3D_REQUIRE(xyz_in == 512, "PosePrior/fc_xyz/weights must have shape [512,63] for this variant");
-        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", t2, can, B, 512, 63, 0))) return rc;
+        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", t2, can, fcs, B, 512, 63, 0))) return rc;
     }
     if (variant == H3D_VARIANT_PROPOSED) {
         // ViewpointNet (nets/ColorHandPose3DNetwork.py:274-309) + Rodrigues / flip / rotate (:239-247,311-334)
@@ -549,11 +557,12 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
         if ((rc = pyramid("ViewpointNet", kViewpoint))) return rc;
         pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(bufB, e.hand_side, xcat, B, 4096, s); });
         pl->launches.push_back(1);
-        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp0", xcat, t1, B, 4098, 256, 1))) return rc;
-        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp1", t1, t2, B, 256, 128, 1))) return rc;
+        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp0", xcat, t1, fcs, B, 4098, 256, 1))) return rc;
+        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp1", t1, t2, fcs, B, 256, 128, 1))) return rc;
         const float* hw = ctx->vp_head_w; const float* hb = ctx->vp_head_b;
-        pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_fc(t2, hw, hb, uxyz, B, 128, 3, 0, 128, s); });
-        pl->launches.push_back(1);
+        pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_fc(t2, hw, hb, uxyz, fcs, B, 128, 3, 0, 128, s); });
+        pl->launches.push_back(2);
+        tag(pl.get(), KIND_FC, 2ll * B * 128 * 3);
         pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
             if (e.out2) H3D_CUDA(cudaMemcpyAsync(e.out2, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
             return launch_rotate_canonical(can, uxyz, e.hand_side, B, e.out3, e.out, s);
@@ -836,8 +845,15 @@ int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const floa
     a.x = x; a.Cin_total = Cin; a.cin_off = 0; a.w = w_hwio; a.bias = bias; a.y = y; a.Cout_total = Cout; a.cout_off = 0;
     a.ys = Split(); a.Cs_total = 0; a.cs_off = 0; a.half = Half16::BF16;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = ksize; a.stride = stride; a.leaky = leaky;
+    float* scratch = nullptr;   // lets tiny layers take the split-K path exactly as the lifting stage does
+    const bool tiny = (int64_t)B * ceil_div(H, stride) * ceil_div(W, stride) <= 64 * 119;
+    if (tiny) {
+        H3D_CUDA(cudaMalloc(&scratch, (size_t)kConvSplitKScratchFloats * 4));
+        a.splitk_scratch = scratch; a.splitk_scratch_floats = kConvSplitKScratchFloats;
+    }
     int rc = launch_conv_direct(a, s);
     if (!rc) ctx->launches += 1;
+    if (tiny) { cudaStreamSynchronize(s); cudaFree(scratch); }
     return rc;
 }
 
@@ -890,8 +906,12 @@ int h3d_maxpool2x2_f32(h3d_ctx* ctx, const float* x, float* y, int B, int H, int
 int h3d_fully_connected_f32(h3d_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int in_features,
                             int out_features, int leaky, void* stream) {
     H3D_OP_PROLOGUE(ctx);
-    int rc = launch_fc(x, w, bias, y, B, in_features, out_features, leaky, in_features, s);
-    if (!rc) ctx->launches += 1;
+    float* scratch = nullptr;
+    H3D_CUDA(cudaMalloc(&scratch, (size_t)fc_scratch_floats(B, in_features, out_features) * 4));
+    int rc = launch_fc(x, w, bias, y, scratch, B, in_features, out_features, leaky, in_features, s);
+    if (!rc) ctx->launches += 2;
+    cudaStreamSynchronize(s);
+    cudaFree(scratch);
     return rc;
 }
 int h3d_resize_bilinear_tf1(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, int out_h, int out_w, void* stream) {

@@ -87,9 +87,14 @@ struct DirectConvArgs {
     int Cs_total, cs_off;
     Half16 half;
     int B, H, W, Cin, Cout, k, stride, leaky;
+    float* splitk_scratch = nullptr;        // optional: enables deterministic split-K for layers with too few tiles
+    int64_t splitk_scratch_floats = 0;
 };
+constexpr int64_t kConvSplitKScratchFloats = 296ll * 64 * 64;   // upper bound used by launch_conv_direct's split-K policy
 int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s);
-int launch_fc(const float* x, const float* w, const float* bias, float* y, int B, int in_f, int out_f, int leaky,
+// scratch: fc_scratch_floats(B, in_f, out_f) floats (split-K partial sums); two kernels per call
+int64_t fc_scratch_floats(int B, int in_f, int out_f);
+int launch_fc(const float* x, const float* w, const float* bias, float* y, float* scratch, int B, int in_f, int out_f, int leaky,
               int x_stride, cudaStream_t s);
 // gathers [conv_feat(b, :feat) , hand_side(b, :2)] -> xcat [B, feat+2]
 int launch_concat_handside(const float* feat, const float* hand_side, float* out, int B, int feat_n, cudaStream_t s);
@@ -112,6 +117,7 @@ struct TcConvDesc {
     int B, H, W, k, leaky;
     int passes;  // 1 or 3
     Half16 half;
+    int pool = 0;  // fuse the following 2x2/2 max-pool: outputs are [B, H/2, W/2, C]
 };
 TcConvPlan* tc_conv_plan_create(const TcConvDesc& d);   // nullptr on failure (h3d_last_error set)
 void tc_conv_plan_destroy(TcConvPlan* p);

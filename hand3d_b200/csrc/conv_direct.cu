@@ -27,6 +27,8 @@ struct ConvGeom {
     int B, H, W, Ho, Wo, Cin, Cout, k, stride, pad_t, pad_l;
     int Cin_total, cin_off, Cout_total, cout_off, Cs_total, cs_off;
     int leaky;
+    int k_per_split;     // reduction range handled by one blockIdx.z (multiple of KC); == Ktot when not split
+    float* partial;      // split-K: raw partial sums [gridDim.z][M][Cout]
 };
 
 // VEC: Cin % 16 == 0 and 16-byte aligned input channels -> one tap per K chunk, float4 gathers.
@@ -62,7 +64,8 @@ conv_direct_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int kk0 = 0; kk0 < Ktot; kk0 += KC) {
+    const int kk_begin = blockIdx.z * g.k_per_split, kk_end = min(Ktot, kk_begin + g.k_per_split);
+    for (int kk0 = kk_begin; kk0 < kk_end; kk0 += KC) {
         // ---- gather A chunk
         if (VEC) {
             const int tap = kk0 / g.Cin, c0 = kk0 - tap * g.Cin;
@@ -120,8 +123,19 @@ conv_direct_kernel(const float* __restrict__ x, const float* __restrict__ w, con
         __syncthreads();
     }
 
-    // ---- epilogue: bias + leaky ReLU, fp32 and / or split store
     const int nb = n0 + ty * 4;
+    if (g.partial) {   // split-K: raw partial sums, reduced (+ bias, activation) by conv_splitk_reduce_kernel
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t m = m0 + tx * 4 + i;
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (nb + j < g.Cout) g.partial[((int64_t)blockIdx.z * M + m) * g.Cout + nb + j] = acc[i][j];
+        }
+        return;
+    }
+    // ---- epilogue: bias + leaky ReLU, fp32 and / or split store
     float bvals[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bvals[j] = (nb + j < g.Cout) ? __ldg(bias + nb + j) : 0.f;
@@ -160,6 +174,113 @@ conv_direct_kernel(const float* __restrict__ x, const float* __restrict__ w, con
     }
 }
 
+__global__ void conv_splitk_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ y,
+                                          int64_t M, int Cout, int ksplit, int Cout_total, int cout_off, int leaky) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * Cout) return;
+    float v = 0.f;
+    for (int z = 0; z < ksplit; ++z) v += part[(int64_t)z * M * Cout + i];   // fixed order: deterministic
+    const int n = (int)(i % Cout);
+    v += __ldg(bias + n);
+    if (leaky) v = fmaxf(v, kNegSlope * v);
+    y[(i / Cout) * Cout_total + cout_off + n] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// First layers (HandSegNet/conv1_1, PoseNet2D/conv1_1): 3x3, Cin = 3, Cout = 64, stride 1.  K = 27 is too small
+// for the tensor pipe; the layer is bound by its 64-channel output write, so it runs on CUDA cores with
+// register tiling: one CTA = 8 x 32 output pixels, one warp = one image row of the tile, one thread =
+// 8 pixels x 8 output channels (64 accumulators).  Weights [27][64] and the haloed input tile live in shared
+// memory; all shared loads are 128-bit and warp-broadcast (8 lanes share an address), so the inner loop is
+// 192 FFMA per 10 LDS.128.  Stores: the 8 lanes of a pixel write 128 (split) / 256 (fp32) contiguous bytes.
+// ---------------------------------------------------------------------------------------------
+constexpr int C3_TH = 8, C3_TW = 32, C3_LD = 40;   // tile rows, tile cols, padded smem row (pixel x=-1 sits at index 3)
+
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                  uint16_t* __restrict__ yhi, uint16_t* __restrict__ ylo, int B, int H, int W, int Cy_total, int cy_off,
+                  int Cs_total, int cs_off, int leaky) {
+    __shared__ __align__(16) float ws[27][64];
+    __shared__ __align__(16) float xs[3][C3_TH + 2][C3_LD];
+    const int t = threadIdx.x;
+    const int tiles_w = (W + C3_TW - 1) / C3_TW, tiles_h = (H + C3_TH - 1) / C3_TH;
+    const int tile = blockIdx.x;
+    const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
+    const int x0 = tw * C3_TW, y0 = th * C3_TH;
+    for (int i = t; i < 27 * 64; i += 256) (&ws[0][0])[i] = __ldg(w + i);
+    for (int i = t; i < 3 * (C3_TH + 2) * C3_LD; i += 256) (&xs[0][0][0])[i] = 0.f;
+    __syncthreads();
+    const float* xb = x + (int64_t)b * H * W * 3;
+    for (int i = t; i < (C3_TH + 2) * (C3_TW + 2) * 3; i += 256) {
+        const int r = i / ((C3_TW + 2) * 3), rem = i - r * ((C3_TW + 2) * 3);
+        const int c = rem / 3, ci = rem - c * 3;
+        const int gy = y0 - 1 + r, gx = x0 - 1 + c;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) xs[ci][r][c + 3] = __ldg(xb + ((int64_t)gy * W + gx) * 3 + ci);
+    }
+    __syncthreads();
+    const int warp = t >> 5, lane = t & 31;
+    const int cg = lane & 7, pg = lane >> 3;      // 8 output channels [8cg, 8cg+8), 8 pixels [8pg, 8pg+8) of row `warp`
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+            float in[16];
+            const float4* src = reinterpret_cast<const float4*>(&xs[ci][warp + kh][pg * 8]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float4 v = src[q]; in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w; }
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&ws[(kh * 3 + kw) * 3 + ci][cg * 8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&ws[(kh * 3 + kw) * 3 + ci][cg * 8 + 4]);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float a = in[3 + i + kw];      // pixel 8pg + i, tap kw: x = 8pg + i + kw - 1 -> index 8pg + i + kw + 3
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a, wv[j], acc[i][j]);
+                }
+            }
+        }
+    }
+    float bv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + cg * 8 + j);
+    const int gy = y0 + warp;
+    if (gy >= H) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gx = x0 + pg * 8 + i;
+        if (gx >= W) continue;
+        const int64_t pix = ((int64_t)b * H + gy) * W + gx;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = acc[i][j] + bv[j];
+            if (leaky) v = fmaxf(v, kNegSlope * v);
+            o[j] = v;
+        }
+        if (y) {
+            float4* dst = reinterpret_cast<float4*>(y + pix * Cy_total + cy_off + cg * 8);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (yhi) {
+            uint16_t h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { h[j] = to_h16<FP16>(o[j]); l[j] = to_h16<FP16>(o[j] - from_h16<FP16>(h[j])); }
+            const int64_t off = pix * Cs_total + cs_off + cg * 8;
+            *reinterpret_cast<uint4*>(yhi + off) = *reinterpret_cast<const uint4*>(h);
+            if (ylo) *reinterpret_cast<uint4*>(ylo + off) = *reinterpret_cast<const uint4*>(l);
+        }
+    }
+}
+
 }  // namespace
 
 int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
@@ -172,7 +293,33 @@ int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
     g.Cin_total = a.Cin_total; g.cin_off = a.cin_off; g.Cout_total = a.Cout_total; g.cout_off = a.cout_off;
     g.Cs_total = a.Cs_total; g.cs_off = a.cs_off; g.leaky = a.leaky;
     const int64_t M = (int64_t)g.B * g.Ho * g.Wo;
+    if (a.Cin == 3 && a.Cin_total == 3 && a.cin_off == 0 && a.k == 3 && a.stride == 1 && a.Cout == 64 &&
+        (!a.y || ((a.Cout_total % 4) == 0 && (a.cout_off % 4) == 0)) && (!a.ys.hi || ((a.Cs_total % 8) == 0 && (a.cs_off % 8) == 0))) {
+        const int tiles = ceil_div(a.W, C3_TW) * ceil_div(a.H, C3_TH) * a.B;
+        if (a.half == Half16::FP16)
+            conv3x3_c3_kernel<true><<<tiles, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, a.B, a.H, a.W, a.Cout_total, a.cout_off, a.Cs_total, a.cs_off, a.leaky);
+        else
+            conv3x3_c3_kernel<false><<<tiles, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, a.B, a.H, a.W, a.Cout_total, a.cout_off, a.Cs_total, a.cs_off, a.leaky);
+        H3D_CHECK_LAUNCH();
+        return H3D_OK;
+    }
     dim3 grid((unsigned)ceil_div64(M, TM), (unsigned)ceil_div(a.Cout, TN));
+    const int Ktot = a.k * a.k * a.Cin;
+    g.k_per_split = (int)align_up(Ktot, KC);
+    g.partial = nullptr;
+    int ksplit = 1;
+    if (a.splitk_scratch && a.y && !a.ys.hi && (int)(grid.x * grid.y) < 120 && Ktot >= 256) {
+        // tiny spatial maps (the stride-2 lifting pyramids): too few tiles to fill 148 SMs -> split the reduction
+        ksplit = std::min(ceil_div(Ktot, 128), std::max(1, 296 / (int)(grid.x * grid.y)));
+        if (ksplit > 1 && (int64_t)ksplit * M * a.Cout <= a.splitk_scratch_floats) {
+            g.k_per_split = (int)align_up(ceil_div(Ktot, ksplit), KC);
+            ksplit = ceil_div(Ktot, g.k_per_split);
+            g.partial = a.splitk_scratch;
+            grid.z = ksplit;
+        } else {
+            ksplit = 1;
+        }
+    }
     const bool vec = (a.Cin % KC == 0) && (a.Cin_total % 4 == 0) && (a.cin_off % 4 == 0) && (((uintptr_t)a.x & 15) == 0);
     const bool fp16 = a.half == Half16::FP16;
 #define LAUNCH(V, F) conv_direct_kernel<V, F><<<grid, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, g)
@@ -180,57 +327,87 @@ int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
     else     { if (fp16) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
     H3D_CHECK_LAUNCH();
+    if (ksplit > 1) {
+        conv_splitk_reduce_kernel<<<(unsigned)ceil_div64(M * a.Cout, 256), 256, 0, s>>>(a.splitk_scratch, a.bias, a.y, M, a.Cout, ksplit,
+                                                                                 a.Cout_total, a.cout_off, a.leaky);
+        H3D_CHECK_LAUNCH();
+    }
     return H3D_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// NetworkOps.fully_connected(_relu): y = x @ W[in,out] + b (+ leaky).  16 batch rows x 64 outputs per
-// CTA; W is streamed once per batch tile with coalesced reads, x is staged in shared memory.
+// NetworkOps.fully_connected(_relu): y = x @ W[in,out] + b (+ leaky).  M = batch is tiny, so the op is a
+// weight-streaming problem: split-K over many CTAs (32 batch rows x 64 outputs x one K slice each, W read
+// with coalesced 256-byte rows exactly once per batch tile), partial sums to a scratch buffer, then a
+// fixed-order reduction + bias + leaky ReLU (deterministic: no floating-point atomics).
 // ---------------------------------------------------------------------------------------------
+constexpr int FCB = 32, FCN = 64, FCK = 32;
+
 __global__ void __launch_bounds__(256)
-fc_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
-          int B, int in_f, int out_f, int leaky, int x_stride) {
-    constexpr int FB = 16, FK = 64;
-    __shared__ float xs[FB][FK];
+fc_splitk_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ part, int B, int in_f, int out_f,
+                 int x_stride, int k_per_split) {
+    __shared__ float xs[FCB][FCK + 1];
     const int t = threadIdx.x;
-    const int n = blockIdx.x * 64 + (t & 63);
-    const int rb = (t >> 6) * 4;          // 4 batch rows per thread
-    const int b0 = blockIdx.y * FB;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < in_f; k0 += FK) {
-        for (int i = t; i < FB * FK; i += 256) {
-            const int r = i / FK, c = i - r * FK;
-            xs[r][c] = (b0 + r < B && k0 + c < in_f) ? x[(int64_t)(b0 + r) * x_stride + k0 + c] : 0.f;
+    const int n = blockIdx.x * FCN + (t & 63);
+    const int rb = (t >> 6) * 8;            // 8 batch rows per thread
+    const int b0 = blockIdx.z * FCB;
+    const int ks = blockIdx.y;
+    const int kbeg = ks * k_per_split, kend = min(in_f, kbeg + k_per_split);
+    float acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += FCK) {
+        for (int i = t; i < FCB * FCK; i += 256) {
+            const int r = i / FCK, c = i - r * FCK;
+            xs[r][c] = (b0 + r < B && k0 + c < kend) ? __ldg(x + (int64_t)(b0 + r) * x_stride + k0 + c) : 0.f;
         }
         __syncthreads();
         if (n < out_f) {
-            const int kmax = min(FK, in_f - k0);
+            const int kmax = min(FCK, kend - k0);
+#pragma unroll 8
             for (int k = 0; k < kmax; ++k) {
                 const float wv = __ldg(w + (int64_t)(k0 + k) * out_f + n);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) acc[r] = fmaf(xs[rb + r][k], wv, acc[r]);
+                for (int r = 0; r < 8; ++r) acc[r] = fmaf(xs[rb + r][k], wv, acc[r]);
             }
         }
         __syncthreads();
     }
     if (n < out_f) {
-        const float bv = __ldg(bias + n);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 8; ++r) {
             const int b = b0 + rb + r;
-            if (b < B) {
-                float v = acc[r] + bv;
-                if (leaky) v = fmaxf(v, kNegSlope * v);
-                y[(int64_t)b * out_f + n] = v;
-            }
+            if (b < B) part[((int64_t)ks * B + b) * out_f + n] = acc[r];
         }
     }
 }
 
-int launch_fc(const float* x, const float* w, const float* bias, float* y, int B, int in_f, int out_f, int leaky, int x_stride,
-              cudaStream_t s) {
-    dim3 grid(ceil_div(out_f, 64), ceil_div(B, 16));
-    fc_kernel<<<grid, 256, 0, s>>>(x, w, bias, y, B, in_f, out_f, leaky, x_stride);
+__global__ void fc_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ y, int B,
+                                 int out_f, int ksplit, int leaky) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * out_f) return;
+    float v = 0.f;
+    for (int ks = 0; ks < ksplit; ++ks) v += part[(int64_t)ks * B * out_f + i];   // fixed order
+    v += __ldg(bias + (i % out_f));
+    if (leaky) v = fmaxf(v, kNegSlope * v);
+    y[i] = v;
+}
+
+int fc_ksplit(int B, int in_f, int out_f) {
+    const int ctas = ceil_div(out_f, FCN) * ceil_div(B, FCB);
+    int ks = std::max(1, std::min(ceil_div(in_f, 64), 296 / std::max(1, ctas)));
+    return ks;
+}
+int64_t fc_scratch_floats(int B, int in_f, int out_f) { return (int64_t)fc_ksplit(B, in_f, out_f) * B * out_f; }
+
+int launch_fc(const float* x, const float* w, const float* bias, float* y, float* scratch, int B, int in_f, int out_f, int leaky,
+              int x_stride, cudaStream_t s) {
+    const int ksplit = fc_ksplit(B, in_f, out_f);
+    const int k_per_split = (int)align_up(ceil_div(in_f, ksplit), FCK);
+    dim3 grid(ceil_div(out_f, FCN), ksplit, ceil_div(B, FCB));
+    fc_splitk_kernel<<<grid, 256, 0, s>>>(x, w, scratch, B, in_f, out_f, x_stride, k_per_split);
+    H3D_CHECK_LAUNCH();
+    fc_reduce_kernel<<<ceil_div(B * out_f, 256), 256, 0, s>>>(scratch, bias, y, B, out_f, ksplit, leaky);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }

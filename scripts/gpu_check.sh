@@ -16,6 +16,7 @@ for s in $STAGES; do
              timeout 900 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 --precision $p --no-cpu-baseline > gpurun_out/bench_$p.json 2> gpurun_out/bench_$p.err; echo "bench $p rc=$?"
            done ;;
     benchfull) timeout 1200 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "benchfull rc=$?" ;;
+    errors) timeout 900 python scripts/debug_errors.py > gpurun_out/errors.log 2>&1; echo "errors rc=$?" ;;
     ref)   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?" ;;
     ncu)   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
              python bench.py --steps 1 --warmup 3 --batch ${NCU_BATCH:-8} --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?" ;;

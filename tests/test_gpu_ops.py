@@ -104,7 +104,7 @@ def test_detect_keypoints_first_occurrence(ctx):
 CONV_CASES = [  # B,H,W,Cin,Cout,k,stride
     (2, 32, 32, 3, 64, 3, 1), (1, 17, 23, 21, 32, 3, 1), (2, 32, 32, 32, 32, 3, 2), (1, 16, 16, 64, 64, 3, 2),
     (1, 8, 8, 128, 256, 3, 1), (2, 16, 16, 512, 2, 1, 1), (1, 16, 16, 128, 21, 1, 1), (1, 12, 12, 149, 128, 7, 1),
-    (1, 9, 7, 16, 8, 3, 2), (1, 40, 40, 64, 128, 3, 1),
+    (1, 9, 7, 16, 8, 3, 2), (1, 40, 40, 64, 128, 3, 1), (2, 19, 45, 3, 64, 3, 1), (3, 4, 4, 256, 256, 3, 1), (2, 8, 8, 128, 128, 3, 2),
 ]
 
 
