@@ -306,7 +306,7 @@ static int add_direct(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, con
         if (!aa.x) aa.x = e.in;
         return launch_conv_direct(aa, s);
     });
-    pl->launches.push_back(1);
+    pl->launches.push_back(conv_direct_num_launches(a));
     const int64_t fl = 2ll * B * ceil_div(H, l.stride) * ceil_div(W, l.stride) * l.k * l.k * l.cin * l.cout;
     pl->flops += fl;
     tag(pl, KIND_DIRECT, fl);
@@ -388,14 +388,18 @@ static int build_handsegnet(h3d_ctx* ctx, int B, int H, int W) {
     char* slot0 = r; char* slot1 = r + align_up(se * 4, 1024);
     Act last; int h, w, rc;
     if ((rc = build_trunk(ctx, pl.get(), "HandSegNet", kHandSeg, 14, B, H, W, slot0, slot1, se, &last, &h, &w, nullptr, 0))) return rc;
-    // conv6_1 (1x1, 128 -> 512, leaky) -> fp32; conv6_2 (1x1, 512 -> 2, linear) on CUDA cores
+    // conv6_1 (1x1, 128 -> 512, leaky) and the score-map head conv6_2 (1x1, 512 -> 2, linear; N padded to 64 on the tensor path)
     char* other = (last.f ? (char*)last.f : (char*)last.s.hi) == slot0 ? slot1 : slot0;
-    float* f512 = (float*)other;
-    if (tc) rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.s, last.C, 128, {}, Split(), 0, 0, f512, 512, 0);
-    else rc = add_direct(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.f, last.C, 0, f512, 512, 0, Split(), 0, 0);
-    if (rc) return rc;
     float* low = ctx->lay.seg_low;
-    if ((rc = add_direct(ctx, pl.get(), "HandSegNet", kHandSeg[15], B, h, w, f512, 512, 0, low, 2, 0, Split(), 0, 0))) return rc;
+    if (tc) {
+        Act mid = slot_view(other, (int64_t)B * h * w * 512, 512, true, passes_of(ctx->precision) == 3);
+        if ((rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.s, last.C, 128, {}, mid.s, 512, 0, nullptr, 0, 0))) return rc;
+        if ((rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[15], B, h, w, mid.s, 512, 512, {}, Split(), 0, 0, low, 2, 0))) return rc;
+    } else {
+        float* f512 = (float*)other;
+        if ((rc = add_direct(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.f, last.C, 0, f512, 512, 0, Split(), 0, 0))) return rc;
+        if ((rc = add_direct(ctx, pl.get(), "HandSegNet", kHandSeg[15], B, h, w, f512, 512, 0, low, 2, 0, Split(), 0, 0))) return rc;
+    }
     pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_resize_bilinear_tf1(low, e.out, B, h, w, 2, H, W, s); });
     pl->launches.push_back(1);
     ctx->seg = std::move(pl);
@@ -440,11 +444,14 @@ static int build_posenet(h3d_ctx* ctx, int B, int Hc, int Wc) {
         // 1x1 conv (cin6 -> 512 or 128, leaky) then 1x1 conv (-> 21, linear); score-map also fed back into the concat buffer
         LayerSpec l6{n6, 1, 1, 128, cin6, 1}, l7{n7, 1, 1, cin6, 21, 0};
         int rc2;
-        if (tc) rc2 = add_tc(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.s, in6.C, 128, {}, Split(), 0, 0, f512, cin6, 0);
-        else rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.f, in6.C, in6.f == cb.f ? 21 : 0, f512, cin6, 0, Split(), 0, 0);
-        if (rc2) return rc2;
-        if (tc) rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l7, B, h, w, f512, cin6, 0, sm_out, 21, 0, feed_back ? cb.s : Split(), 192, 128);
-        else rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l7, B, h, w, f512, cin6, 0, sm_out, 21, 0, Split(), 0, 0);
+        if (tc) {
+            Act mid = slot_view((char*)f512, pix * cin6, cin6, true, lo);
+            if ((rc2 = add_tc(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.s, in6.C, 128, {}, mid.s, cin6, 0, nullptr, 0, 0))) return rc2;
+            rc2 = add_tc(ctx, pl.get(), "PoseNet2D", l7, B, h, w, mid.s, cin6, cin6, {}, feed_back ? cb.s : Split(), 192, 128, sm_out, 21, 0);
+        } else {
+            if ((rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.f, in6.C, in6.f == cb.f ? 21 : 0, f512, cin6, 0, Split(), 0, 0))) return rc2;
+            rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l7, B, h, w, f512, cin6, 0, sm_out, 21, 0, Split(), 0, 0);
+        }
         if (rc2) return rc2;
         if (!tc && feed_back) {
             float* dst = cb.f;
@@ -846,7 +853,7 @@ int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const floa
     a.ys = Split(); a.Cs_total = 0; a.cs_off = 0; a.half = Half16::BF16;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = ksize; a.stride = stride; a.leaky = leaky;
     float* scratch = nullptr;   // lets tiny layers take the split-K path exactly as the lifting stage does
-    const bool tiny = (int64_t)B * ceil_div(H, stride) * ceil_div(W, stride) <= 64 * 119;
+    const bool tiny = (int64_t)B * ceil_div(H, stride) * ceil_div(W, stride) <= 64 * 295;
     if (tiny) {
         H3D_CUDA(cudaMalloc(&scratch, (size_t)kConvSplitKScratchFloats * 4));
         a.splitk_scratch = scratch; a.splitk_scratch_floats = kConvSplitKScratchFloats;

@@ -90,8 +90,9 @@ struct DirectConvArgs {
     float* splitk_scratch = nullptr;        // optional: enables deterministic split-K for layers with too few tiles
     int64_t splitk_scratch_floats = 0;
 };
-constexpr int64_t kConvSplitKScratchFloats = 296ll * 64 * 64;   // upper bound used by launch_conv_direct's split-K policy
+constexpr int64_t kConvSplitKScratchFloats = 600ll * 64 * 64;   // upper bound used by launch_conv_direct's split-K policy
 int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s);
+int conv_direct_num_launches(const DirectConvArgs& a);   // 1, or 2 when the split-K policy applies
 // scratch: fc_scratch_floats(B, in_f, out_f) floats (split-K partial sums); two kernels per call
 int64_t fc_scratch_floats(int B, int in_f, int out_f);
 int launch_fc(const float* x, const float* w, const float* bias, float* y, float* scratch, int B, int in_f, int out_f, int leaky,

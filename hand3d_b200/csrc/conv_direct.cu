@@ -283,9 +283,14 @@ conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 
 }  // namespace
 
-int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
-    H3D_REQUIRE(a.k >= 1 && a.stride >= 1 && a.Cin >= 1 && a.Cout >= 1, "conv_direct: bad geometry");
-    ConvGeom g;
+static bool is_c3_case(const DirectConvArgs& a) {
+    return a.Cin == 3 && a.Cin_total == 3 && a.cin_off == 0 && a.k == 3 && a.stride == 1 && a.Cout == 64 &&
+           (!a.y || ((a.Cout_total % 4) == 0 && (a.cout_off % 4) == 0)) && (!a.ys.hi || ((a.Cs_total % 8) == 0 && (a.cs_off % 8) == 0));
+}
+
+// Launch geometry + split-K policy shared by the launcher and by conv_direct_num_launches().
+static void plan_direct(const DirectConvArgs& a, ConvGeom* gp, dim3* gridp, int* ksplitp) {
+    ConvGeom& g = *gp;
     g.B = a.B; g.H = a.H; g.W = a.W; g.Cin = a.Cin; g.Cout = a.Cout; g.k = a.k; g.stride = a.stride;
     g.Ho = ceil_div(a.H, a.stride); g.Wo = ceil_div(a.W, a.stride);
     const int tot_h = std::max((g.Ho - 1) * a.stride + a.k - a.H, 0), tot_w = std::max((g.Wo - 1) * a.stride + a.k - a.W, 0);
@@ -293,8 +298,36 @@ int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
     g.Cin_total = a.Cin_total; g.cin_off = a.cin_off; g.Cout_total = a.Cout_total; g.cout_off = a.cout_off;
     g.Cs_total = a.Cs_total; g.cs_off = a.cs_off; g.leaky = a.leaky;
     const int64_t M = (int64_t)g.B * g.Ho * g.Wo;
-    if (a.Cin == 3 && a.Cin_total == 3 && a.cin_off == 0 && a.k == 3 && a.stride == 1 && a.Cout == 64 &&
-        (!a.y || ((a.Cout_total % 4) == 0 && (a.cout_off % 4) == 0)) && (!a.ys.hi || ((a.Cs_total % 8) == 0 && (a.cs_off % 8) == 0))) {
+    dim3 grid((unsigned)ceil_div64(M, TM), (unsigned)ceil_div(a.Cout, TN));
+    const int Ktot = a.k * a.k * a.Cin;
+    g.k_per_split = (int)align_up(Ktot, KC);
+    g.partial = nullptr;
+    int ksplit = 1;
+    const int ctas = (int)(grid.x * grid.y);
+    if (a.splitk_scratch && a.y && !a.ys.hi && ctas < 296 && Ktot >= 256) {
+        // tiny spatial maps (the stride-2 lifting pyramids): too few tiles to fill 148 SMs -> split the reduction
+        ksplit = std::min(ceil_div(Ktot, 128), std::max(1, 592 / ctas));
+        if (ksplit > 1 && (int64_t)ksplit * M * a.Cout <= a.splitk_scratch_floats) {
+            g.k_per_split = (int)align_up(ceil_div(Ktot, ksplit), KC);
+            ksplit = ceil_div(Ktot, g.k_per_split);
+            if (ksplit > 1) { g.partial = a.splitk_scratch; grid.z = ksplit; }
+        } else {
+            ksplit = 1;
+        }
+    }
+    *gridp = grid; *ksplitp = ksplit;
+}
+
+int conv_direct_num_launches(const DirectConvArgs& a) {
+    if (is_c3_case(a)) return 1;
+    ConvGeom g; dim3 grid; int ksplit;
+    plan_direct(a, &g, &grid, &ksplit);
+    return ksplit > 1 ? 2 : 1;
+}
+
+int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
+    H3D_REQUIRE(a.k >= 1 && a.stride >= 1 && a.Cin >= 1 && a.Cout >= 1, "conv_direct: bad geometry");
+    if (is_c3_case(a)) {
         const int tiles = ceil_div(a.W, C3_TW) * ceil_div(a.H, C3_TH) * a.B;
         if (a.half == Half16::FP16)
             conv3x3_c3_kernel<true><<<tiles, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, a.B, a.H, a.W, a.Cout_total, a.cout_off, a.Cs_total, a.cs_off, a.leaky);
@@ -303,23 +336,9 @@ int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
         H3D_CHECK_LAUNCH();
         return H3D_OK;
     }
-    dim3 grid((unsigned)ceil_div64(M, TM), (unsigned)ceil_div(a.Cout, TN));
-    const int Ktot = a.k * a.k * a.Cin;
-    g.k_per_split = (int)align_up(Ktot, KC);
-    g.partial = nullptr;
-    int ksplit = 1;
-    if (a.splitk_scratch && a.y && !a.ys.hi && (int)(grid.x * grid.y) < 120 && Ktot >= 256) {
-        // tiny spatial maps (the stride-2 lifting pyramids): too few tiles to fill 148 SMs -> split the reduction
-        ksplit = std::min(ceil_div(Ktot, 128), std::max(1, 296 / (int)(grid.x * grid.y)));
-        if (ksplit > 1 && (int64_t)ksplit * M * a.Cout <= a.splitk_scratch_floats) {
-            g.k_per_split = (int)align_up(ceil_div(Ktot, ksplit), KC);
-            ksplit = ceil_div(Ktot, g.k_per_split);
-            g.partial = a.splitk_scratch;
-            grid.z = ksplit;
-        } else {
-            ksplit = 1;
-        }
-    }
+    ConvGeom g; dim3 grid; int ksplit;
+    plan_direct(a, &g, &grid, &ksplit);
+    const int64_t M = (int64_t)g.B * g.Ho * g.Wo;
     const bool vec = (a.Cin % KC == 0) && (a.Cin_total % 4 == 0) && (a.cin_off % 4 == 0) && (((uintptr_t)a.x & 15) == 0);
     const bool fp16 = a.half == Half16::FP16;
 #define LAUNCH(V, F) conv_direct_kernel<V, F><<<grid, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, g)

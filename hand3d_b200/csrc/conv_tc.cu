@@ -48,6 +48,7 @@ struct TcParams {
     float* yf; int Cyf_total, cyf_off;
     int B, H, W, k, pad, cin_chunks;
     int TW, TH, TB, tiles_w, tiles_h, n_tiles, num_tiles;
+    int n_valid;    // number of real output channels (Cout); channels [n_valid, Cout_pad) are padding and never stored
     int pool;       // fuse NetworkOps.max_pool (2x2 / 2) into the epilogue: outputs are [B, H/2, W/2, C]
     int chunk_kb;   // K blocks accumulated inside the tensor core before the epilogue folds the partial sum into fp32 registers
     int leaky;
@@ -175,6 +176,31 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
         }
     }
     if (!valid) return;
+    if (n + 32 > p.n_valid) {   // score-map heads (Cout = 2 / 21 padded to 64): masked scalar tail
+        if (n >= p.n_valid) return;
+        const int cnt = p.n_valid - n;
+        if (p.yf) {
+            float* dst = p.yf + pix * p.Cyf_total + p.cyf_off + n;
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+                if (q < cnt) dst[q] = f[q];
+        }
+        if (p.y_hi) {
+            const int64_t off = pix * p.Cy_total + p.cy_off + n;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                if (q < cnt) {
+                    const uint32_t h2 = pack_hi2<FP16>(f[q], 0.f);
+                    p.y_hi[off + q] = (uint16_t)(h2 & 0xFFFFu);
+                    if (PASSES == 3 && p.y_lo) {
+                        const float2 r = unpack2<FP16>(h2);
+                        p.y_lo[off + q] = (uint16_t)(pack_hi2<FP16>(f[q] - r.x, 0.f) & 0xFFFFu);
+                    }
+                }
+            }
+        }
+        return;
+    }
     if (p.yf) {
         float4* dst = reinterpret_cast<float4*>(p.yf + pix * p.Cyf_total + p.cyf_off + n);
 #pragma unroll
@@ -479,8 +505,10 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
         set_error("tc_conv: unsupported geometry (Cin_pad=%d Cout_pad=%d k=%d passes=%d)", d.Cin_pad, d.Cout_pad, d.k, d.passes);
         return nullptr;
     }
+    const bool padded_out = d.Cout % 32 != 0;   // masked scalar tail in the epilogue: no alignment requirement there
     if (d.y.hi && ((d.Cy_total % 8) || (d.cy_off % 8))) { set_error("tc_conv: split output channel offset/stride must be multiples of 8"); return nullptr; }
-    if (d.yf && ((d.Cyf_total % 4) || (d.cyf_off % 4))) { set_error("tc_conv: fp32 output channel offset/stride must be multiples of 4"); return nullptr; }
+    if (d.yf && !padded_out && ((d.Cyf_total % 4) || (d.cyf_off % 4))) { set_error("tc_conv: fp32 output channel offset/stride must be multiples of 4"); return nullptr; }
+    if (padded_out && d.pool) { set_error("tc_conv: fused pooling needs Cout %% 32 == 0"); return nullptr; }
     if (d.passes == 3 && (!d.x.lo || !d.w.lo)) { set_error("tc_conv: 3-pass mode needs lo planes"); return nullptr; }
     TcConvPlan* pl = new TcConvPlan();
     pl->d = d;
@@ -504,6 +532,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     p.n_tiles = d.Cout_pad / BN;
     p.num_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
     p.leaky = d.leaky;
+    p.n_valid = d.Cout;
     p.pool = d.pool;
     p.err_flag = nullptr;
     // <= ~108 accumulating MMAs per TMEM partial sum (9 K blocks x 4 K steps x 3 passes); BN = 256 keeps everything in

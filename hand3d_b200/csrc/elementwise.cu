@@ -18,8 +18,11 @@ __device__ __forceinline__ float lerp_tf(float a, float b, float t) {
 // tf.image.resize_images bilinear, align_corners=False, legacy (nets/ColorHandPose3DNetwork.py:97,128,166)
 // One thread produces 4 consecutive floats of the flattened (ox, c) output row -> float4 stores.
 // =============================================================================================
+// CT > 0: channel count known at compile time (2 and 21 on the hot path) -> the per-element e / C becomes a multiply-shift.
+template <int CT>
 __global__ void resize_bilinear_tf1_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
-                                           int C, int oh, int ow, float hscale, float wscale) {
+                                           int C_rt, int oh, int ow, float hscale, float wscale) {
+    const int C = CT > 0 ? CT : C_rt;
     const int row_elems = ow * C;
     const int vec_per_row = (row_elems + 3) >> 2;
     const int64_t total = (int64_t)B * oh * vec_per_row;
@@ -72,7 +75,9 @@ int launch_resize_bilinear_tf1(const float* x, float* y, int B, int H, int W, in
     const int64_t total = (int64_t)B * oh * ((ow * C + 3) / 4);
     const int threads = 256;
     const int blocks = (int)std::min<int64_t>(ceil_div64(total, threads), 148 * 32);
-    resize_bilinear_tf1_kernel<<<blocks, threads, 0, s>>>(x, y, B, H, W, C, oh, ow, hscale, wscale);
+    if (C == 21) resize_bilinear_tf1_kernel<21><<<blocks, threads, 0, s>>>(x, y, B, H, W, C, oh, ow, hscale, wscale);
+    else if (C == 2) resize_bilinear_tf1_kernel<2><<<blocks, threads, 0, s>>>(x, y, B, H, W, C, oh, ow, hscale, wscale);
+    else resize_bilinear_tf1_kernel<0><<<blocks, threads, 0, s>>>(x, y, B, H, W, C, oh, ow, hscale, wscale);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }
