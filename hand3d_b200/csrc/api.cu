@@ -271,6 +271,20 @@ static int ensure_layout(h3d_ctx* ctx, int B, int H, int W) {
     return H3D_OK;
 }
 
+// A stage call fits the current layout when its batch and spatial sizes are covered by what layout(B,H,W) reserved
+// (HandSegNet slots for HxW, PoseNet slots for max(H,256) x max(W,256), lifting for B); otherwise the layout grows to
+// the element-wise maximum (which needs a workspace sized for it).
+static int ensure_layout_covers(h3d_ctx* ctx, int B, int segH, int segW, int poseH, int poseW) {
+    const h3d_ctx::Layout& L = ctx->lay;
+    const bool have = ctx->ws && L.hand_scoremap == (float*)ctx->ws && L.B > 0;
+    if (have && B <= L.B && segH <= L.H && segW <= L.W && poseH <= std::max(L.H, 256) && poseW <= std::max(L.W, 256)) return H3D_OK;
+    int nB = B, nH = std::max(segH, 8), nW = std::max(segW, 8);
+    if (poseH > 256) nH = std::max(nH, poseH);
+    if (poseW > 256) nW = std::max(nW, poseW);
+    if (have) { nB = std::max(nB, L.B); nH = std::max(nH, L.H); nW = std::max(nW, L.W); }
+    return ensure_layout(ctx, nB, nH, nW);
+}
+
 // ------------------------------------------------------------------------------------------ step builders
 struct Act {   // an activation tensor living in the workspace
     float* f = nullptr;   // fp32 view
@@ -764,7 +778,7 @@ int h3d_set_workspace(h3d_ctx* ctx, void* dev_ptr, int64_t bytes) {
 int h3d_handsegnet_forward(h3d_ctx* ctx, const float* image, int B, int H, int W, float* logits, void* stream) {
     H3D_REQUIRE(ctx && image && logits && B > 0, "h3d_handsegnet_forward: bad argument");
     int rc;
-    if ((rc = ensure_layout(ctx, std::max(B, ctx->lay.B), std::max(H, ctx->lay.H), std::max(W, ctx->lay.W)))) return rc;
+    if ((rc = ensure_layout_covers(ctx, B, H, W, 0, 0))) return rc;
     if (!ctx->seg || ctx->seg->B != B || ctx->seg->H != H || ctx->seg->W != W)
         if ((rc = build_handsegnet(ctx, B, H, W))) return rc;
     Ext e; e.in = image; e.out = logits;
@@ -774,7 +788,7 @@ int h3d_handsegnet_forward(h3d_ctx* ctx, const float* image, int B, int H, int W
 int h3d_posenet_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, int Wc, float* s0, float* s1, float* s2, void* stream) {
     H3D_REQUIRE(ctx && image_crop && B > 0, "h3d_posenet_forward: bad argument");
     int rc;
-    if ((rc = ensure_layout(ctx, std::max(B, ctx->lay.B), std::max(Hc, ctx->lay.H), std::max(Wc, ctx->lay.W)))) return rc;
+    if ((rc = ensure_layout_covers(ctx, B, 0, 0, Hc, Wc))) return rc;
     if (!ctx->pose || ctx->pose->B != B || ctx->pose->H != Hc || ctx->pose->W != Wc)
         if ((rc = build_posenet(ctx, B, Hc, Wc))) return rc;
     Ext e; e.in = image_crop;
@@ -791,7 +805,7 @@ int h3d_lifting_forward(h3d_ctx* ctx, const float* scoremap32, const float* hand
     H3D_REQUIRE(ctx && scoremap32 && hand_side && coord_xyz_rel_normed && B > 0, "h3d_lifting_forward: bad argument");
     H3D_REQUIRE(variant >= H3D_VARIANT_DIRECT && variant <= H3D_VARIANT_PROPOSED, "h3d_lifting_forward: unknown variant");
     int rc;
-    if ((rc = ensure_layout(ctx, std::max(B, ctx->lay.B), std::max(8, ctx->lay.H), std::max(8, ctx->lay.W)))) return rc;
+    if ((rc = ensure_layout_covers(ctx, B, 0, 0, 0, 0))) return rc;
     if (!ctx->lift || ctx->lift->B != B || ctx->lift->variant != variant)
         if ((rc = build_lifting(ctx, B, variant))) return rc;
     Ext e; e.in = scoremap32; e.hand_side = hand_side; e.out = coord_xyz_rel_normed; e.out2 = coord_can; e.out3 = rot_mat;
@@ -806,7 +820,7 @@ int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_sid
     H3D_REQUIRE(!with_pose3d || (hand_side && keypoint_coord3d), "h3d_pipeline_forward: hand_side / keypoint_coord3d required with pose3d");
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    if ((rc = ensure_layout(ctx, B, H, W))) return rc;
+    if ((rc = ensure_layout_covers(ctx, B, H, W, 256, 256))) return rc;
     h3d_ctx::Layout& L = ctx->lay;
     float* seg = hand_scoremap ? hand_scoremap : L.hand_scoremap;
     float* crop = image_crop ? image_crop : L.image_crop;

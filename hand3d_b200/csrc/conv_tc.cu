@@ -127,6 +127,47 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants.  Shared-window addresses of a CTA in a cluster carry the CTA rank; clearing the
+// peer bit (cute::Sm100MmaPeerBitMask) makes a TMA completion / arrive land on the EVEN CTA's barrier at the same offset.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* map, void* dst, uint64_t* leader_bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, void* dst, uint64_t* leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(leader_bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs (mask 0b11)
+__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version = 1, layout = SWIZZLE_128B (2).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -134,8 +175,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format f32 (bit 4), a/b format (bits 7, 10:
 // 0 = f16, 1 = bf16), K-major A and B (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc(int N, bool fp16) {
-    return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int N, bool fp16, int M = BM) {
+    return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 template <bool FP16>
@@ -405,6 +446,176 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair kernel
+// Same algorithm on a cluster of two CTAs (two SMs of one TPC) with tcgen05 cta_group::2: one UMMA covers M = 256 pixels
+// (CTA r owns pixel tile 2*pair + r and TMEM rows of it) x N = BN channels; each CTA stages its own A tile and HALF of the
+// B tile, so per MMA each SM reads half the shared-memory bytes of the single-CTA kernel (which is shared-memory-bandwidth
+// bound at M = N = 128: 8 KB of operands per 64-cycle MMA = the full 128 B/clk) and pulls half the bytes through L2.
+// Roles per CTA: warps 0-7 epilogue (lane quadrant = warp % 4, column half = warp / 4), warp 8 TMA producer, warp 9 MMA
+// issuer (leader CTA only) + TMEM allocation.  Barriers: full[s] lives in the leader and counts the bytes of both CTAs'
+// TMA loads; empty[s] / tmem_full[a] are signalled in both CTAs by multicast commits; tmem_empty[a] lives in the leader
+// and collects one arrive per epilogue warp of both CTAs.
+constexpr int kThreads2 = 32 * 10;
+__host__ __device__ constexpr int stage_bytes2(int BN, int PASSES) { return (PASSES == 3 ? 2 : 1) * (A_TILE_BYTES + (BN / 2) * BK * 2); }
+__host__ __device__ constexpr int num_stages2(int BN, int PASSES) {
+    return kSmemBudget / stage_bytes2(BN, PASSES) > 8 ? 8 : kSmemBudget / stage_bytes2(BN, PASSES);
+}
+
+template <int BN, int PASSES, bool FP16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+    constexpr int STAGES = num_stages2(BN, PASSES);
+    constexpr int STAGE_BYTES = stage_bytes2(BN, PASSES);
+    constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;
+    constexpr uint32_t IDESC = make_idesc(BN, FP16, 256);
+    constexpr int COLS = BN / 2;                       // accumulator columns drained by one epilogue warp
+    static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int kblocks = p.k * p.k * p.cin_chunks;
+
+    if (warp == 8 && lane == 0) {
+        prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w_hi);
+        if (PASSES == 3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();          // barriers of BOTH CTAs are initialised before any remote arrive / TMA completion
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ================================ TMA producer (both CTAs) ================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
+                const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * p.TW - p.pad, h0 = th * p.TH - p.pad, b0 = tb * p.TB, n0 = nt * BN + (int)rank * (BN / 2);
+                int kcol = 0;
+                for (int kh = 0; kh < p.k; ++kh) {
+                    for (int kw = 0; kw < p.k; ++kw) {
+                        for (int cc = 0; cc < p.cin_chunks; ++cc, kcol += BK) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+                            uint8_t* st = smem + stage * STAGE_BYTES;
+                            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
+                            tma_load_4d_2sm(&map_x_hi, st, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                            tma_load_2d_2sm(&map_w_hi, st + (PASSES == 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
+                            if (PASSES == 3) {
+                                tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                tma_load_2d_2sm(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
+                            }
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================================ MMA issuer (leader CTA) ================================
+        if (rank == 0 && lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc_it = 0;
+            for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
+                for (int kb0 = 0; kb0 < kblocks; kb0 += p.chunk_kb, ++acc_it) {
+                    const int acc = acc_it & 1;
+                    mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    const int kb1 = min(kblocks, kb0 + p.chunk_kb);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                        const uint64_t a_hi = make_smem_desc(sa);
+                        const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
+                        const uint64_t b_hi = make_smem_desc(sa + (PASSES == 3 ? 2 : 1) * A_TILE_BYTES);
+                        const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                        for (int j = 0; j < BK / UMMA_K; ++j) {
+                            const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                            tc_mma_f16_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC, (uint32_t)((kb > kb0) | (j != 0)));
+                            if (PASSES == 3) {
+                                tc_mma_f16_2cta(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
+                                tc_mma_f16_2cta(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+                            }
+                        }
+                        tc_commit_2cta(&empty_bar[stage]);   // frees this smem stage in both CTAs
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit_2cta(&tfull_bar[acc]);         // partial accumulator complete -> epilogues of both CTAs
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue (8 warps: lane quadrant q, column half ch) ================================
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;                       // tile row = TMEM lane
+        const int w_l = row % p.TW, h_l = (row / p.TW) % p.TH, b_l = row / (p.TW * p.TH);
+        int acc_it = 0;
+        for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
+            const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+            const int w = tw * p.TW + w_l, h = th * p.TH + h_l, b = tb * p.TB + b_l, n0 = nt * BN + ch * COLS;
+            bool valid = (w < p.W) && (h < p.H) && (b < p.B);
+            int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
+            if (p.pool) {
+                valid = valid && ((w & 1) == 0) && ((h & 1) == 0);
+                pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+            }
+            float racc[COLS];
+            for (int kb0 = 0; kb0 < kblocks; kb0 += p.chunk_kb, ++acc_it) {
+                const int acc = acc_it & 1;
+                mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, p.err_flag, 4);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * COLS);
+#pragma unroll
+                for (int c0 = 0; c0 < COLS; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld_32x32b_x32(taddr + c0, v);
+                    tc_wait_ld();
+                    if (kb0 == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) racc[c0 + i] = __uint_as_float(v[i]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) racc[c0 + i] += __uint_as_float(v[i]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // leader's barrier: 16 arrivals per phase
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < COLS; c0 += 32) epilogue_store32<PASSES, FP16>(p, &racc[c0], pix, n0 + c0, valid);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();          // nobody leaves (or frees TMEM) while the peer may still touch this CTA's smem / TMEM
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -469,6 +680,7 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s);
 }  // namespace
 
 struct TcConvPlan {
+    bool two_cta = false;
     TcConvDesc d;
     CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo;
     TcParams p;
@@ -500,6 +712,21 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s) {
 }
 }  // namespace
 
+namespace {
+template <int BN, int PASSES, bool FP16>
+int launch_inst2(const TcConvPlan* pl, cudaStream_t s) {
+    constexpr int smem = num_stages2(BN, PASSES) * stage_bytes2(BN, PASSES) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static bool attr = false;
+    if (!attr) {
+        H3D_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, PASSES, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    conv_tc2_kernel<BN, PASSES, FP16><<<pl->grid, kThreads2, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+}  // namespace
+
 TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if (d.Cin_pad % BK != 0 || d.Cout_pad % 64 != 0 || (d.k != 1 && d.k != 3 && d.k != 5 && d.k != 7) || (d.passes != 1 && d.passes != 3)) {
         set_error("tc_conv: unsupported geometry (Cin_pad=%d Cout_pad=%d k=%d passes=%d)", d.Cin_pad, d.Cout_pad, d.k, d.passes);
@@ -513,11 +740,15 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     TcConvPlan* pl = new TcConvPlan();
     pl->d = d;
     int BN = d.Cout_pad % 128 == 0 ? 128 : 64;
+    bool two = true;   // CTA-pair kernel by default (H3D_TC_2CTA=0 selects the single-CTA kernel)
+    if (const char* e = getenv("H3D_TC_2CTA")) two = atoi(e) != 0;
+    if (two) BN = d.Cout_pad % 256 == 0 ? 256 : (d.Cout_pad % 128 == 0 ? 128 : 64);   // CTA pair: UMMA 256 x BN
     if (const char* e = getenv("H3D_TC_BN")) {
         const int v = atoi(e);
         if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
     }
     pl->BN = BN;
+    pl->two_cta = two;
     int TW, TH, TB;
     if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool needs even H and W"); delete pl; return nullptr; }
     choose_tile(d.B, d.H, d.W, &TW, &TH, &TB, d.pool != 0);
@@ -531,6 +762,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     const int tiles_b = ceil_div(d.B, TB);
     p.n_tiles = d.Cout_pad / BN;
     p.num_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
+    if (two) p.num_tiles = ceil_div(p.tiles_w * p.tiles_h * tiles_b, 2) * p.n_tiles;   // work items = pixel-tile PAIRS x N tiles
     p.leaky = d.leaky;
     p.n_valid = d.Cout;
     p.pool = d.pool;
@@ -539,14 +771,15 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     // TMEM (its 256 fp32 partial sums per thread would not fit the register file)
     p.chunk_kb = d.passes == 3 ? 9 : 27;
     if (const char* e = getenv("H3D_TC_CHUNK_KB")) { const int v = atoi(e); if (v > 0) p.chunk_kb = v; }
-    if (BN > 128) p.chunk_kb = 1 << 30;
-    pl->grid = std::min(p.num_tiles, tc_num_sms());
+    if (BN > 128 && !two) p.chunk_kb = 1 << 30;
+    pl->grid = two ? 2 * std::min(p.num_tiles, tc_num_sms() / 2) : std::min(p.num_tiles, tc_num_sms());
+    const int w_box_rows = two ? BN / 2 : BN;
     const int Ktot = d.k * d.k * d.Cin_pad;
     bool ok = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB) &&
-              encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, BN);
+              encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, w_box_rows);
     if (ok && d.passes == 3)
         ok = encode_act_map(&pl->map_x_lo, d.x.lo, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB) &&
-             encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, BN);
+             encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, w_box_rows);
     if (ok && d.passes == 1) { pl->map_x_lo = pl->map_x_hi; pl->map_w_lo = pl->map_w_hi; }
     if (!ok) { delete pl; return nullptr; }
     return pl;
@@ -561,6 +794,15 @@ int64_t tc_conv_flops(const TcConvPlan* p) {
 int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
     const bool fp16 = pl->d.half == Half16::FP16;
     const int key = pl->BN * 10 + pl->d.passes;
+    if (pl->two_cta) {
+#define CASE2(BN_, P_)                                                                 \
+    case BN_ * 10 + P_:                                                                \
+        return fp16 ? launch_inst2<BN_, P_, true>(pl, s) : launch_inst2<BN_, P_, false>(pl, s);
+        switch (key) {
+            CASE2(64, 1) CASE2(64, 3) CASE2(128, 1) CASE2(128, 3) CASE2(256, 1) CASE2(256, 3)
+        }
+#undef CASE2
+    }
 #define CASE(BN_, P_)                                                                  \
     case BN_ * 10 + P_:                                                                \
         return fp16 ? launch_inst<BN_, P_, true>(pl, s) : launch_inst<BN_, P_, false>(pl, s);

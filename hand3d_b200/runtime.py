@@ -124,7 +124,7 @@ class Context:
     def posenet(self, image_crop):
         image_crop = _chk_f32(image_crop, "image_crop", 4)
         B, H, W, _ = image_crop.shape
-        self.ensure_workspace(B, H, W)
+        self.ensure_workspace(B, H if H > 256 else 8, W if W > 256 else 8)   # crops up to 256x256 fit every layout
         outs = [torch.empty((B, H // 8, W // 8, 21), dtype=torch.float32, device=image_crop.device) for _ in range(3)]
         _lib.check(self.lib.h3d_posenet_forward(self.h, _ptr(image_crop), B, H, W, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
                                                 _stream()), "h3d_posenet_forward")
