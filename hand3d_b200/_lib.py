@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libhand3d_b200.so")
 OK, EINVAL, ENODEVICE, ECUDA, EWEIGHTS, EWORKSPACE = 0, -1, -2, -3, -4, -5
 PREC_FP32_FFMA, PREC_BF16X3, PREC_FP16X3, PREC_FP16, PREC_BF16 = 0, 1, 2, 3, 4
 PRECISIONS = {"fp32_ffma": 0, "bf16x3": 1, "fp16x3": 2, "fp16": 3, "bf16": 4}
-VARIANTS = {"direct": 0, "bottleneck": 1, "proposed": 2}
+VARIANTS = {"direct": 0, "bottleneck": 1, "proposed": 2, "local": 3, "local_w_xyz_loss": 3}
 
 _p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -47,6 +47,7 @@ SIGNATURES = {
     "h3d_seg_postprocess": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "h3d_crop_image_from_xy": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "h3d_detect_keypoints": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "h3d_bone_rel_trafo_inv": (_i, [_p, _p, _p, _i, _p]),
     "h3d_rotate_canonical": (_i, [_p, _p, _p, _p, _i, _p, _p, _p]),
 }
 

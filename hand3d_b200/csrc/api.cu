@@ -589,6 +589,13 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
             return launch_rotate_canonical(can, uxyz, e.hand_side, B, e.out3, e.out, s);
         });
         pl->launches.push_back(1);
+    } else if (variant == H3D_VARIANT_LOCAL) {
+        // nets/PosePriorNetwork.py:70-75: the network predicts bone-relative coordinates; assemble xyz by forward kinematics
+        pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
+            if (e.out2) H3D_CUDA(cudaMemcpyAsync(e.out2, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
+            return launch_bone_rel_trafo_inv(can, e.out, B, s);
+        });
+        pl->launches.push_back(1);
     } else {
         pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
             H3D_CUDA(cudaMemcpyAsync(e.out, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
@@ -803,7 +810,7 @@ int h3d_posenet_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, in
 int h3d_lifting_forward(h3d_ctx* ctx, const float* scoremap32, const float* hand_side, int B, int variant,
                         float* coord_xyz_rel_normed, float* coord_can, float* rot_mat, void* stream) {
     H3D_REQUIRE(ctx && scoremap32 && hand_side && coord_xyz_rel_normed && B > 0, "h3d_lifting_forward: bad argument");
-    H3D_REQUIRE(variant >= H3D_VARIANT_DIRECT && variant <= H3D_VARIANT_PROPOSED, "h3d_lifting_forward: unknown variant");
+    H3D_REQUIRE(variant >= H3D_VARIANT_DIRECT && variant <= H3D_VARIANT_LOCAL, "h3d_lifting_forward: unknown variant");
     int rc;
     if ((rc = ensure_layout_covers(ctx, B, 0, 0, 0, 0))) return rc;
     if (!ctx->lift || ctx->lift->B != B || ctx->lift->variant != variant)
@@ -976,6 +983,13 @@ int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int
     ctx->launches += nl;
     cudaStreamSynchronize(s);
     cudaFree(scratch);
+    return rc;
+}
+int h3d_bone_rel_trafo_inv(h3d_ctx* ctx, const float* coords_rel, float* coords_xyz, int B, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(coords_rel && coords_xyz && B > 0, "h3d_bone_rel_trafo_inv: bad argument");
+    int rc = launch_bone_rel_trafo_inv(coords_rel, coords_xyz, B, s);
+    if (!rc) ctx->launches += 1;
     return rc;
 }
 int h3d_rotate_canonical(h3d_ctx* ctx, const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot_mat,

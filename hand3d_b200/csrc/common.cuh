@@ -72,6 +72,7 @@ int launch_detect_keypoints(const float* sm, int B, int H, int W, int C, void* s
                             int* n_launch);
 // dst[r, dst_off + c] = src[r, c] for c < C (fp32 channel copy into a wider NHWC tensor)
 int launch_copy_channels(const float* src, float* dst, int64_t rows, int C, int dst_total, int dst_off, cudaStream_t s);
+int launch_bone_rel_trafo_inv(const float* rel, float* xyz, int B, cudaStream_t s);
 int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot,
                             float* out, cudaStream_t s);
 

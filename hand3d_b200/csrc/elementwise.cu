@@ -631,6 +631,48 @@ __global__ void rotate_canonical_kernel(const float* __restrict__ can, const flo
     }
 }
 
+// =============================================================================================
+// bone_rel_trafo_inv (utils/relative_trafo.py:243-295): forward kinematics over the 21-node hand chain.
+// One thread per (sample, chain): the root key-point and the 5 fingers are independent chains of rigid
+// transforms T <- Trans_z(-len) RotX(-ax) RotY(-ay) T; the key-point is inv(T) [0,0,0,1]^T = -R^T t.
+// =============================================================================================
+__global__ void bone_rel_trafo_inv_kernel(const float* __restrict__ rel, float* __restrict__ xyz, int B) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * 6) return;
+    const int b = idx / 6, c = idx - b * 6;
+    float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+    const int n = c == 0 ? 1 : 4;
+    for (int i = 0; i < n; ++i) {
+        const int bone = c == 0 ? 0 : 4 * c - i;        // kinematic_chain_list: 4,3,2,1 | 8,7,6,5 | ...
+        const float* r = rel + ((int64_t)b * 21 + bone) * 3;
+        const float len = r[0], ax = -r[1], ay = -r[2];
+        const float cx = cosf(ax), sx = sinf(ax), cy = cosf(ay), sy = sinf(ay);
+        // M = RotX(ax) * RotY(ay)
+        const float M[9] = {cy, 0.f, sy, sx * sy, cx, -sx * cy, -cx * sy, sx, cx * cy};
+        float Rn[9], tn[3];
+#pragma unroll
+        for (int i2 = 0; i2 < 3; ++i2) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) Rn[3 * i2 + j] = M[3 * i2] * R[j] + M[3 * i2 + 1] * R[3 + j] + M[3 * i2 + 2] * R[6 + j];
+            tn[i2] = M[3 * i2] * t[0] + M[3 * i2 + 1] * t[1] + M[3 * i2 + 2] * t[2];
+        }
+        tn[2] -= len;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) R[j] = Rn[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) t[j] = tn[j];
+        float* o = xyz + ((int64_t)b * 21 + bone) * 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[j] = -(R[j] * t[0] + R[3 + j] * t[1] + R[6 + j] * t[2]);
+    }
+}
+
+int launch_bone_rel_trafo_inv(const float* rel, float* xyz, int B, cudaStream_t s) {
+    bone_rel_trafo_inv_kernel<<<ceil_div(B * 6, 128), 128, 0, s>>>(rel, xyz, B);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
 int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot, float* out,
                             cudaStream_t s) {
     rotate_canonical_kernel<<<B, 64, 0, s>>>(coord_can, uxyz, hand_side, B, rot, out);

@@ -1,7 +1,7 @@
 """PosePriorNetwork -- lifting 2D score maps to 3D behind the reference's API
-(nets/PosePriorNetwork.py:29-159).  Variants 'direct', 'bottleneck' and 'proposed' run on the same
-sm_100a kernels as ColorHandPose3DNetwork; 'local' / 'local_w_xyz_loss' need bone_rel_trafo_inv
-(utils/relative_trafo.py), a SURVEY.md 8(f) "next" row that is not built yet.
+(nets/PosePriorNetwork.py:29-159).  All five variants ('direct', 'bottleneck', 'local',
+'local_w_xyz_loss', 'proposed') run on the same sm_100a kernels as ColorHandPose3DNetwork; the 'local*' variants add
+the forward-kinematics kernel that replaces bone_rel_trafo_inv (utils/relative_trafo.py:243-295).
 """
 from __future__ import annotations
 
@@ -49,7 +49,9 @@ class PosePriorNetwork(object):
             c, _, _ = ctx.lifting(scoremap_pooled, hand_side, self.variant)
             return c, c, None
         elif self.variant in ('local', 'local_w_xyz_loss'):
-            raise NotImplementedError("variant '%s' needs bone_rel_trafo_inv (SURVEY.md 8(f) row 1, not built yet)" % self.variant)
+            # :70-75 -- the net predicts bone-relative coords; bone_rel_trafo_inv (utils/relative_trafo.py:243) assembles xyz
+            normed, rel, _ = ctx.lifting(scoremap_pooled, hand_side, 'local')
+            return normed, rel, None
         elif self.variant == 'proposed':
             out, can, R = ctx.lifting(scoremap_pooled, hand_side, 'proposed')
             return out, can, R

@@ -258,6 +258,15 @@ class Context:
         _lib.check(self.lib.h3d_detect_keypoints(self.h, _ptr(scoremaps), B, H, W, Cc, _ptr(uv), _stream()), "h3d_detect_keypoints")
         return uv
 
+    def bone_rel_trafo_inv(self, coords_rel):
+        coords_rel = _chk_f32(coords_rel, "coords_rel")
+        if coords_rel.dim() == 2:
+            coords_rel = coords_rel.unsqueeze(0)
+        B = coords_rel.shape[0]
+        out = torch.empty((B, 21, 3), dtype=torch.float32, device=coords_rel.device)
+        _lib.check(self.lib.h3d_bone_rel_trafo_inv(self.h, _ptr(coords_rel), _ptr(out), B, _stream()), "h3d_bone_rel_trafo_inv")
+        return out
+
     def rotate_canonical(self, coord_can, uxyz, hand_side):
         coord_can = _chk_f32(coord_can, "coord_can", 3); uxyz = _chk_f32(uxyz, "uxyz", 2); hand_side = _chk_f32(hand_side, "hand_side", 2)
         B = coord_can.shape[0]

@@ -50,6 +50,7 @@ extern "C" {
 #define H3D_VARIANT_DIRECT 0
 #define H3D_VARIANT_BOTTLENECK 1
 #define H3D_VARIANT_PROPOSED 2
+#define H3D_VARIANT_LOCAL 3 /* 'local' and 'local_w_xyz_loss': direct prediction of bone-relative coords + bone_rel_trafo_inv */
 
 typedef struct h3d_ctx h3d_ctx;
 
@@ -147,6 +148,8 @@ H3D_API int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float
  * first occurrence of the maximum in row-major order. */
 H3D_API int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int C,
                          int32_t* keypoints_uv, void* stream);
+/* bone_rel_trafo_inv (utils/relative_trafo.py:243-295): coords_rel [B,21,3] (length, angle_x, angle_y) -> xyz [B,21,3]. */
+H3D_API int h3d_bone_rel_trafo_inv(h3d_ctx* ctx, const float* coords_rel, float* coords_xyz, int B, void* stream);
 /* _get_rot_mat + _flip_right_hand + matmul (nets/ColorHandPose3DNetwork.py:239-247,311-384). */
 H3D_API int h3d_rotate_canonical(h3d_ctx* ctx, const float* coord_can, const float* uxyz, const float* hand_side,
                          int B, float* rot_mat, float* coord_out, void* stream);

@@ -294,8 +294,90 @@ def inference2d(image, weights, dtype=np.float32, literal_mask=True):
     return T.resize_bilinear_tf1(s32, CROP_SIZE, CROP_SIZE), image_crop, scale_crop, center
 
 
+# --------------------------------------------------------------------------------------------
+# Kinematic-chain transform (utils/relative_trafo.py) -- needed by the 'local' lifting variants
+# --------------------------------------------------------------------------------------------
+KINEMATIC_CHAIN_PARENT = {0: None, 4: None, 3: 4, 2: 3, 1: 2, 8: None, 7: 8, 6: 7, 5: 6, 12: None, 11: 12, 10: 11, 9: 10,
+                          16: None, 15: 16, 14: 15, 13: 14, 20: None, 19: 20, 18: 19, 17: 18}      # utils/relative_trafo.py:148-171
+KINEMATIC_CHAIN_LIST = [0, 4, 3, 2, 1, 8, 7, 6, 5, 12, 11, 10, 9, 16, 15, 14, 13, 20, 19, 18, 17]   # :174-179
+
+
+def _rot_x_hom(a):   # utils/relative_trafo.py:49-57
+    c, s_ = np.cos(a), np.sin(a)
+    return np.array([[1, 0, 0, 0], [0, c, -s_, 0], [0, s_, c, 0], [0, 0, 0, 1]], a.dtype)
+
+
+def _rot_y_hom(a):   # :60-68
+    c, s_ = np.cos(a), np.sin(a)
+    return np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1]], a.dtype)
+
+
+def _trans_hom(t):   # :82-90 -- translation along z only
+    m = np.eye(4, dtype=t.dtype)
+    m[2, 3] = t
+    return m
+
+
+def _atan2_ref(y, x):
+    """utils/relative_trafo.py:27-46 (the reference's own atan2 built from atan)."""
+    ft = type(y)
+    pi = ft(3.141592653589793)
+    tan = np.arctan(y / (x + ft(1e-8)))
+    tan_c = tan + (pi if (x + ft(1e-8)) < 0 else ft(0))
+    tan_02pi = tan_c + (ft(2) * pi if tan_c < 0 else ft(0))
+    return ft(tan_02pi + (ft(-2) * pi if tan_02pi > pi else ft(0)))
+
+
+def bone_rel_trafo_inv(coords_rel):
+    """utils/relative_trafo.py:243-295: [B,21,3] (length, angle_x, angle_y) per bone -> xyz [B,21,3]."""
+    coords_rel = np.asarray(coords_rel)
+    if coords_rel.ndim == 2:
+        coords_rel = coords_rel[None]
+    B = coords_rel.shape[0]
+    out = np.zeros((B, 21, 3), coords_rel.dtype)
+    x0 = np.array([0, 0, 0, 1], coords_rel.dtype)
+    for b in range(B):
+        trafo = {}
+        for bone in KINEMATIC_CHAIN_LIST:
+            parent = KINEMATIC_CHAIN_PARENT[bone]
+            T = np.eye(4, dtype=coords_rel.dtype) if parent is None else trafo[parent]
+            length, ax, ay = coords_rel[b, bone]
+            T_this = _trans_hom(-length) @ (_rot_x_hom(-ax) @ _rot_y_hom(-ay))      # _forward :102-114
+            T = T_this @ T
+            out[b, bone] = (np.linalg.inv(T) @ x0)[:3]
+            trafo[bone] = T
+    return out
+
+
+def bone_rel_trafo(coords_xyz):
+    """utils/relative_trafo.py:182-240 (forward direction; only used here for round-trip property tests)."""
+    coords_xyz = np.asarray(coords_xyz).reshape(-1, 21, 3)
+    B = coords_xyz.shape[0]
+    dt = coords_xyz.dtype
+    out = np.zeros((B, 21, 3), dt)
+    for b in range(B):
+        trafo = {}
+        for bone in KINEMATIC_CHAIN_LIST:
+            parent = KINEMATIC_CHAIN_PARENT[bone]
+            if parent is None:
+                T = np.eye(4, dtype=dt)
+                delta = np.append(coords_xyz[b, bone], dt.type(1))
+            else:
+                T = trafo[parent]
+                d3 = (T @ np.append(coords_xyz[b, bone], dt.type(1)) - T @ np.append(coords_xyz[b, parent], dt.type(1)))[:3]
+                delta = np.append(d3, dt.type(1))
+            length = np.sqrt(delta[0] ** 2 + delta[1] ** 2 + delta[2] ** 2)             # _backward :117-142
+            ay = _atan2_ref(delta[0], delta[2])
+            tmp = _rot_y_hom(-ay) @ delta
+            ax = _atan2_ref(-tmp[1], tmp[2])
+            T_this = _trans_hom(-length) @ (_rot_x_hom(-ax) @ _rot_y_hom(-ay))
+            trafo[bone] = T_this @ T
+            out[b, bone] = (length, ax, ay)
+    return out
+
+
 def pose_prior_inference(scoremap256, hand_side, weights, variant, dtype=np.float32):
-    """nets/PosePriorNetwork.py:59-95 for variants direct / bottleneck / proposed.
+    """nets/PosePriorNetwork.py:59-95 for all five variants (direct / bottleneck / local / local_w_xyz_loss / proposed).
     Returns (coord_xyz_rel_normed, coord3d, R)."""
     pooled = T.avg_pool_8x8(scoremap256.astype(np.float32))                # :61
     if variant == "direct":
@@ -304,6 +386,9 @@ def pose_prior_inference(scoremap256, hand_side, weights, variant, dtype=np.floa
     if variant == "bottleneck":
         c = inference_pose3d_can(pooled, hand_side, weights, dtype, bottleneck=True)
         return c, c, None
+    if variant in ("local", "local_w_xyz_loss"):                           # :70-75
+        c = inference_pose3d_can(pooled, hand_side, weights, dtype)
+        return bone_rel_trafo_inv(c.astype(np.float32)), c, None
     if variant == "proposed":
         out, can, R = inference_pose3d(pooled, hand_side, weights, dtype)
         return out, can, R

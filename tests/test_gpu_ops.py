@@ -144,6 +144,19 @@ def test_rotate_canonical(ctx):
     np.testing.assert_allclose(out.cpu().numpy(), np.matmul(O.flip_right_hand(can, hs), R), atol=1e-5)
 
 
+def test_bone_rel_trafo_inv(ctx):
+    """Forward kinematics kernel vs the oracle, and the round trip xyz -> bone_rel_trafo (oracle) -> device -> xyz."""
+    rng = np.random.default_rng(15)
+    rel = np.stack([rng.uniform(0.1, 1.5, (9, 21)), rng.uniform(-3, 3, (9, 21)), rng.uniform(-3, 3, (9, 21))], -1).astype(f32)
+    out = ctx.bone_rel_trafo_inv(_dev(rel)).cpu().numpy()
+    np.testing.assert_allclose(out, O.bone_rel_trafo_inv(rel), atol=2e-5)
+    xyz = rng.normal(size=(4, 21, 3)).astype(f32)
+    back = ctx.bone_rel_trafo_inv(_dev(O.bone_rel_trafo(xyz))).cpu().numpy()
+    np.testing.assert_allclose(back, xyz, atol=2e-5)
+    from hand3d_b200.utils.relative_trafo import bone_rel_trafo_inv
+    np.testing.assert_allclose(bone_rel_trafo_inv(_dev(rel[0])).cpu().numpy()[0], out[0], atol=0)
+
+
 def test_network_ops_mirror(ctx):
     """NetworkOps.conv_relu / max_pool / fully_connected_relu with tf-style variable scopes."""
     from hand3d_b200 import weights as Wt

@@ -120,8 +120,15 @@ def test_pose_prior_network_variants(wd):
     np.testing.assert_allclose(out.cpu().numpy(), O.pose_prior_inference(sm, hs, wb, "bottleneck")[0], atol=1e-4)
     # restore the standard weights for the tests that follow
     runtime.default_context().load_weights({k: v for k, v in wd.items() if k.startswith("PosePrior")})
-    with pytest.raises(NotImplementedError):
-        PosePriorNetwork("local").inference(_dev(sm), _dev(hs), True)
+    for variant in ("local", "local_w_xyz_loss"):      # bone_rel_trafo_inv on device (utils/relative_trafo.py:243-295)
+        p = PosePriorNetwork(variant)
+        out, c3, R = p.inference(_dev(sm), _dev(hs), True)
+        ref = O.pose_prior_inference(sm, hs, wd, variant)
+        np.testing.assert_allclose(c3.cpu().numpy(), ref[1], atol=1e-4)
+        np.testing.assert_allclose(out.cpu().numpy(), ref[0], atol=1e-3)
+        assert R is None
+    with pytest.raises(AssertionError):
+        PosePriorNetwork("nonsense").inference(_dev(sm), _dev(hs), True)
 
 
 def _pipeline_case(kind):

@@ -195,3 +195,17 @@ def test_avg_pool():
     x = np.arange(16 * 16, dtype=f32).reshape(1, 16, 16, 1)
     np.testing.assert_allclose(T.avg_pool_8x8(x)[0, :, :, 0], [[x[0, :8, :8].mean(), x[0, :8, 8:].mean()],
                                                              [x[0, 8:, :8].mean(), x[0, 8:, 8:].mean()]], rtol=1e-6)
+
+
+def test_bone_rel_trafo_round_trip_and_kat():
+    """utils/relative_trafo.py: inv(fwd(xyz)) == xyz; a single bone of length L with zero angles points along +z."""
+    rng = np.random.default_rng(3)
+    xyz = rng.normal(size=(2, 21, 3))
+    np.testing.assert_allclose(O.bone_rel_trafo_inv(O.bone_rel_trafo(xyz)), xyz, atol=1e-6)   # the reference atan2 adds 1e-8 to x
+    rel = np.zeros((1, 21, 3)); rel[0, :, 0] = 1.0           # every bone: length 1, no articulation
+    out = O.bone_rel_trafo_inv(rel)[0]
+    np.testing.assert_allclose(out[0], [0, 0, 1], atol=1e-12)          # root key-point
+    np.testing.assert_allclose(out[4], [0, 0, 1], atol=1e-12)          # first bone of a finger
+    np.testing.assert_allclose(out[1], [0, 0, 4], atol=1e-12)          # finger tip: 4 bones stacked along z
+    rel[0, 4, 2] = np.pi / 2                                           # rotate the first thumb bone about y by 90 degrees
+    np.testing.assert_allclose(O.bone_rel_trafo_inv(rel)[0, 4], [1, 0, 0], atol=1e-12)
