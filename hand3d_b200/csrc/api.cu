@@ -850,13 +850,14 @@ int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_sid
     // PosePrior + ViewpointNet on the 32x32 map (nets/...:93)
     if (with_pose3d)
         if ((rc = h3d_lifting_forward(ctx, L.s[2], hand_side, B, H3D_VARIANT_PROPOSED, keypoint_coord3d, nullptr, nullptr, stream))) return rc;
-    // x8 up-sampling (nets/...:96-97) and detect_keypoints (utils/general.py:331-344)
-    if ((rc = launch_resize_bilinear_tf1(L.s[2], kps, B, 32, 32, 21, 256, 256, s))) return rc;
-    ctx->launches += 1;
+    // x8 up-sampling (nets/...:96-97) and detect_keypoints (utils/general.py:331-344), fused when both are requested
     if (keypoints_uv) {
         nl = 0;
-        if ((rc = launch_detect_keypoints(kps, B, 256, 256, 21, L.argmax_scratch, keypoints_uv, s, &nl))) return rc;
+        if ((rc = launch_resize_argmax21(L.s[2], kps, B, 32, 32, 256, 256, L.argmax_scratch, keypoints_uv, s, &nl))) return rc;
         ctx->launches += nl;
+    } else {
+        if ((rc = launch_resize_bilinear_tf1(L.s[2], kps, B, 32, 32, 21, 256, 256, s))) return rc;
+        ctx->launches += 1;
     }
     return H3D_OK;
 }

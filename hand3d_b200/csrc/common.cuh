@@ -70,6 +70,9 @@ int launch_crop_image(const float* image, const float* center, const float* scal
 int64_t argmax_scratch_bytes(int B, int C);
 int launch_detect_keypoints(const float* sm, int B, int H, int W, int C, void* scratch, int32_t* uv, cudaStream_t s,
                             int* n_launch);
+// fused x8 up-sampling of a [B,H,W,21] score map + per-channel arg-max (scratch: argmax_scratch_bytes(B, 21))
+int launch_resize_argmax21(const float* x, float* y, int B, int H, int W, int oh, int ow, void* scratch, int32_t* uv, cudaStream_t s,
+                           int* n_launch);
 // dst[r, dst_off + c] = src[r, c] for c < C (fp32 channel copy into a wider NHWC tensor)
 int launch_copy_channels(const float* src, float* dst, int64_t rows, int C, int dst_total, int dst_off, cudaStream_t s);
 int launch_bone_rel_trafo_inv(const float* rel, float* xyz, int B, cudaStream_t s);

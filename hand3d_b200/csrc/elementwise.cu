@@ -632,6 +632,62 @@ __global__ void rotate_canonical_kernel(const float* __restrict__ can, const flo
 }
 
 // =============================================================================================
+// Fused x8 up-sampling + detect_keypoints: writes the TF1-legacy bilinear up-sampled score map (nets/...:96-97) and
+// reduces its per-channel first-occurrence arg-max (utils/general.py:331-344) in the same pass, so the 5.5 MB/image map
+// is written once and never re-read.  Thread (p_sub, c) produces pixels p_sub, p_sub + P, ... of channel c: the C threads
+// of a pixel write C consecutive floats.  Values are computed exactly as resize_bilinear_tf1_kernel computes them.
+// =============================================================================================
+template <int C>
+__global__ void resize_argmax_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int oh, int ow, float hscale,
+                                     float wscale, int P, unsigned long long* __restrict__ key) {
+    extern __shared__ unsigned long long skey[];   // [P][C]
+    const int b = blockIdx.y;
+    const int t = threadIdx.x;
+    const int p_sub = t / C, c = t - p_sub * C;
+    const int HW = oh * ow;
+    unsigned long long best = 0ull;
+    if (p_sub < P) {
+        const float* xb = x + (int64_t)b * H * W * C;
+        float* yb = y + (int64_t)b * HW * C;
+        for (int p = blockIdx.x * P + p_sub; p < HW; p += gridDim.x * P) {
+            const int oy = p / ow, ox = p - oy * ow;
+            const float in_y = __fmul_rn((float)oy, hscale), in_x = __fmul_rn((float)ox, wscale);
+            const int y0 = (int)floorf(in_y), x0 = (int)floorf(in_x);
+            const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+            const float ly = __fsub_rn(in_y, (float)y0), lx = __fsub_rn(in_x, (float)x0);
+            const float tl = __ldg(xb + (y0 * W + x0) * C + c), tr = __ldg(xb + (y0 * W + x1) * C + c);
+            const float bl = __ldg(xb + (y1 * W + x0) * C + c), br = __ldg(xb + (y1 * W + x1) * C + c);
+            const float v = lerp_tf(lerp_tf(tl, tr, lx), lerp_tf(bl, br, lx), ly);
+            yb[(int64_t)p * C + c] = v;
+            const unsigned long long k = ((unsigned long long)float_orderable(v) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)p);
+            best = k > best ? k : best;
+        }
+        skey[p_sub * C + c] = best;
+    }
+    __syncthreads();
+    if (t < C) {
+        unsigned long long m = 0ull;
+        for (int q = 0; q < P; ++q) { const unsigned long long k = skey[q * C + t]; m = k > m ? k : m; }
+        atomicMax(key + (int64_t)b * C + t, m);
+    }
+}
+
+int launch_resize_argmax21(const float* x, float* y, int B, int H, int W, int oh, int ow, void* scratch, int32_t* uv, cudaStream_t s,
+                           int* n_launch) {
+    constexpr int C = 21;
+    unsigned long long* key = (unsigned long long*)scratch;
+    H3D_CUDA(cudaMemsetAsync(key, 0, (size_t)B * C * 8, s));
+    const int P = 256 / C;
+    dim3 grid(std::max(1, std::min(ceil_div(oh * ow, P * 8), 4 * 148 / std::max(1, std::min(B, 4)))), B);
+    resize_argmax_kernel<C><<<grid, P * C, (size_t)P * C * 8, s>>>(x, y, H, W, oh, ow, (float)H / (float)oh, (float)W / (float)ow, P, key);
+    H3D_CHECK_LAUNCH();
+    argmax_decode_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(key, B * C, ow, uv);
+    H3D_CHECK_LAUNCH();
+    if (n_launch) *n_launch += 2;
+    return H3D_OK;
+}
+
+// =============================================================================================
 // bone_rel_trafo_inv (utils/relative_trafo.py:243-295): forward kinematics over the 21-node hand chain.
 // One thread per (sample, chain): the root key-point and the 5 fingers are independent chains of rigid
 // transforms T <- Trans_z(-len) RotX(-ax) RotY(-ay) T; the key-point is inv(T) [0,0,0,1]^T = -R^T t.
