@@ -194,10 +194,10 @@ __global__ void conv_splitk_reduce_kernel(const float* __restrict__ part, const 
 // memory; all shared loads are 128-bit and warp-broadcast (8 lanes share an address), so the inner loop is
 // 192 FFMA per 10 LDS.128.  Stores: the 8 lanes of a pixel write 128 (split) / 256 (fp32) contiguous bytes.
 // ---------------------------------------------------------------------------------------------
-constexpr int C3_TH = 8, C3_TW = 32, C3_LD = 40;   // tile rows, tile cols, padded smem row (pixel x=-1 sits at index 3)
+constexpr int C3_TH = 8, C3_TW = 32, C3_LD = 40, C3_TILES_PER_CTA = 4;   // tile rows, tile cols, padded smem row (pixel x=-1 sits at index 3)
 
 template <bool FP16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
                   uint16_t* __restrict__ yhi, uint16_t* __restrict__ ylo, int B, int H, int W, int Cy_total, int cy_off,
                   int Cs_total, int cs_off, int leaky) {
@@ -205,18 +205,21 @@ conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     __shared__ __align__(16) float xs[3][C3_TH + 2][C3_LD];
     const int t = threadIdx.x;
     const int tiles_w = (W + C3_TW - 1) / C3_TW, tiles_h = (H + C3_TH - 1) / C3_TH;
-    const int tile = blockIdx.x;
+    const int num_tiles = tiles_w * tiles_h * B;
+    for (int i = t; i < 27 * 64; i += 256) (&ws[0][0])[i] = __ldg(w + i);      // weights staged once per CTA
+    for (int i = t; i < 3 * (C3_TH + 2) * C3_LD; i += 256) (&xs[0][0][0])[i] = 0.f;   // alignment padding columns stay zero
+    for (int tile = blockIdx.x * C3_TILES_PER_CTA; tile < min(num_tiles, (blockIdx.x + 1) * C3_TILES_PER_CTA); ++tile) {
     const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
     const int x0 = tw * C3_TW, y0 = th * C3_TH;
-    for (int i = t; i < 27 * 64; i += 256) (&ws[0][0])[i] = __ldg(w + i);
-    for (int i = t; i < 3 * (C3_TH + 2) * C3_LD; i += 256) (&xs[0][0][0])[i] = 0.f;
-    __syncthreads();
+    __syncthreads();                                                            // previous tile fully consumed (and ws visible)
     const float* xb = x + (int64_t)b * H * W * 3;
-    for (int i = t; i < (C3_TH + 2) * (C3_TW + 2) * 3; i += 256) {
+    for (int i = t; i < (C3_TH + 2) * (C3_TW + 2) * 3; i += 256) {              // haloed input tile (contiguous (x, c) reads), zero outside the image
         const int r = i / ((C3_TW + 2) * 3), rem = i - r * ((C3_TW + 2) * 3);
         const int c = rem / 3, ci = rem - c * 3;
         const int gy = y0 - 1 + r, gx = x0 - 1 + c;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) xs[ci][r][c + 3] = __ldg(xb + ((int64_t)gy * W + gx) * 3 + ci);
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(xb + ((int64_t)gy * W + gx) * 3 + ci);
+        xs[ci][r][c + 3] = v;
     }
     __syncthreads();
     const int warp = t >> 5, lane = t & 31;
@@ -252,7 +255,7 @@ conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 #pragma unroll
     for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + cg * 8 + j);
     const int gy = y0 + warp;
-    if (gy >= H) return;
+    if (gy < H) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int gx = x0 + pg * 8 + i;
@@ -279,6 +282,8 @@ conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
             if (ylo) *reinterpret_cast<uint4*>(ylo + off) = *reinterpret_cast<const uint4*>(l);
         }
     }
+    }   // gy < H
+    }   // tile loop
 }
 
 }  // namespace
@@ -328,7 +333,7 @@ int conv_direct_num_launches(const DirectConvArgs& a) {
 int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
     H3D_REQUIRE(a.k >= 1 && a.stride >= 1 && a.Cin >= 1 && a.Cout >= 1, "conv_direct: bad geometry");
     if (is_c3_case(a)) {
-        const int tiles = ceil_div(a.W, C3_TW) * ceil_div(a.H, C3_TH) * a.B;
+        const int tiles = ceil_div(ceil_div(a.W, C3_TW) * ceil_div(a.H, C3_TH) * a.B, C3_TILES_PER_CTA);
         if (a.half == Half16::FP16)
             conv3x3_c3_kernel<true><<<tiles, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, a.B, a.H, a.W, a.Cout_total, a.cout_off, a.Cs_total, a.cs_off, a.leaky);
         else

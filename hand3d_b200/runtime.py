@@ -177,6 +177,23 @@ class Context:
             _stream()), "h3d_pipeline_forward")
         return r
 
+    def capture_pipeline(self, image, hand_side=None, with_pose3d=True, outputs="keypoints"):
+        """Captures one pipeline() call on fixed input tensors into a CUDA graph (the forward pass has no host
+        synchronisation, no allocation and only fixed workspace pointers, so ~90 launches replay as one).
+        Returns (replay, results): refill `image` / `hand_side` in place, call replay(), read `results`."""
+        image = _chk_f32(image, "image", 4)
+        self.ensure_workspace(*image.shape[:3])
+        side = torch.cuda.Stream(device=image.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up outside capture: builds plans, packs weights
+            self.pipeline(image, hand_side, with_pose3d, outputs=outputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(image.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            results = self.pipeline(image, hand_side, with_pose3d, outputs=outputs)
+        return graph.replay, results
+
     # ---- operators ---------------------------------------------------------------------------
     def conv2d(self, x, w, b, stride=1, leaky=False):
         x = _chk_f32(x, "x", 4); w = _chk_f32(w, "w", 4); b = _chk_f32(b, "b", 1)
