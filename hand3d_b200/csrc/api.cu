@@ -986,6 +986,31 @@ int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int
     cudaFree(scratch);
     return rc;
 }
+int h3d_decode_records(h3d_ctx* ctx, int dataset, const uint8_t* records, int B, int step, float* header, float* image, uint8_t* mask,
+                       uint8_t* visibility, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(records && image && B > 0 && (step == 1 || step == 2 || step == 4), "h3d_decode_records: bad argument");
+    int rc;
+    if (dataset == H3D_DATASET_RHD) {
+        const int hdr = 42 * 3 + 42 * 2 + 9;                           // 219 floats = 876 B, then 2 B padding
+        rc = launch_decode_records(records, 410520, hdr, 878, 320, 320, step, 878 + 320 * 320 * 3, 42, header, image, mask, visibility, B, s);
+    } else if (dataset == H3D_DATASET_STB) {
+        const int hdr = 21 * 3 + 21 * 3;                               // 126 floats = 504 B
+        rc = launch_decode_records(records, 922104, hdr, 504, 480, 640, step, -1, 0, header, image, nullptr, nullptr, B, s);
+    } else {
+        set_error("h3d_decode_records: unknown dataset %d", dataset);
+        return H3D_EINVAL;
+    }
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_eval_keypoint_dist(h3d_ctx* ctx, const float* gt, const uint8_t* vis, const float* pred, int n, int D, float* dist, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(gt && vis && pred && dist && n > 0 && D >= 1 && D <= 4, "h3d_eval_keypoint_dist: bad argument");
+    int rc = launch_eval_dist(gt, vis, pred, n, D, dist, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
 int h3d_bone_rel_trafo_inv(h3d_ctx* ctx, const float* coords_rel, float* coords_xyz, int B, void* stream) {
     H3D_OP_PROLOGUE(ctx);
     H3D_REQUIRE(coords_rel && coords_xyz && B > 0, "h3d_bone_rel_trafo_inv: bad argument");

@@ -75,6 +75,10 @@ int launch_resize_argmax21(const float* x, float* y, int B, int H, int W, int oh
                            int* n_launch);
 // dst[r, dst_off + c] = src[r, c] for c < C (fp32 channel copy into a wider NHWC tensor)
 int launch_copy_channels(const float* src, float* dst, int64_t rows, int C, int dst_total, int dst_off, cudaStream_t s);
+int launch_decode_records(const uint8_t* rec, int64_t record_bytes, int header_floats, int64_t image_off, int H, int W, int step,
+                          int64_t mask_off, int tail_bytes, float* header, float* image, uint8_t* mask, uint8_t* tail, int B,
+                          cudaStream_t s);
+int launch_eval_dist(const float* gt, const uint8_t* vis, const float* pred, int n, int D, float* dist, cudaStream_t s);
 int launch_bone_rel_trafo_inv(const float* rel, float* xyz, int B, cudaStream_t s);
 int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot,
                             float* out, cudaStream_t s);

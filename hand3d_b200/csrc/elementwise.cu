@@ -688,6 +688,82 @@ int launch_resize_argmax21(const float* x, float* y, int B, int H, int W, int oh
 }
 
 // =============================================================================================
+// On-device decode of the readers' fixed-length binary records:
+//   RHD (data/BinaryDbReader.py:103-208, create_binary_db.py:44-87): 42x3 f32 xyz | 42x2 f32 uv | 9 f32 K | 2 B pad |
+//        320x320x3 u8 RGB | 320x320 u8 part mask | 42 u8 visibility                    = 410 520 B
+//   STB (data/BinaryDbReaderSTB.py:99-185): 21x3 f32 xyz | 21x3 f32 (u, v, valid) | 480x640x3 u8 RGB = 922 104 B
+// The float header is copied as is; the image becomes fp32 `u8 / 255 - 0.5` (two fp32 ops, as the readers do), optionally
+// sub-sampled by `step` (eval_full.py:50 resizes 480x640 -> 240x320, which TF1's legacy bilinear turns into "every 2nd pixel").
+// =============================================================================================
+__global__ void decode_records_kernel(const uint8_t* __restrict__ rec, int64_t record_bytes, int header_floats, int64_t image_off,
+                                      int H, int W, int step, int64_t mask_off, int tail_bytes, float* __restrict__ header,
+                                      float* __restrict__ image, uint8_t* __restrict__ mask, uint8_t* __restrict__ tail, int B) {
+    const int Ho = H / step, Wo = W / step;
+    const int64_t per_img = (int64_t)Ho * Wo * 3;
+    const int64_t total = (int64_t)B * per_img;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per_img);
+        const int64_t r = i - (int64_t)b * per_img;
+        const int c = (int)(r % 3), x = (int)((r / 3) % Wo), y = (int)(r / (3 * (int64_t)Wo));
+        const uint8_t v = rec[(int64_t)b * record_bytes + image_off + ((int64_t)(y * step) * W + x * step) * 3 + c];
+        image[i] = __fsub_rn(__fdiv_rn((float)v, 255.0f), 0.5f);
+    }
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gstride = (int64_t)gridDim.x * blockDim.x;
+    if (header) {
+        for (int64_t i = gtid; i < (int64_t)B * header_floats; i += gstride) {
+            const int b = (int)(i / header_floats), j = (int)(i - (int64_t)b * header_floats);
+            const uint8_t* p = rec + (int64_t)b * record_bytes + 4 * j;       // records start 4-byte aligned (both sizes are multiples of 4)
+            uint32_t u = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+            header[i] = __uint_as_float(u);
+        }
+    }
+    if (mask && mask_off >= 0) {
+        const int64_t n = (int64_t)H * W;
+        for (int64_t i = gtid; i < (int64_t)B * n; i += gstride) {
+            const int b = (int)(i / n);
+            mask[i] = rec[(int64_t)b * record_bytes + mask_off + (i - (int64_t)b * n)];
+        }
+    }
+    if (tail && tail_bytes > 0) {
+        for (int64_t i = gtid; i < (int64_t)B * tail_bytes; i += gstride) {
+            const int b = (int)(i / tail_bytes);
+            tail[i] = rec[(int64_t)b * record_bytes + record_bytes - tail_bytes + (i - (int64_t)b * tail_bytes)];
+        }
+    }
+}
+
+int launch_decode_records(const uint8_t* rec, int64_t record_bytes, int header_floats, int64_t image_off, int H, int W, int step,
+                          int64_t mask_off, int tail_bytes, float* header, float* image, uint8_t* mask, uint8_t* tail, int B,
+                          cudaStream_t s) {
+    const int64_t total = (int64_t)B * (H / step) * (W / step) * 3;
+    decode_records_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 148 * 16), 256, 0, s>>>(
+        rec, record_bytes, header_floats, image_off, H, W, step, mask_off, tail_bytes, header, image, mask, tail, B);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
+// EvalUtil.feed (utils/general.py:531-549), batched: euclidean distance per key-point, -1 where not visible.
+// =============================================================================================
+__global__ void eval_dist_kernel(const float* __restrict__ gt, const uint8_t* __restrict__ vis, const float* __restrict__ pred,
+                                 int n, int D, float* __restrict__ dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float df = __fsub_rn(gt[(int64_t)i * D + d], pred[(int64_t)i * D + d]);
+        acc = __fadd_rn(acc, __fmul_rn(df, df));
+    }
+    dist[i] = vis[i] ? sqrtf(acc) : -1.0f;
+}
+
+int launch_eval_dist(const float* gt, const uint8_t* vis, const float* pred, int n, int D, float* dist, cudaStream_t s) {
+    eval_dist_kernel<<<ceil_div(n, 256), 256, 0, s>>>(gt, vis, pred, n, D, dist);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
 // bone_rel_trafo_inv (utils/relative_trafo.py:243-295): forward kinematics over the 21-node hand chain.
 // One thread per (sample, chain): the root key-point and the 5 fingers are independent chains of rigid
 // transforms T <- Trans_z(-len) RotX(-ax) RotY(-ay) T; the key-point is inv(T) [0,0,0,1]^T = -R^T t.

@@ -275,6 +275,35 @@ class Context:
         _lib.check(self.lib.h3d_detect_keypoints(self.h, _ptr(scoremaps), B, H, W, Cc, _ptr(uv), _stream()), "h3d_detect_keypoints")
         return uv
 
+    def decode_records(self, records, dataset="rhd", step=1, want_aux=True):
+        """records: uint8 CUDA tensor [B, record_bytes] -> dict(image fp32 NHWC, header, mask, visibility)."""
+        if records.dtype != torch.uint8 or not records.is_cuda or records.dim() != 2:
+            raise TypeError("records must be a 2-D uint8 CUDA tensor")
+        records = records.contiguous()
+        B = records.shape[0]
+        ds = {"rhd": 0, "stb": 1}[dataset]
+        rb, H, W, hdr = (410520, 320, 320, 219) if ds == 0 else (922104, 480, 640, 126)
+        if records.shape[1] != rb:
+            raise ValueError("%s records are %d bytes, got %d" % (dataset, rb, records.shape[1]))
+        dev = records.device
+        image = torch.empty((B, H // step, W // step, 3), dtype=torch.float32, device=dev)
+        header = torch.empty((B, hdr), dtype=torch.float32, device=dev) if want_aux else None
+        mask = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if (want_aux and ds == 0) else None
+        vis = torch.empty((B, 42), dtype=torch.uint8, device=dev) if (want_aux and ds == 0) else None
+        _lib.check(self.lib.h3d_decode_records(self.h, ds, _ptr(records), B, step, _ptr(header), _ptr(image), _ptr(mask), _ptr(vis),
+                                               _stream()), "h3d_decode_records")
+        return {"image": image, "header": header, "mask": mask, "visibility": vis}
+
+    def eval_keypoint_dist(self, gt, vis, pred):
+        gt = _chk_f32(gt, "keypoint_gt"); pred = _chk_f32(pred, "keypoint_pred")
+        D = gt.shape[-1]
+        n = gt.numel() // D
+        vis = vis.to(torch.uint8).contiguous()
+        dist = torch.empty(gt.shape[:-1], dtype=torch.float32, device=gt.device)
+        _lib.check(self.lib.h3d_eval_keypoint_dist(self.h, _ptr(gt), _ptr(vis), _ptr(pred), n, D, _ptr(dist), _stream()),
+                   "h3d_eval_keypoint_dist")
+        return dist
+
     def bone_rel_trafo_inv(self, coords_rel):
         coords_rel = _chk_f32(coords_rel, "coords_rel")
         if coords_rel.dim() == 2:

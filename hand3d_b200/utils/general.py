@@ -4,8 +4,9 @@ hand-written sm_100a kernels behind the C ABI (include/hand3d_b200.h).
 
 Reference: utils/general.py:26-65,113-148 (NetworkOps), :163 crop_image_from_xy, :199 find_max_location,
 :233 single_obj_scoremap, :271 calc_center_bb, :331 detect_keypoints, :347 trafo_coords.
+EvalUtil (:522-611) is mirrored with a batched device path.
 Not mirrored (dead code in every graph / out of scope): upconv*, spatial_dropout,
-plot helpers, LearningRateScheduler, EvalUtil, load_weights_from_snapshot.
+plot helpers, LearningRateScheduler, load_weights_from_snapshot.
 """
 from __future__ import annotations
 
@@ -181,3 +182,65 @@ def trafo_coords(keypoints_crop_coords, centers, scale, crop_size):
         scale = scale.reshape(-1, 1, 1)
         centers = centers.reshape(-1, 1, 2)
     return k / scale + centers
+
+
+class EvalUtil:
+    """ Util class for evaluation networks (utils/general.py:522-611): end-point error, PCK curve and AUC per key-point.
+
+        feed() keeps the reference's single-sample numpy semantics and additionally accepts batches of torch CUDA
+        tensors ([B,K,D] ground truth / prediction, [B,K] visibility): distances are then computed on the device by one
+        kernel and only B*K floats travel to the host.  get_measures() returns the same 5-tuple as the reference.
+    """
+    def __init__(self, num_kp=21):
+        self.num_kp = num_kp
+        self.data = [list() for _ in range(num_kp)]
+
+    def feed(self, keypoint_gt, keypoint_vis, keypoint_pred):
+        if torch.is_tensor(keypoint_gt) and keypoint_gt.is_cuda:
+            gt = keypoint_gt.to(torch.float32).reshape(-1, self.num_kp, keypoint_gt.shape[-1]).contiguous()
+            pred = torch.as_tensor(keypoint_pred, device=gt.device).to(torch.float32).reshape(gt.shape).contiguous()
+            vis = torch.as_tensor(keypoint_vis, device=gt.device).reshape(gt.shape[0], self.num_kp)
+            dist = runtime.default_context().eval_keypoint_dist(gt, vis != 0, pred).cpu().numpy()
+            for i in range(self.num_kp):
+                col = dist[:, i]
+                self.data[i].extend(col[col >= 0].tolist())
+            return
+        keypoint_gt = np.squeeze(np.asarray(keypoint_gt))
+        keypoint_pred = np.squeeze(np.asarray(keypoint_pred))
+        keypoint_vis = np.squeeze(np.asarray(keypoint_vis)).astype('bool')
+        assert len(keypoint_gt.shape) == 2
+        assert len(keypoint_pred.shape) == 2
+        assert len(keypoint_vis.shape) == 1
+        euclidean_dist = np.sqrt(np.sum(np.square(keypoint_gt - keypoint_pred), axis=1))
+        for i in range(keypoint_gt.shape[0]):
+            if keypoint_vis[i]:
+                self.data[i].append(euclidean_dist[i])
+
+    def _get_pck(self, kp_id, threshold):
+        if len(self.data[kp_id]) == 0:
+            return None
+        return np.mean((np.array(self.data[kp_id]) <= threshold).astype('float'))
+
+    def _get_epe(self, kp_id):
+        if len(self.data[kp_id]) == 0:
+            return None, None
+        d = np.array(self.data[kp_id])
+        return np.mean(d), np.median(d)
+
+    def get_measures(self, val_min, val_max, steps):
+        """ (mean EPE, median EPE, AUC, PCK curve, thresholds), each averaged over the key-points that have data. """
+        trapz = getattr(np, "trapezoid", None) or np.trapz
+        thresholds = np.linspace(val_min, val_max, steps)
+        norm_factor = trapz(np.ones_like(thresholds), thresholds)
+        means, medians, aucs, curves = [], [], [], []
+        for part_id in range(self.num_kp):
+            mean, median = self._get_epe(part_id)
+            if mean is None:
+                continue                      # no valid measurement for this key-point
+            means.append(mean)
+            medians.append(median)
+            curve = np.array([self._get_pck(part_id, t) for t in thresholds])
+            curves.append(curve)
+            aucs.append(trapz(curve, thresholds) / norm_factor)
+        return (np.mean(np.array(means)), np.mean(np.array(medians)), np.mean(np.array(aucs)), np.mean(np.array(curves), 0),
+                thresholds)

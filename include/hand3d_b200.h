@@ -148,6 +148,19 @@ H3D_API int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float
  * first occurrence of the maximum in row-major order. */
 H3D_API int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int C,
                          int32_t* keypoints_uv, void* stream);
+/* On-device decode of the dataset readers' fixed-length records.  dataset 0 = RHD
+ * (data/BinaryDbReader.py:103-208; 410520-byte records: header [B,219] = 42x3 xyz | 42x2 uv | 3x3 K, image [B,320,320,3],
+ * mask [B,320,320] u8, visibility [B,42] u8), dataset 1 = STB (data/BinaryDbReaderSTB.py:99-185; 922104-byte records:
+ * header [B,126] = 21x3 xyz | 21x3 (u,v,valid), image [B,480/step,640/step,3]; eval_full.py:50 uses step 2).
+ * image = u8 / 255 - 0.5 exactly as the readers compute it; header / mask / visibility may be NULL. */
+#define H3D_DATASET_RHD 0
+#define H3D_DATASET_STB 1
+H3D_API int h3d_decode_records(h3d_ctx* ctx, int dataset, const uint8_t* records, int B, int step, float* header, float* image,
+                               uint8_t* mask, uint8_t* visibility, void* stream);
+/* EvalUtil.feed (utils/general.py:531-549), batched on device: gt / pred [n, D] (D = 2 or 3), vis [n] u8 ->
+ * dist [n] = ||gt - pred||_2, or -1 where the key-point is not visible. */
+H3D_API int h3d_eval_keypoint_dist(h3d_ctx* ctx, const float* gt, const uint8_t* vis, const float* pred, int n, int D, float* dist,
+                                   void* stream);
 /* bone_rel_trafo_inv (utils/relative_trafo.py:243-295): coords_rel [B,21,3] (length, angle_x, angle_y) -> xyz [B,21,3]. */
 H3D_API int h3d_bone_rel_trafo_inv(h3d_ctx* ctx, const float* coords_rel, float* coords_xyz, int B, void* stream);
 /* _get_rot_mat + _flip_right_hand + matmul (nets/ColorHandPose3DNetwork.py:239-247,311-384). */

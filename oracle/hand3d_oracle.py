@@ -416,3 +416,61 @@ def trafo_coords(keypoints_crop_coords, centers, scale, crop_size):
     k /= scale
     k += centers
     return k
+
+
+# --------------------------------------------------------------------------------------------
+# Record formats and evaluation bookkeeping
+# --------------------------------------------------------------------------------------------
+def decode_rhd_record(record):
+    """data/BinaryDbReader.py:103-208 (raw items only) for ONE 410 520-byte record (bytes / uint8 array)."""
+    raw = np.frombuffer(bytes(record), dtype=np.uint8)
+    assert raw.size == 410520, "Doesnt add up."                                          # :210
+    f = np.frombuffer(bytes(record[:876]), dtype=np.float32)
+    u8 = raw[878:]
+    img = u8[:307200].reshape(320, 320, 3).astype(np.float32) / np.float32(255.0) - np.float32(0.5)   # :176-182
+    parts = u8[307200:409600].reshape(320, 320).astype(np.int32)
+    hand = parts > 1
+    return {"keypoint_xyz": f[:126].reshape(42, 3), "keypoint_uv": f[126:210].reshape(42, 2).astype(np.int32).astype(np.float32),
+            "cam_mat": f[210:219].reshape(3, 3), "image": img, "hand_parts": parts,
+            "hand_mask": np.stack([~hand, hand], 2).astype(np.int32), "keypoint_vis": u8[409600:409642].astype(bool)}
+
+
+def decode_stb_record(record, subsample=2):
+    """data/BinaryDbReaderSTB.py:99-185 (raw items) + eval_full.py:50 (legacy bilinear 480x640 -> 240x320 = every 2nd pixel)."""
+    raw = np.frombuffer(bytes(record), dtype=np.uint8)
+    assert raw.size == 922104
+    f = np.frombuffer(bytes(record[:504]), dtype=np.float32)
+    img = raw[504:].reshape(480, 640, 3).astype(np.float32) / np.float32(255.0) - np.float32(0.5)
+    if subsample > 1:
+        img = T.resize_bilinear_tf1(img[None], 480 // subsample, 640 // subsample)[0]
+    uvv = f[63:126].reshape(21, 3)
+    return {"keypoint_xyz": f[:63].reshape(21, 3), "keypoint_uv": uvv[:, :2], "keypoint_vis": uvv[:, 2] > 0.5, "image": img}
+
+
+class EvalUtil:
+    """utils/general.py:522-611, restated per sample."""
+    def __init__(self, num_kp=21):
+        self.num_kp = num_kp
+        self.data = [[] for _ in range(num_kp)]
+
+    def feed(self, keypoint_gt, keypoint_vis, keypoint_pred):
+        gt, pr = np.squeeze(keypoint_gt), np.squeeze(keypoint_pred)
+        vis = np.squeeze(keypoint_vis).astype(bool)
+        d = np.sqrt(np.sum(np.square(gt - pr), axis=1))
+        for i in range(gt.shape[0]):
+            if vis[i]:
+                self.data[i].append(d[i])
+
+    def get_measures(self, val_min, val_max, steps):
+        trapz = getattr(np, "trapezoid", None) or np.trapz
+        th = np.linspace(val_min, val_max, steps)
+        norm = trapz(np.ones_like(th), th)
+        mean, med, auc, curves = [], [], [], []
+        for k in range(self.num_kp):
+            if not self.data[k]:
+                continue
+            d = np.array(self.data[k])
+            mean.append(d.mean()); med.append(np.median(d))
+            c = np.array([np.mean((d <= t).astype(float)) for t in th])
+            curves.append(c); auc.append(trapz(c, th) / norm)
+        return np.mean(mean), np.mean(med), np.mean(auc), np.mean(np.array(curves), 0), th

@@ -172,3 +172,48 @@ def test_network_ops_mirror(ctx):
     r = T.conv_relu(r, wd["PosePrior/conv_pose_0_2/weights"], wd["PosePrior/conv_pose_0_2/biases"], 2)
     np.testing.assert_allclose(y.cpu().numpy(), r, atol=1e-5)
     np.testing.assert_allclose(p.cpu().numpy(), T.max_pool_2x2(r), atol=1e-5)
+
+
+def _fake_rhd_record(rng):
+    xyz = rng.normal(size=(42, 3)).astype(f32); uv = rng.uniform(-5, 330, size=(42, 2)).astype(f32); K = rng.normal(size=9).astype(f32)
+    img = rng.integers(0, 256, size=(320, 320, 3), dtype=np.uint8); parts = rng.integers(0, 34, size=(320, 320), dtype=np.uint8)
+    vis = rng.integers(0, 2, size=42, dtype=np.uint8)
+    rec = xyz.tobytes() + uv.tobytes() + K.tobytes() + bytes([255, 255]) + img.tobytes() + parts.tobytes() + vis.tobytes()
+    assert len(rec) == 410520
+    return rec
+
+
+def test_decode_rhd_and_stb_records(ctx):
+    """On-device decode of the readers' binary records vs the oracle restatement (bit-exact)."""
+    from hand3d_b200.data.records import decode_rhd_records, decode_stb_records
+    rng = np.random.default_rng(16)
+    recs = [_fake_rhd_record(rng) for _ in range(3)]
+    out = decode_rhd_records(b"".join(recs))
+    for b, r in enumerate(recs):
+        ref = O.decode_rhd_record(r)
+        for k in ref:
+            np.testing.assert_array_equal(out[k][b].cpu().numpy(), ref[k], err_msg=k)
+    xyz = rng.normal(size=(21, 3)).astype(f32); uvv = np.concatenate([rng.uniform(0, 640, (21, 2)), rng.integers(0, 2, (21, 1))], 1).astype(f32)
+    img = rng.integers(0, 256, size=(480, 640, 3), dtype=np.uint8)
+    rec = xyz.tobytes() + uvv.tobytes() + img.tobytes()
+    for sub in (1, 2):
+        out = decode_stb_records(rec + rec, subsample=sub)
+        ref = O.decode_stb_record(rec, subsample=sub)
+        for k in ref:
+            np.testing.assert_array_equal(out[k][1].cpu().numpy(), ref[k], err_msg=k)
+
+
+def test_eval_util_device_matches_reference_semantics(ctx):
+    from hand3d_b200.utils.general import EvalUtil
+    rng = np.random.default_rng(17)
+    B = 40
+    gt = rng.normal(size=(B, 21, 2)).astype(f32) * 20; pred = gt + rng.normal(size=(B, 21, 2)).astype(f32) * 6
+    vis = rng.integers(0, 2, size=(B, 21)).astype(bool); vis[:, 5] = False
+    ours, ours_np, ref = EvalUtil(), EvalUtil(), O.EvalUtil()
+    ours.feed(_dev(gt), _dev(vis), _dev(pred))                        # one batched device call
+    for b in range(B):
+        ours_np.feed(gt[b], vis[b], pred[b]); ref.feed(gt[b], vis[b], pred[b])
+    for a in (ours, ours_np):
+        got, exp = a.get_measures(0.0, 30.0, 20), ref.get_measures(0.0, 30.0, 20)
+        for x, y in zip(got, exp):
+            np.testing.assert_allclose(x, y, rtol=1e-6)

@@ -209,3 +209,31 @@ def test_bone_rel_trafo_round_trip_and_kat():
     np.testing.assert_allclose(out[1], [0, 0, 4], atol=1e-12)          # finger tip: 4 bones stacked along z
     rel[0, 4, 2] = np.pi / 2                                           # rotate the first thumb bone about y by 90 degrees
     np.testing.assert_allclose(O.bone_rel_trafo_inv(rel)[0, 4], [1, 0, 0], atol=1e-12)
+
+
+def test_rhd_record_layout_kat():
+    """data/BinaryDbReader.py:103-208: 42x3 f32 | 42x2 f32 | 9 f32 | 2 B | 320x320x3 u8 | 320x320 u8 | 42 u8 = 410520 B."""
+    xyz = np.arange(126, dtype=f32).reshape(42, 3); uv = (np.arange(84, dtype=f32) + 0.75).reshape(42, 2); K = np.arange(9, dtype=f32)
+    img = np.zeros((320, 320, 3), np.uint8); img[1, 2, 0] = 255; img[3, 4, 1] = 51
+    parts = np.zeros((320, 320), np.uint8); parts[5, 6] = 1; parts[7, 8] = 2
+    vis = np.zeros(42, np.uint8); vis[41] = 1
+    rec = xyz.tobytes() + uv.tobytes() + K.tobytes() + b"\xff\xff" + img.tobytes() + parts.tobytes() + vis.tobytes()
+    d = O.decode_rhd_record(rec)
+    np.testing.assert_array_equal(d["keypoint_xyz"], xyz)
+    np.testing.assert_array_equal(d["keypoint_uv"], np.floor(uv))          # cast to int32 and back (:151-154)
+    np.testing.assert_array_equal(d["cam_mat"].ravel(), K)
+    assert d["image"][1, 2, 0] == f32(0.5) and d["image"][0, 0, 0] == f32(-0.5) and d["image"][3, 4, 1] == f32(51) / f32(255) - f32(0.5)
+    assert d["hand_mask"][7, 8, 1] == 1 and d["hand_mask"][5, 6, 1] == 0 and d["hand_mask"][5, 6, 0] == 1   # hand = parts > 1
+    assert d["keypoint_vis"][41] and not d["keypoint_vis"][0]
+    with pytest.raises(AssertionError):
+        O.decode_rhd_record(rec[:-1])
+
+
+def test_eval_util_kat():
+    e = O.EvalUtil(num_kp=2)
+    e.feed(np.array([[0.0, 0.0], [0.0, 0.0]]), np.array([1, 0]), np.array([[3.0, 4.0], [9.0, 9.0]]))    # dist 5, second invisible
+    e.feed(np.array([[0.0, 0.0], [0.0, 0.0]]), np.array([1, 0]), np.array([[0.0, 1.0], [9.0, 9.0]]))    # dist 1
+    mean, med, auc, curve, th = e.get_measures(0.0, 10.0, 11)
+    assert mean == 3.0 and med == 3.0
+    np.testing.assert_allclose(curve, [0, .5, .5, .5, .5, 1, 1, 1, 1, 1, 1])
+    np.testing.assert_allclose(auc, (0.25 + 0.5 * 3 + 0.75 + 5.0) / 10.0)
