@@ -161,7 +161,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from hand3d_b200 import runtime, weights as Wt
-    from hand3d_b200.distributed import gather_records, pack_records
+    from hand3d_b200.distributed import P2PGather, gather_records, pack_records
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,6 +183,17 @@ def run_ours(args):
     dev_imgs = [t.to(dev) for t in host_imgs]
     dev_hs = [t.to(dev) for t in host_hs]
 
+    # multi-GPU result exchange: fused pack + peer-memory all-gather kernel (NCCL all_gather only with --gather nccl)
+    p2p = None
+    if world > 1 and args.gather == "p2p":
+        p2p = P2PGather(ctx, max_batch=B)
+
+    def exchange(r):
+        if p2p is not None:
+            return p2p.gather(r["keypoint_coord3d"], r["keypoints_uv"], r["center"], r["scale_crop"])
+        rec = pack_records(r["keypoint_coord3d"], r["keypoints_uv"], r["center"], r["scale_crop"])
+        return gather_records(rec) if world > 1 else rec
+
     # one CUDA graph per input buffer (the forward pass is sync-free with fixed pointers: ~90 launches replay as one)
     graphs = None
     if args.cuda_graph:
@@ -200,8 +211,7 @@ def run_ours(args):
             graph_launches[0] += nl
         else:
             r = ctx.pipeline(dev_imgs[i % NBUF], dev_hs[i % NBUF], True, outputs="keypoints")
-        rec = pack_records(r["keypoint_coord3d"], r["keypoints_uv"], r["center"], r["scale_crop"])
-        return gather_records(rec) if world > 1 else rec
+        return exchange(r)
 
     def barrier():
         if world > 1:
@@ -262,10 +272,7 @@ def run_ours(args):
             cur.wait_event(ready[k])
             r = ctx.pipeline(stage_img[k], stage_hs[k], True, outputs="keypoints")
             consumed[k].record(cur)
-            rec = pack_records(r["keypoint_coord3d"], r["keypoints_uv"], r["center"], r["scale_crop"])
-            if world > 1:
-                rec = gather_records(rec)
-            out_host.copy_(rec, non_blocking=True)         # device -> host read of the step's result
+            out_host.copy_(exchange(r), non_blocking=True)  # device -> host read of the step's (gathered) result
 
     out_host = torch.empty((world * B, 108), dtype=torch.float32).pin_memory()
     run_e2e(max(2, args.warmup // 2))
@@ -325,7 +332,10 @@ def run_ours(args):
                        "global_batch": world * B, "precision": args.precision, "parallelism": "dp%d" % world, "cuda_graph": bool(args.cuda_graph),
                        "l2": "inputs rotate over %d distinct batches per rank (%.0f MB > L2); activations per step %.1f GB" % (
                            NBUF, NBUF * B * H * W * 12 / 1e6, B * 0.312),
-                       "collective": "all_gather of 432 B/image key-point records (NCCL)" if world > 1 else "none (single GPU)"},
+                       "collective": ("none (single GPU)" if world == 1 else
+                                      "fused pack + all-gather of 432 B/image records over NVLink peer memory (h3d_gather_records_p2p, %s)" % (
+                                          "multimem store" if (p2p is not None and p2p.mc) else "peer stores")
+                                      if p2p is not None else "NCCL all_gather of 432 B/image records")},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
@@ -351,6 +361,7 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=8, help="bounded CPU-baseline sample (images per oracle call)")
     ap.add_argument("--ref-images", type=int, default=8, help="--impl reference: images per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default=os.environ.get("H3D_GATHER", "p2p"), choices=["p2p", "nccl"], help="multi-GPU result exchange")
     ap.add_argument("--cuda-graph", type=int, default=int(os.environ.get("H3D_CUDA_GRAPH", "0")), help="replay the step from a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

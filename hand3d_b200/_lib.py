@@ -47,6 +47,7 @@ SIGNATURES = {
     "h3d_seg_postprocess": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "h3d_crop_image_from_xy": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "h3d_detect_keypoints": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "h3d_gather_records_p2p": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, C.c_uint64, _i, _i, C.c_uint32, _i64, _p]),
     "h3d_decode_records": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "h3d_eval_keypoint_dist": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "h3d_bone_rel_trafo_inv": (_i, [_p, _p, _p, _i, _p]),

@@ -986,6 +986,17 @@ int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int
     cudaFree(scratch);
     return rc;
 }
+int h3d_gather_records_p2p(h3d_ctx* ctx, const float* coord3d, const int32_t* keypoints_uv, const float* center, const float* scale_crop,
+                           int B, const uint64_t* peer_buffers, const uint64_t* peer_signals, uint64_t multicast_ptr, int rank, int world,
+                           uint32_t epoch, int64_t parity_stride_floats, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(coord3d && keypoints_uv && center && scale_crop && peer_buffers && peer_signals, "h3d_gather_records_p2p: NULL argument");
+    H3D_REQUIRE(parity_stride_floats >= (int64_t)world * B * 108, "h3d_gather_records_p2p: parity stride too small");
+    int rc = launch_gather_records_p2p(coord3d, keypoints_uv, center, scale_crop, B, peer_buffers, peer_signals, multicast_ptr, rank,
+                                       world, epoch, parity_stride_floats, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
 int h3d_decode_records(h3d_ctx* ctx, int dataset, const uint8_t* records, int B, int step, float* header, float* image, uint8_t* mask,
                        uint8_t* visibility, void* stream) {
     H3D_OP_PROLOGUE(ctx);

@@ -79,6 +79,9 @@ int launch_decode_records(const uint8_t* rec, int64_t record_bytes, int header_f
                           int64_t mask_off, int tail_bytes, float* header, float* image, uint8_t* mask, uint8_t* tail, int B,
                           cudaStream_t s);
 int launch_eval_dist(const float* gt, const uint8_t* vis, const float* pred, int n, int D, float* dist, cudaStream_t s);
+int launch_gather_records_p2p(const float* coord3d, const int32_t* uv, const float* center, const float* scale, int B,
+                              const uint64_t* peer_buffers, const uint64_t* peer_signals, uint64_t multicast_ptr, int rank, int world,
+                              uint32_t epoch, int64_t parity_stride_floats, cudaStream_t s);
 int launch_bone_rel_trafo_inv(const float* rel, float* xyz, int B, cudaStream_t s);
 int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot,
                             float* out, cudaStream_t s);

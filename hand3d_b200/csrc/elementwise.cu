@@ -764,6 +764,68 @@ int launch_eval_dist(const float* gt, const uint8_t* vis, const float* pred, int
 }
 
 // =============================================================================================
+// Fused record pack + all-gather over NVLink peer memory (SURVEY.md 8(e) "fusion target").
+// Every rank owns a symmetric gather buffer [2 parities][world*B][108] that all peers have mapped.  One CTA packs this
+// rank's 432-byte per-image records (coord3d 63 f32 | key-points 42 i32 | center 2 | scale 1) and stores them straight
+// into slot `rank` of EVERY peer's buffer (plain st.global on peer-mapped addresses, or one multimem.st on the NVSwitch
+// multicast address when available), fences at system scope, raises flag[rank] = epoch in every peer's signal pad and
+// then waits until all peers have raised theirs here: when the kernel ends the local buffer holds the full gather.
+// No NCCL launch, no separate pack kernel, one kernel on the critical path (payload is latency-bound: 13.8 KB per rank).
+// =============================================================================================
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+gather_records_p2p_kernel(const float* __restrict__ coord3d, const int32_t* __restrict__ uv, const float* __restrict__ center,
+                          const float* __restrict__ scale, int B, const uint64_t* __restrict__ peer_buffers,
+                          const uint64_t* __restrict__ peer_signals, uint64_t multicast_ptr, int rank, int world, uint32_t epoch,
+                          int64_t parity_stride_floats, int* __restrict__ err_flag) {
+    const int n = B * 108;
+    const int64_t base = (int64_t)(epoch & 1u) * parity_stride_floats + (int64_t)rank * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = i / 108, j = i - b * 108;
+        float v;
+        if (j < 63) v = coord3d[b * 63 + j];
+        else if (j < 105) v = __int_as_float(uv[b * 42 + (j - 63)]);
+        else if (j < 107) v = center[b * 2 + (j - 105)];
+        else v = scale[b];
+        if (multicast_ptr) {
+            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(reinterpret_cast<float*>(multicast_ptr) + base + i), "f"(v) : "memory");
+        } else {
+            for (int r = 0; r < world; ++r) reinterpret_cast<float*>(peer_buffers[r])[base + i] = v;   // peer-mapped NVLink stores
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const int r = threadIdx.x;
+        st_release_sys_u32(reinterpret_cast<uint32_t*>(peer_signals[r]) + rank, epoch);          // "rank's records have landed at r"
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(peer_signals[rank]) + r;
+        const long long t0 = clock64();
+        while ((int32_t)(ld_acquire_sys_u32(mine) - epoch) < 0) {                                 // wait for peer r's records
+            if (clock64() - t0 > 20000000000ll) { if (err_flag) atomicExch(err_flag, 100 + r); break; }
+        }
+    }
+    __syncthreads();
+}
+
+int launch_gather_records_p2p(const float* coord3d, const int32_t* uv, const float* center, const float* scale, int B,
+                              const uint64_t* peer_buffers, const uint64_t* peer_signals, uint64_t multicast_ptr, int rank, int world,
+                              uint32_t epoch, int64_t parity_stride_floats, cudaStream_t s) {
+    H3D_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && B > 0, "gather_records_p2p: bad geometry");
+    gather_records_p2p_kernel<<<1, 1024, 0, s>>>(coord3d, uv, center, scale, B, peer_buffers, peer_signals, multicast_ptr, rank, world,
+                                                 epoch, parity_stride_floats, nullptr);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
 // bone_rel_trafo_inv (utils/relative_trafo.py:243-295): forward kinematics over the 21-node hand chain.
 // One thread per (sample, chain): the root key-point and the 5 fingers are independent chains of rigid
 // transforms T <- Trans_z(-len) RotX(-ax) RotY(-ay) T; the key-point is inv(T) [0,0,0,1]^T = -R^T t.

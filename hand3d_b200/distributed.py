@@ -52,3 +52,42 @@ def gather_ragged_records(rec, total: int, group=None):
     pad[: sizes[rank]] = rec
     full = gather_records(pad, group).reshape(world, mx, rec.shape[1])
     return torch.cat([full[r, : sizes[r]] for r in range(world)], dim=0)
+
+
+class P2PGather:
+    """Fused record pack + all-gather over NVLink peer memory (h3d_gather_records_p2p): the per-image records are written
+    by ONE kernel straight into every peer's symmetric gather buffer (peer-mapped stores, or a multimem store on the NVSwitch
+    multicast address), with flag-based completion -- no NCCL launch and no separate pack kernel on the critical path.
+    torch.distributed._symmetric_memory only provides the allocation / address exchange (plumbing)."""
+
+    def __init__(self, ctx, max_batch: int, group=None, use_multicast: bool = True):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        self.ctx, self.C = ctx, C
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.max_batch = max_batch
+        self.stride = self.world * max_batch * RECORD_FLOATS                       # floats per parity
+        self.buf = symm_mem.empty(2 * self.stride, dtype=torch.float32, device=ctx.device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
+        self.epoch = 0
+        self.hdl.barrier()
+
+    def gather(self, coord3d, keypoints_uv, center, scale_crop):
+        """-> [world * B, 108] view of the local gather buffer holding all ranks' records (rank-major)."""
+        from . import _lib
+        B = coord3d.shape[0]
+        if B > self.max_batch:
+            raise ValueError("batch %d exceeds the gather buffer (%d)" % (B, self.max_batch))
+        self.epoch += 1
+        C = self.C
+        cs = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.ctx.lib.h3d_gather_records_p2p(
+            self.ctx.h, C.c_void_p(coord3d.data_ptr()), C.c_void_p(keypoints_uv.data_ptr()), C.c_void_p(center.data_ptr()),
+            C.c_void_p(scale_crop.data_ptr()), B, C.c_void_p(int(self.hdl.buffer_ptrs_dev)), C.c_void_p(int(self.hdl.signal_pad_ptrs_dev)),
+            C.c_uint64(self.mc), self.rank, self.world, C.c_uint32(self.epoch), C.c_int64(self.stride), C.c_void_p(cs)),
+            "h3d_gather_records_p2p")
+        off = (self.epoch & 1) * self.stride
+        return self.buf[off: off + self.world * B * RECORD_FLOATS].view(self.world * B, RECORD_FLOATS)

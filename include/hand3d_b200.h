@@ -148,6 +148,17 @@ H3D_API int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float
  * first occurrence of the maximum in row-major order. */
 H3D_API int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int C,
                          int32_t* keypoints_uv, void* stream);
+/* Multi-GPU result exchange (the reference has no multi-GPU code): packs this rank's per-image records
+ * (coord3d [B,21,3] | keypoints_uv [B,21,2] i32 | center [B,2] | scale_crop [B,1] = 108 words) and all-gathers them over
+ * NVLink peer memory in ONE kernel.  peer_buffers / peer_signals are DEVICE arrays of `world` device pointers: the
+ * symmetric gather buffers ([2][world*B][108] floats each, parity_stride_floats = world*B*108 or more) and uint32 signal pads
+ * (>= world entries, zero-initialised) of all ranks, e.g. from torch.distributed._symmetric_memory.  multicast_ptr: NVSwitch
+ * multicast address of the gather buffer or 0.  epoch must increase by 1 per call (start at 1).  On completion (stream order)
+ * the local buffer's parity (epoch & 1) holds all ranks' records in rank-major order. */
+H3D_API int h3d_gather_records_p2p(h3d_ctx* ctx, const float* coord3d, const int32_t* keypoints_uv, const float* center,
+                                   const float* scale_crop, int B, const uint64_t* peer_buffers, const uint64_t* peer_signals,
+                                   uint64_t multicast_ptr, int rank, int world, uint32_t epoch, int64_t parity_stride_floats,
+                                   void* stream);
 /* On-device decode of the dataset readers' fixed-length records.  dataset 0 = RHD
  * (data/BinaryDbReader.py:103-208; 410520-byte records: header [B,219] = 42x3 xyz | 42x2 uv | 3x3 K, image [B,320,320,3],
  * mask [B,320,320] u8, visibility [B,42] u8), dataset 1 = STB (data/BinaryDbReaderSTB.py:99-185; 922104-byte records:

@@ -17,6 +17,10 @@ for s in $STAGES; do
            done ;;
     benchfull) timeout 1200 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "benchfull rc=$?" ;;
     errors) timeout 900 python scripts/debug_errors.py > gpurun_out/errors.log 2>&1; echo "errors rc=$?" ;;
+    sanitize) for tool in ${SAN_TOOLS:-memcheck synccheck}; do
+             timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_ops.py tests/test_gpu_tc_conv.py tests/test_golden.py -q -m gpu -x --timeout 1200 \
+               -k "not test_conv2d_tc_vs_oracle or (case0 or case1 or case3 or case5)" > gpurun_out/sanitize_$tool.log 2>&1; echo "sanitize $tool rc=$?"; tail -5 gpurun_out/sanitize_$tool.log
+           done ;;
     ref)   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?" ;;
     ncu)   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
              python bench.py --steps 1 --warmup 3 --batch ${NCU_BATCH:-32} --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?" ;;

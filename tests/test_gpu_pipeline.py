@@ -258,3 +258,15 @@ def test_fp16_fast_mode_tolerance(wd):
     assert (fast["keypoints_scoremap"] - base["keypoints_scoremap"]).abs().max().item() < 1e-2
     assert (fast["keypoint_coord3d"] - base["keypoint_coord3d"]).abs().max().item() < 1e-2
     ctx.set_precision("bf16x3")
+
+
+def test_example_drivers_run():
+    """The run.py / eval2d.py shaped drivers (examples/) execute end to end on synthetic data."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for script, args in (("run_demo.py", []), ("eval2d_demo.py", ["--samples", "8", "--batch", "4"])):
+        r = subprocess.run([sys.executable, os.path.join(root, "examples", script)] + args, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert ("3D wrist" in r.stdout) or ("Area under curve" in r.stdout), r.stdout
