@@ -22,7 +22,7 @@ def _records(records, record_bytes):
     if isinstance(records, (bytes, bytearray, memoryview)):
         records = np.frombuffer(records, dtype=np.uint8)
     if isinstance(records, np.ndarray):
-        records = torch.from_numpy(np.ascontiguousarray(records, dtype=np.uint8))
+        records = torch.from_numpy(np.array(records, dtype=np.uint8, copy=True))     # own, writable host copy
     records = records.reshape(-1, record_bytes)
     if not records.is_cuda:
         records = records.pin_memory().to(runtime.default_context().device, non_blocking=True)
