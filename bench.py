@@ -311,7 +311,7 @@ def run_ours(args):
                 "achieved_per_launch": {"gflop": d["flops"] / max(1, d["launches"]) / 1e9, "us": 1e3 * d["ms"] / max(1, d["launches"])},
                 "peak_source": peaks["source"] + (", bf16 sustained" if dominant == "tc_conv" else ", nominal fp32 FFMA"),
                 "launches_per_step": d["launches"] // prof_steps, "ms_per_step": d["ms"] / prof_steps,
-                "mma_passes": 3 if args.precision in ("bf16x3", "fp16x3") else 1,
+                "mma_passes": 3 if args.precision in ("bf16x3", "fp16x3") else (2 if args.precision == "fp16_f8c" else 1),
                 "share_of_step": (d["ms"] / prof_steps) / (ms / args.steps),
                 "by_class_ms_per_step": {k: v["ms"] / prof_steps for k, v in prof.items()}}
 
@@ -325,6 +325,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16x3": "bf16 hi/lo split x3 MMA passes, fp32 accumulate (fp32 parity, 1e-3)",
                       "fp16x3": "fp16 hi/lo split x3 MMA passes, fp32 accumulate (fp32 parity, 1e-3)",
+                      "fp16_f8c": "fp16 main pass + two fp8 (e4m3) correction passes, fp32 accumulate (fp32 parity, 1e-3)",
                       "fp16": "fp16 (1e-2 path)", "bf16": "bf16", "fp32_ffma": "f32"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "full ColorHandPose3DNetwork.inference (HandSegNet+PoseNet2D+PosePrior/Viewpoint, %dx%d input, 256x256 crop), "
@@ -357,7 +358,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--height", type=int, default=320)
     ap.add_argument("--width", type=int, default=320)
-    ap.add_argument("--precision", default=os.environ.get("H3D_PRECISION", "bf16x3"), choices=["bf16x3", "fp16x3", "fp16", "bf16", "fp32_ffma"])
+    ap.add_argument("--precision", default=os.environ.get("H3D_PRECISION", "bf16x3"), choices=["bf16x3", "fp16x3", "fp16", "bf16", "fp32_ffma", "fp16_f8c"])
     ap.add_argument("--cpu-images", type=int, default=8, help="bounded CPU-baseline sample (images per oracle call)")
     ap.add_argument("--ref-images", type=int, default=8, help="--impl reference: images per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "split_fmt.cuh"
 
 namespace h3d {
 
@@ -85,7 +86,7 @@ static const std::map<std::string, VarShape>& known_vars() {
 
 // ------------------------------------------------------------------------------------------ context
 struct HostTensor { std::vector<float> data; std::vector<int64_t> shape; };
-struct PackedW { Split w; float* bias = nullptr; int Cin_pad = 0, Cout_pad = 0; };
+struct PackedW { Split w; float* bias = nullptr; int Cin_pad = 0, Cout_pad = 0; float corr_scale = 0.f; };
 
 struct Arena {   // bump allocator over the caller-owned workspace (base == nullptr -> size query)
     char* base = nullptr; int64_t off = 0;
@@ -152,8 +153,14 @@ struct h3d_ctx {
 namespace h3d {
 
 static bool is_tc(int precision) { return precision != H3D_PREC_FP32_FFMA; }
-static int passes_of(int precision) { return (precision == H3D_PREC_BF16X3 || precision == H3D_PREC_FP16X3) ? 3 : 1; }
-static Half16 half_of(int precision) { return (precision == H3D_PREC_FP16X3 || precision == H3D_PREC_FP16) ? Half16::FP16 : Half16::BF16; }
+// 1 = single 16-bit pass, 3 = hi/lo 16-bit planes (3 MMA passes), 4 = fp16 plane + e4m3 residual / coarse planes (1 fp16 + 2 fp8 passes)
+static int passes_of(int precision) {
+    if (precision == H3D_PREC_FP16_F8C) return 4;
+    return (precision == H3D_PREC_BF16X3 || precision == H3D_PREC_FP16X3) ? 3 : 1;
+}
+static Half16 half_of(int precision) {
+    return (precision == H3D_PREC_FP16X3 || precision == H3D_PREC_FP16 || precision == H3D_PREC_FP16_F8C) ? Half16::FP16 : Half16::BF16;
+}
 
 static uint16_t host_h16(float v, Half16 t) {
     if (t == Half16::FP16) { __half h = __float2half_rn(v); uint16_t b; memcpy(&b, &h, 2); return b; }
@@ -167,10 +174,23 @@ static float host_f32(uint16_t b, Half16 t) {
 // Pack HWIO fp32 -> K-major [Cout_pad][kh][kw][Cin_pad] hi/lo planes.  perm[j] = source input channel of
 // packed channel j (or -1 for zero padding); empty perm = identity.
 static int pack_conv_weights(const float* w, const float* bias, int k, int Cin, int Cout, int Cin_pad, int Cout_pad,
-                             const std::vector<int>& perm, Half16 t, bool want_lo, PackedW* out) {
+                             const std::vector<int>& perm, Half16 t, int passes, PackedW* out) {
     const int64_t Ktot = (int64_t)k * k * Cin_pad;
+    const bool want_lo = passes == 3, f8c = passes == 4;
     std::vector<uint16_t> hi((size_t)Cout_pad * Ktot, 0), lo;
+    std::vector<uint8_t> h8, l8;
     if (want_lo) lo.assign((size_t)Cout_pad * Ktot, 0);
+    int b = 0;
+    if (f8c) {
+        // e4m3 planes: wh8 = e4m3(w 2^b), wl8 = e4m3((w - fp16(w)) 2^(12+b)); b puts max|w| just below the e4m3 maximum (448).
+        // Paired with the activation planes (l8 = residual 2^10, h8 = x 2^-2) both fp8 products carry 2^(10+b).
+        float mx = 0.f;
+        for (int64_t i = 0; i < (int64_t)k * k * Cin * Cout; ++i) mx = std::max(mx, std::fabs(w[i]));
+        b = mx > 0.f ? (int)std::floor(std::log2(240.0f / mx)) : 0;
+        b = std::max(-20, std::min(20, b));
+        h8.assign((size_t)Cout_pad * Ktot, 0); l8.assign((size_t)Cout_pad * Ktot, 0);
+        out->corr_scale = std::ldexp(1.0f, -(kF8XLoShift + b));
+    }
     for (int co = 0; co < Cout; ++co)
         for (int tap = 0; tap < k * k; ++tap)
             for (int cj = 0; cj < Cin_pad; ++cj) {
@@ -181,17 +201,26 @@ static int pack_conv_weights(const float* w, const float* bias, int k, int Cin, 
                 const int64_t idx = (int64_t)co * Ktot + (int64_t)tap * Cin_pad + cj;
                 hi[idx] = h;
                 if (want_lo) lo[idx] = host_h16(v - host_f32(h, t), t);
+                if (f8c) {
+                    h8[idx] = f32_to_e4m3(std::ldexp(v, b));
+                    l8[idx] = f32_to_e4m3(std::ldexp(v - host_f32(h, t), 12 + b));
+                }
             }
-    std::vector<float> b((size_t)Cout_pad, 0.f);
-    for (int co = 0; co < Cout; ++co) b[co] = bias[co];
+    std::vector<float> bv((size_t)Cout_pad, 0.f);
+    for (int co = 0; co < Cout; ++co) bv[co] = bias[co];
     H3D_CUDA(cudaMalloc(&out->w.hi, hi.size() * 2));
     H3D_CUDA(cudaMemcpy(out->w.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
     if (want_lo) {
         H3D_CUDA(cudaMalloc(&out->w.lo, lo.size() * 2));
         H3D_CUDA(cudaMemcpy(out->w.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
     }
-    H3D_CUDA(cudaMalloc(&out->bias, b.size() * 4));
-    H3D_CUDA(cudaMemcpy(out->bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    if (f8c) {
+        H3D_CUDA(cudaMalloc(&out->w.h8, h8.size())); H3D_CUDA(cudaMalloc(&out->w.l8, l8.size()));
+        H3D_CUDA(cudaMemcpy(out->w.h8, h8.data(), h8.size(), cudaMemcpyHostToDevice));
+        H3D_CUDA(cudaMemcpy(out->w.l8, l8.data(), l8.size(), cudaMemcpyHostToDevice));
+    }
+    H3D_CUDA(cudaMalloc(&out->bias, bv.size() * 4));
+    H3D_CUDA(cudaMemcpy(out->bias, bv.data(), bv.size() * 4, cudaMemcpyHostToDevice));
     out->Cin_pad = Cin_pad; out->Cout_pad = Cout_pad;
     return H3D_OK;
 }
@@ -199,6 +228,8 @@ static int pack_conv_weights(const float* w, const float* bias, int k, int Cin, 
 static void free_packed(PackedW& p) {
     if (p.w.hi) cudaFree(p.w.hi);
     if (p.w.lo) cudaFree(p.w.lo);
+    if (p.w.l8) cudaFree(p.w.l8);
+    if (p.w.h8) cudaFree(p.w.h8);
     if (p.bias) cudaFree(p.bias);
     p = PackedW();
 }
@@ -206,14 +237,14 @@ static void free_packed(PackedW& p) {
 static int get_packed(h3d_ctx* ctx, const std::string& scope, const LayerSpec& l, int Cin_pad, const std::vector<int>& perm,
                       const PackedW** out) {
     const Half16 t = half_of(ctx->precision);
-    const bool lo = passes_of(ctx->precision) == 3;
-    const std::string key = scope + "/" + l.name + (t == Half16::FP16 ? "|h" : "|b") + (lo ? "3" : "1");
+    const int passes = passes_of(ctx->precision);
+    const std::string key = scope + "/" + l.name + (t == Half16::FP16 ? "|h" : "|b") + std::to_string(passes);
     auto it = ctx->packed.find(key);
     if (it == ctx->packed.end()) {
         auto wi = ctx->host_w.find(scope + "/" + l.name + "/weights"), bi = ctx->host_w.find(scope + "/" + l.name + "/biases");
         if (wi == ctx->host_w.end() || bi == ctx->host_w.end()) { set_error("weights for %s/%s not loaded", scope.c_str(), l.name); return H3D_EWEIGHTS; }
         PackedW p;
-        int rc = pack_conv_weights(wi->second.data.data(), bi->second.data.data(), l.k, l.cin, l.cout, Cin_pad, (int)align_up(l.cout, 64), perm, t, lo, &p);
+        int rc = pack_conv_weights(wi->second.data.data(), bi->second.data.data(), l.k, l.cin, l.cout, Cin_pad, (int)align_up(l.cout, 64), perm, t, passes, &p);
         if (rc) return rc;
         it = ctx->packed.emplace(key, p).first;
     }
@@ -291,10 +322,16 @@ struct Act {   // an activation tensor living in the workspace
     Split s;              // split view (tensor-core modes)
     int C = 0;            // channel stride
 };
-static Act slot_view(char* p, int64_t elems, int C, bool split, bool lo) {
+// planes of one activation tensor inside a slot of 4 bytes / element: passes 3 -> [hi 2B | lo 2B]; 4 -> [fp16 2B | l8 1B | h8 1B]
+static Act slot_view(char* p, int64_t elems, int C, bool split, int passes) {
     Act a; a.C = C;
-    if (split) { a.s.hi = (uint16_t*)p; a.s.lo = lo ? (uint16_t*)(p + align_up(elems * 2, 1024)) : nullptr; }
-    else a.f = (float*)p;
+    if (!split) { a.f = (float*)p; return a; }
+    a.s.hi = (uint16_t*)p;
+    if (passes == 3) a.s.lo = (uint16_t*)(p + align_up(elems * 2, 1024));
+    if (passes == 4) {
+        a.s.l8 = (uint8_t*)(p + align_up(elems * 2, 1024));
+        a.s.h8 = a.s.l8 + align_up(elems, 1024);
+    }
     return a;
 }
 
@@ -337,6 +374,7 @@ static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const L
     d.x = x; d.Cin_total = Cin_total; d.Cin_pad = Cin_pad; d.w = pw->w; d.bias = pw->bias; d.Cout = l.cout; d.Cout_pad = pw->Cout_pad;
     d.y = y; d.Cy_total = Cy_total; d.cy_off = cy_off; d.yf = yf; d.Cyf_total = Cyf_total; d.cyf_off = cyf_off;
     d.B = B; d.H = H; d.W = W; d.k = l.k; d.leaky = l.leaky; d.passes = passes_of(ctx->precision); d.half = half_of(ctx->precision);
+    d.corr_scale = pw->corr_scale;
     d.pool = pool;
     TcConvPlan* tp = tc_conv_plan_create(d);
     if (!tp) return H3D_ECUDA;
@@ -354,7 +392,8 @@ static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const L
 static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec* layers, int n, int B, int H, int W,
                        char* slot0, char* slot1, int64_t slot_elems, Act* last, int* Hout, int* Wout, Act* final_override,
                        int final_c_off) {
-    const bool tc = is_tc(ctx->precision), lo = passes_of(ctx->precision) == 3;
+    const bool tc = is_tc(ctx->precision);
+    const int lo = passes_of(ctx->precision);
     const Half16 half = half_of(ctx->precision);
     char* slots[2] = {slot0, slot1};
     int cur = 0;
@@ -382,6 +421,7 @@ static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, co
             Act pooled = slot_view(slots[cur], slot_elems, l.cout, tc, lo);
             const Act src = in;
             const int hh = h, ww = w, cc = l.cout;
+            if (tc && lo == 4) { set_error("fp16_f8c: max-pool must be fused into the convolution (even H, W required)"); return H3D_EINVAL; }
             if (tc) pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_maxpool_split(src.s, pooled.s, B, hh, ww, cc, half, s); });
             else pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_maxpool_f32(src.f, pooled.f, B, hh, ww, cc, s); });
             pl->launches.push_back(1);
@@ -406,7 +446,7 @@ static int build_handsegnet(h3d_ctx* ctx, int B, int H, int W) {
     char* other = (last.f ? (char*)last.f : (char*)last.s.hi) == slot0 ? slot1 : slot0;
     float* low = ctx->lay.seg_low;
     if (tc) {
-        Act mid = slot_view(other, (int64_t)B * h * w * 512, 512, true, passes_of(ctx->precision) == 3);
+        Act mid = slot_view(other, (int64_t)B * h * w * 512, 512, true, passes_of(ctx->precision));
         if ((rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.s, last.C, 128, {}, mid.s, 512, 0, nullptr, 0, 0))) return rc;
         if ((rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[15], B, h, w, mid.s, 512, 512, {}, Split(), 0, 0, low, 2, 0))) return rc;
     } else {
@@ -425,7 +465,8 @@ static int build_posenet(h3d_ctx* ctx, int B, int Hc, int Wc) {
     H3D_REQUIRE(Hc <= std::max(ctx->lay.H, 256) && Wc <= std::max(ctx->lay.W, 256), "PoseNet2D: crop %dx%d exceeds the workspace layout", Hc, Wc);
     auto pl = std::make_unique<StagePlan>();
     pl->B = B; pl->H = Hc; pl->W = Wc;
-    const bool tc = is_tc(ctx->precision), lo = passes_of(ctx->precision) == 3;
+    const bool tc = is_tc(ctx->precision);
+    const int lo = passes_of(ctx->precision);
     const int h8 = Hc / 8, w8 = Wc / 8;
     const int LH = std::max(ctx->lay.H, 256), LW = std::max(ctx->lay.W, 256);
     char* r = ctx->ws + ctx->lay.pose_off;
@@ -440,13 +481,14 @@ static int build_posenet(h3d_ctx* ctx, int B, int Hc, int Wc) {
     // concat buffer: tensor-core modes = split planes [pix,192] ordered (encoding 0..127 | scoremap 128..148 | zero pad);
     // fp32 mode = [pix,149] in the reference order (scoremap 0..20 | encoding 21..148)   (nets/...:210)
     Act cb;
-    if (tc) { cb.C = 192; cb.s.hi = (uint16_t*)cbuf; cb.s.lo = lo ? (uint16_t*)(cbuf + align_up(pix * 192 * 2, 1024)) : nullptr; }
+    if (tc) cb = slot_view(cbuf, pix * 192, 192, true, lo);
     else { cb.C = 149; cb.f = (float*)cbuf; }
     if (tc) {
-        uint16_t* hi = cb.s.hi; uint16_t* lop = cb.s.lo; const size_t bytes = (size_t)pix * 192 * 2;
+        const Split cs = cb.s; const size_t bytes = (size_t)pix * 192 * 2;
         pl->steps.push_back([=](const Ext&, cudaStream_t s) {   // zero the padding channels (and everything else) once per call
-            H3D_CUDA(cudaMemsetAsync(hi, 0, bytes, s));
-            if (lop) H3D_CUDA(cudaMemsetAsync(lop, 0, bytes, s));
+            H3D_CUDA(cudaMemsetAsync(cs.hi, 0, bytes, s));
+            if (cs.lo) H3D_CUDA(cudaMemsetAsync(cs.lo, 0, bytes, s));
+            if (cs.l8) { H3D_CUDA(cudaMemsetAsync(cs.l8, 0, bytes / 2, s)); H3D_CUDA(cudaMemsetAsync(cs.h8, 0, bytes / 2, s)); }
             return H3D_OK;
         });
         pl->launches.push_back(0);
@@ -683,7 +725,7 @@ int h3d_destroy(h3d_ctx* ctx) {
 }
 
 int h3d_set_precision(h3d_ctx* ctx, int precision) {
-    H3D_REQUIRE(ctx && precision >= H3D_PREC_FP32_FFMA && precision <= H3D_PREC_BF16, "h3d_set_precision: bad argument");
+    H3D_REQUIRE(ctx && precision >= H3D_PREC_FP32_FFMA && precision <= H3D_PREC_FP16_F8C, "h3d_set_precision: bad argument");
     if (precision != ctx->precision) { ctx->precision = precision; ctx->drop_plans(); }
     return H3D_OK;
 }
@@ -889,24 +931,27 @@ int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const floa
 int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y, int B, int H, int W,
                   int Cin, int Cout, int ksize, int leaky, int precision, void* stream) {
     H3D_OP_PROLOGUE(ctx);
-    H3D_REQUIRE(precision >= H3D_PREC_BF16X3 && precision <= H3D_PREC_BF16, "h3d_conv2d_tc: precision must be a tensor-core mode");
+    H3D_REQUIRE(precision >= H3D_PREC_BF16X3 && precision <= H3D_PREC_FP16_F8C, "h3d_conv2d_tc: precision must be a tensor-core mode");
     const Half16 half = half_of(precision);
     const int passes = passes_of(precision);
     const int Cin_pad = (int)align_up(Cin, 64), Cout_pad = (int)align_up(Cout, 64);
     PackedW pw;
-    int rc = pack_conv_weights(host_w_hwio, host_bias, ksize, Cin, Cout, Cin_pad, Cout_pad, {}, half, passes == 3, &pw);
+    int rc = pack_conv_weights(host_w_hwio, host_bias, ksize, Cin, Cout, Cin_pad, Cout_pad, {}, half, passes, &pw);
     if (rc) return rc;
     const int64_t rows = (int64_t)B * H * W;
     Split xs, ys;
     TcConvPlan* tp = nullptr;
     auto cleanup = [&]() {
         if (xs.hi) cudaFree(xs.hi); if (xs.lo) cudaFree(xs.lo); if (ys.hi) cudaFree(ys.hi); if (ys.lo) cudaFree(ys.lo);
+        if (xs.l8) cudaFree(xs.l8); if (xs.h8) cudaFree(xs.h8); if (ys.l8) cudaFree(ys.l8); if (ys.h8) cudaFree(ys.h8);
         if (tp) tc_conv_plan_destroy(tp);
         free_packed(pw);
     };
     auto fail = [&](int code) { cleanup(); return code; };
     if (cudaMalloc(&xs.hi, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.hi, rows * Cout_pad * 2) != cudaSuccess ||
-        (passes == 3 && (cudaMalloc(&xs.lo, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.lo, rows * Cout_pad * 2) != cudaSuccess))) {
+        (passes == 3 && (cudaMalloc(&xs.lo, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.lo, rows * Cout_pad * 2) != cudaSuccess)) ||
+        (passes == 4 && (cudaMalloc(&xs.l8, rows * Cin_pad) != cudaSuccess || cudaMalloc(&xs.h8, rows * Cin_pad) != cudaSuccess ||
+                         cudaMalloc(&ys.l8, rows * Cout_pad) != cudaSuccess || cudaMalloc(&ys.h8, rows * Cout_pad) != cudaSuccess))) {
         set_error("h3d_conv2d_tc: out of device memory");
         return fail(H3D_ECUDA);
     }
@@ -914,7 +959,7 @@ int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const 
     TcConvDesc d;
     d.x = xs; d.Cin_total = Cin_pad; d.Cin_pad = Cin_pad; d.w = pw.w; d.bias = pw.bias; d.Cout = Cout; d.Cout_pad = Cout_pad;
     d.y = ys; d.Cy_total = Cout_pad; d.cy_off = 0; d.yf = nullptr; d.Cyf_total = 0; d.cyf_off = 0;
-    d.B = B; d.H = H; d.W = W; d.k = ksize; d.leaky = leaky; d.passes = passes; d.half = half;
+    d.B = B; d.H = H; d.W = W; d.k = ksize; d.leaky = leaky; d.passes = passes; d.half = half; d.corr_scale = pw.corr_scale;
     tp = tc_conv_plan_create(d);
     if (!tp) return fail(H3D_ECUDA);
     if ((rc = tc_conv_launch(tp, s))) return fail(rc);

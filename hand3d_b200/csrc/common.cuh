@@ -42,8 +42,10 @@ constexpr float kNegSlope = 0.01f;  // utils/general.py:28
 // Activation tensors on the tensor-core path are stored as two 16-bit planes (hi, lo) with
 // x ~= hi + lo ("split" format); lo == nullptr in single-pass modes.
 struct Split {
-    uint16_t* hi = nullptr;
-    uint16_t* lo = nullptr;
+    uint16_t* hi = nullptr;   // bf16 / fp16 main plane
+    uint16_t* lo = nullptr;   // 16-bit residual plane (3-pass modes)
+    uint8_t* l8 = nullptr;    // e4m3 residual plane  (fp16_f8c mode, see split_fmt.cuh)
+    uint8_t* h8 = nullptr;    // e4m3 coarse copy     (fp16_f8c mode)
 };
 
 enum class Half16 : int { BF16 = 0, FP16 = 1 };
@@ -127,7 +129,8 @@ struct TcConvDesc {
     float* yf;
     int Cyf_total, cyf_off;
     int B, H, W, k, leaky;
-    int passes;  // 1 or 3
+    int passes;  // 1, 3, or 4 = fp16 main pass + two fp8 (e4m3) correction passes (needs the l8 / h8 planes)
+    float corr_scale = 0.f;   // passes == 4: 2^-(10 + b), un-does the scales of the fp8 operands (b: per-layer weight shift)
     Half16 half;
     int pool = 0;  // fuse the following 2x2/2 max-pool: outputs are [B, H/2, W/2, C]
 };

@@ -3,6 +3,7 @@
 // Cout = 2 / 21 score-map heads; the tiny stride-2 lifting pyramids), the fully connected layers
 // (utils/general.py:113-136) and as the fp32 yard-stick path (H3D_PREC_FP32_FFMA).
 #include "common.cuh"
+#include "split_fmt.cuh"
 
 namespace h3d {
 
@@ -27,6 +28,7 @@ struct ConvGeom {
     int B, H, W, Ho, Wo, Cin, Cout, k, stride, pad_t, pad_l;
     int Cin_total, cin_off, Cout_total, cout_off, Cs_total, cs_off;
     int leaky;
+    uint8_t* yl8; uint8_t* yh8;   // fp16_f8c planes (see split_fmt.cuh); yhi then holds fp16
     int k_per_split;     // reduction range handled by one blockIdx.z (multiple of KC); == Ktot when not split
     float* partial;      // split-K: raw partial sums [gridDim.z][M][Cout]
 };
@@ -165,9 +167,14 @@ conv_direct_kernel(const float* __restrict__ x, const float* __restrict__ w, con
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (nb + j < g.Cout) {
-                    const uint16_t h = to_h16<FP16>(o[j]);
-                    yhi[off + j] = h;
-                    if (ylo) ylo[off + j] = to_h16<FP16>(o[j] - from_h16<FP16>(h));
+                    if (g.yl8) {
+                        const F8cPlanes pl = f32_to_f8c(o[j]);
+                        yhi[off + j] = pl.h16; g.yl8[off + j] = pl.l8; g.yh8[off + j] = pl.h8;
+                    } else {
+                        const uint16_t h = to_h16<FP16>(o[j]);
+                        yhi[off + j] = h;
+                        if (ylo) ylo[off + j] = to_h16<FP16>(o[j] - from_h16<FP16>(h));
+                    }
                 }
             }
         }
@@ -199,8 +206,8 @@ constexpr int C3_TH = 8, C3_TW = 32, C3_LD = 40, C3_TILES_PER_CTA = 4;   // tile
 template <bool FP16>
 __global__ void __launch_bounds__(256, 2)
 conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
-                  uint16_t* __restrict__ yhi, uint16_t* __restrict__ ylo, int B, int H, int W, int Cy_total, int cy_off,
-                  int Cs_total, int cs_off, int leaky) {
+                  uint16_t* __restrict__ yhi, uint16_t* __restrict__ ylo, uint8_t* __restrict__ yl8, uint8_t* __restrict__ yh8, int B, int H,
+                  int W, int Cy_total, int cy_off, int Cs_total, int cs_off, int leaky) {
     __shared__ __align__(16) float ws[27][64];
     __shared__ __align__(16) float xs[3][C3_TH + 2][C3_LD];
     const int t = threadIdx.x;
@@ -273,7 +280,15 @@ conv3x3_c3_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
             dst[0] = make_float4(o[0], o[1], o[2], o[3]);
             dst[1] = make_float4(o[4], o[5], o[6], o[7]);
         }
-        if (yhi) {
+        if (yhi && yl8) {            // fp16 + e4m3 planes (fp16_f8c)
+            uint16_t h[8]; uint8_t l8[8], h8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const F8cPlanes pl = f32_to_f8c(o[j]); h[j] = pl.h16; l8[j] = pl.l8; h8[j] = pl.h8; }
+            const int64_t off = pix * Cs_total + cs_off + cg * 8;
+            *reinterpret_cast<uint4*>(yhi + off) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint2*>(yl8 + off) = *reinterpret_cast<const uint2*>(l8);
+            *reinterpret_cast<uint2*>(yh8 + off) = *reinterpret_cast<const uint2*>(h8);
+        } else if (yhi) {
             uint16_t h[8], l[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) { h[j] = to_h16<FP16>(o[j]); l[j] = to_h16<FP16>(o[j] - from_h16<FP16>(h[j])); }
@@ -302,6 +317,7 @@ static void plan_direct(const DirectConvArgs& a, ConvGeom* gp, dim3* gridp, int*
     g.pad_t = tot_h / 2; g.pad_l = tot_w / 2;   // TF 'SAME': the odd pixel goes to the bottom / right
     g.Cin_total = a.Cin_total; g.cin_off = a.cin_off; g.Cout_total = a.Cout_total; g.cout_off = a.cout_off;
     g.Cs_total = a.Cs_total; g.cs_off = a.cs_off; g.leaky = a.leaky;
+    g.yl8 = a.ys.l8; g.yh8 = a.ys.h8;
     const int64_t M = (int64_t)g.B * g.Ho * g.Wo;
     dim3 grid((unsigned)ceil_div64(M, TM), (unsigned)ceil_div(a.Cout, TN));
     const int Ktot = a.k * a.k * a.Cin;
@@ -335,9 +351,9 @@ int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
     if (is_c3_case(a)) {
         const int tiles = ceil_div(ceil_div(a.W, C3_TW) * ceil_div(a.H, C3_TH) * a.B, C3_TILES_PER_CTA);
         if (a.half == Half16::FP16)
-            conv3x3_c3_kernel<true><<<tiles, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, a.B, a.H, a.W, a.Cout_total, a.cout_off, a.Cs_total, a.cs_off, a.leaky);
+            conv3x3_c3_kernel<true><<<tiles, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, a.ys.l8, a.ys.h8, a.B, a.H, a.W, a.Cout_total, a.cout_off, a.Cs_total, a.cs_off, a.leaky);
         else
-            conv3x3_c3_kernel<false><<<tiles, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, a.B, a.H, a.W, a.Cout_total, a.cout_off, a.Cs_total, a.cs_off, a.leaky);
+            conv3x3_c3_kernel<false><<<tiles, 256, 0, s>>>(a.x, a.w, a.bias, a.y, a.ys.hi, a.ys.lo, a.ys.l8, a.ys.h8, a.B, a.H, a.W, a.Cout_total, a.cout_off, a.Cs_total, a.cs_off, a.leaky);
         H3D_CHECK_LAUNCH();
         return H3D_OK;
     }

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "split_fmt.cuh"
 
 namespace h3d {
 
@@ -36,15 +37,21 @@ constexpr int kThreads = 32 * (kNumEpilogueWarps + 2);
 constexpr int kSmemBudget = 227 * 1024 - 2048;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 
-__host__ __device__ constexpr int stage_bytes(int BN, int PASSES) { return (PASSES == 3 ? 2 : 1) * (A_TILE_BYTES + BN * BK * 2); }
+// PASSES: 1 = one 16-bit pass; 3 = hi/lo 16-bit planes, three passes; 4 = fp16 plane + two e4m3 planes (each half the bytes),
+// one fp16 pass + two fp8 passes.  Modes 3 and 4 stage the same number of bytes.
+__host__ __device__ constexpr int stage_bytes(int BN, int PASSES) { return (PASSES >= 3 ? 2 : 1) * (A_TILE_BYTES + BN * BK * 2); }
 __host__ __device__ constexpr int num_stages(int BN, int PASSES) {
     return kSmemBudget / stage_bytes(BN, PASSES) > 8 ? 8 : kSmemBudget / stage_bytes(BN, PASSES);
 }
-__host__ __device__ constexpr int tmem_cols(int BN) { return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512; }
+__host__ __device__ constexpr int tmem_cols(int BN, int PASSES = 1) {   // two accumulator stages (x2 in mode 4: main + correction)
+    return (PASSES == 4 ? 4 : 2) * BN <= 32 ? 32 : (PASSES == 4 ? 4 : 2) * BN <= 64 ? 64 : (PASSES == 4 ? 4 : 2) * BN <= 128 ? 128
+           : (PASSES == 4 ? 4 : 2) * BN <= 256 ? 256 : 512;
+}
 
 struct TcParams {
     const float* bias;
-    uint16_t* y_hi; uint16_t* y_lo; int Cy_total, cy_off;
+    uint16_t* y_hi; uint16_t* y_lo; uint8_t* y_l8; uint8_t* y_h8; int Cy_total, cy_off;
+    float corr_scale;   // mode 4: weight of the fp8 correction accumulator
     float* yf; int Cyf_total, cyf_off;
     int B, H, W, k, pad, cin_chunks;
     int TW, TH, TB, tiles_w, tiles_h, n_tiles, num_tiles;
@@ -114,6 +121,13 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -172,6 +186,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
 // LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version = 1, layout = SWIZZLE_128B (2).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Same for the 8-bit planes: rows of 64 bytes (64 e4m3 values), SWIZZLE_64B (layout 4), SBO = 512 B (8 rows x 64 B).
+__device__ __forceinline__ uint64_t make_smem_desc64(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format f32 (bit 4), a/b format (bits 7, 10:
 // 0 = f16, 1 = bf16), K-major A and B (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
@@ -237,6 +255,10 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
                         const float2 r = unpack2<FP16>(h2);
                         p.y_lo[off + q] = (uint16_t)(pack_hi2<FP16>(f[q] - r.x, 0.f) & 0xFFFFu);
                     }
+                    if (PASSES == 4) {
+                        const F8cPlanes pl = f32_to_f8c(f[q]);
+                        p.y_l8[off + q] = pl.l8; p.y_h8[off + q] = pl.h8;
+                    }
                 }
             }
         }
@@ -266,6 +288,23 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
             dh[g] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (PASSES == 3 && p.y_lo) dl[g] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
+        if (PASSES == 4) {   // e4m3 residual and coarse planes: 32 bytes each
+            uint32_t l8[8], h8[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                uint32_t wl = 0, wh = 0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const F8cPlanes pl = f32_to_f8c(f[4 * q + e]);
+                    wl |= (uint32_t)pl.l8 << (8 * e); wh |= (uint32_t)pl.h8 << (8 * e);
+                }
+                l8[q] = wl; h8[q] = wh;
+            }
+            uint4* d8l = reinterpret_cast<uint4*>(p.y_l8 + off);
+            uint4* d8h = reinterpret_cast<uint4*>(p.y_h8 + off);
+            d8l[0] = make_uint4(l8[0], l8[1], l8[2], l8[3]); d8l[1] = make_uint4(l8[4], l8[5], l8[6], l8[7]);
+            d8h[0] = make_uint4(h8[0], h8[1], h8[2], h8[3]); d8h[1] = make_uint4(h8[4], h8[5], h8[6], h8[7]);
+        }
     }
 }
 
@@ -273,12 +312,18 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
 template <int BN, int PASSES, bool FP16>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
-               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ CUtensorMap map_x_h8, const __grid_constant__ CUtensorMap map_w_l8, const TcParams p) {
+    // mode 4 operand planes: x_hi = fp16(x), x_lo -> l8 (x residual, e4m3), x_h8 (x, e4m3); w_hi = fp16(w), w_lo -> wh8 (w, e4m3),
+    // w_l8 (w residual, e4m3).  Passes: fp16 x_hi*w_hi -> main accumulator; e4m3 l8*wh8 + x_h8*w_l8 -> correction accumulator.
     constexpr int STAGES = num_stages(BN, PASSES);
     constexpr int STAGE_BYTES = stage_bytes(BN, PASSES);
     constexpr int B_TILE_BYTES = BN * BK * 2;
+    constexpr int A8_TILE_BYTES = BM * BK, B8_TILE_BYTES = BN * BK;       // e4m3 tiles: 64-byte rows
     constexpr uint32_t IDESC = make_idesc(BN, FP16);
+    constexpr int ACC_COLS = (PASSES == 4 ? 2 : 1) * BN;                   // TMEM columns per accumulator stage
     static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
+    static_assert(PASSES != 4 || (FP16 && BN <= 128), "fp8-correction mode: fp16 main plane, two accumulators per stage (BN <= 128)");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -293,13 +338,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
 
     if (warp == 4 && lane == 0) {
         prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w_hi);
-        if (PASSES == 3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
+        if (PASSES >= 3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
+        if (PASSES == 4) { prefetch_tmap(&map_x_h8); prefetch_tmap(&map_w_l8); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kNumEpilogueWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN, PASSES)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -323,10 +369,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                             uint8_t* st = smem + stage * STAGE_BYTES;
                             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                             tma_load_4d(&map_x_hi, st, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
-                            tma_load_2d(&map_w_hi, st + (PASSES == 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
+                            tma_load_2d(&map_w_hi, st + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
                             if (PASSES == 3) {
                                 tma_load_4d(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
                                 tma_load_2d(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
+                            }
+                            if (PASSES == 4) {   // stage = [x fp16 16K | x l8 8K | x h8 8K | w fp16 | w h8 | w l8]
+                                tma_load_4d(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                tma_load_4d(&map_x_h8, st + A_TILE_BYTES + A8_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                tma_load_2d(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
+                                tma_load_2d(&map_w_l8, st + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES, &full_bar[stage], kcol, n0);
                             }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
@@ -344,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                     const int acc = acc_it & 1;
                     mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
                     const int kb1 = min(kblocks, kb0 + p.chunk_kb);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
@@ -352,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                         const uint64_t a_hi = make_smem_desc(sa);
                         const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
-                        const uint64_t b_hi = make_smem_desc(sa + (PASSES == 3 ? 2 : 1) * A_TILE_BYTES);
+                        const uint64_t b_hi = make_smem_desc(sa + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES);
                         const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
                         for (int j = 0; j < BK / UMMA_K; ++j) {
@@ -361,6 +413,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                             if (PASSES == 3) {
                                 tc_mma_f16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
                                 tc_mma_f16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+                            }
+                        }
+                        if (PASSES == 4) {   // two e4m3 correction passes (K = 32 per MMA: 32 bytes per row) into the second accumulator
+                            const uint64_t a_l8 = make_smem_desc64(sa + A_TILE_BYTES), a_h8 = make_smem_desc64(sa + A_TILE_BYTES + A8_TILE_BYTES);
+                            const uint64_t b_h8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                            const uint64_t b_l8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t koff = (uint64_t)((j * 32) >> 4);
+                                tc_mma_f8(d_tmem + BN, a_l8 + koff, b_h8 + koff, IDESC, (uint32_t)((kb > kb0) | (j != 0)));
+                                tc_mma_f8(d_tmem + BN, a_h8 + koff, b_l8 + koff, IDESC, 1u);
                             }
                         }
                         tc_commit(&empty_bar[stage]);   // frees the smem stage once the MMAs above have read it
@@ -394,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                     const int acc = acc_it & 1;
                     mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, p.err_flag, 4);
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 #pragma unroll
                     for (int c0 = 0; c0 < BN; c0 += 32) {
                         uint32_t v[32];
@@ -406,6 +469,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                         } else {
 #pragma unroll
                             for (int q = 0; q < 32; ++q) racc[c0 + q] += __uint_as_float(v[q]);
+                        }
+                        if (PASSES == 4) {   // + corr_scale * (fp8 correction accumulator)
+                            tc_ld_32x32b_x32(taddr + BN + c0, v);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) racc[c0 + q] = fmaf(p.corr_scale, __uint_as_float(v[q]), racc[c0 + q]);
                         }
                     }
                     tc_fence_before();
@@ -442,7 +511,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN, PASSES)) : "memory");
     }
 }
 
@@ -635,30 +704,31 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-bool encode_act_map(CUtensorMap* m, const uint16_t* base, int C_total, int C_used, int W, int H, int B, int TW, int TH, int TB) {
+// es = element size in bytes: 2 (bf16 / fp16 planes, 128-byte rows, SWIZZLE_128B) or 1 (e4m3 planes, 64-byte rows, SWIZZLE_64B)
+bool encode_act_map(CUtensorMap* m, const void* base, int C_total, int C_used, int W, int H, int B, int TW, int TH, int TB, int es = 2) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[4] = {(cuuint64_t)C_used, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C_total * 2, (cuuint64_t)W * C_total * 2, (cuuint64_t)H * W * C_total * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)C_total * es, (cuuint64_t)W * C_total * es, (cuuint64_t)H * W * C_total * es};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint16_t*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, es == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return false; }
     return true;
 }
 
-bool encode_w_map(CUtensorMap* m, const uint16_t* base, int Ktot, int Cout_pad, int BN) {
+bool encode_w_map(CUtensorMap* m, const void* base, int Ktot, int Cout_pad, int BN, int es = 2) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout_pad};
-    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * es};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, es == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return false; }
     return true;
 }
@@ -682,7 +752,7 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s);
 struct TcConvPlan {
     bool two_cta = false;
     TcConvDesc d;
-    CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo;
+    CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo, map_x_h8, map_w_l8;
     TcParams p;
     int BN, grid;
     int* err_flag;
@@ -706,7 +776,8 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s) {
         H3D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, PASSES, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    conv_tc_kernel<BN, PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
+    conv_tc_kernel<BN, PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->map_x_h8,
+                                                                      pl->map_w_l8, pl->p);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }
@@ -728,7 +799,7 @@ int launch_inst2(const TcConvPlan* pl, cudaStream_t s) {
 }  // namespace
 
 TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
-    if (d.Cin_pad % BK != 0 || d.Cout_pad % 64 != 0 || (d.k != 1 && d.k != 3 && d.k != 5 && d.k != 7) || (d.passes != 1 && d.passes != 3)) {
+    if (d.Cin_pad % BK != 0 || d.Cout_pad % 64 != 0 || (d.k != 1 && d.k != 3 && d.k != 5 && d.k != 7) || (d.passes != 1 && d.passes != 3 && d.passes != 4)) {
         set_error("tc_conv: unsupported geometry (Cin_pad=%d Cout_pad=%d k=%d passes=%d)", d.Cin_pad, d.Cout_pad, d.k, d.passes);
         return nullptr;
     }
@@ -737,6 +808,12 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if (d.yf && !padded_out && ((d.Cyf_total % 4) || (d.cyf_off % 4))) { set_error("tc_conv: fp32 output channel offset/stride must be multiples of 4"); return nullptr; }
     if (padded_out && d.pool) { set_error("tc_conv: fused pooling needs Cout %% 32 == 0"); return nullptr; }
     if (d.passes == 3 && (!d.x.lo || !d.w.lo)) { set_error("tc_conv: 3-pass mode needs lo planes"); return nullptr; }
+    if (d.passes == 4 && (!d.x.l8 || !d.x.h8 || !d.w.l8 || !d.w.h8 || d.half != Half16::FP16 || d.corr_scale <= 0.f)) {
+        set_error("tc_conv: fp8-correction mode needs fp16 + e4m3 l8/h8 planes for activations and weights and a correction scale");
+        return nullptr;
+    }
+    if (d.passes == 4 && d.y.hi && (!d.y.l8 || !d.y.h8)) { set_error("tc_conv: fp8-correction mode needs l8/h8 output planes"); return nullptr; }
+    if (d.passes == 4 && d.y.hi && ((d.Cy_total % 16) || (d.cy_off % 16))) { set_error("tc_conv: fp8 planes need 16-channel aligned offsets"); return nullptr; }
     TcConvPlan* pl = new TcConvPlan();
     pl->d = d;
     int BN = d.Cout_pad % 128 == 0 ? 128 : 64;
@@ -744,10 +821,11 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     // shared-memory traffic either way and the single-CTA kernel is as fast or faster).  H3D_TC_2CTA=0/1 forces one kernel.
     bool two = d.Cout_pad % 256 == 0;
     if (const char* e = getenv("H3D_TC_2CTA")) two = atoi(e) != 0;
+    if (d.passes == 4) two = false;   // two accumulators per stage: BN <= 128, single-CTA kernel
     if (two) BN = d.Cout_pad % 256 == 0 ? 256 : (d.Cout_pad % 128 == 0 ? 128 : 64);   // CTA pair: UMMA 256 x BN
     if (const char* e = getenv("H3D_TC_BN")) {
         const int v = atoi(e);
-        if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
+        if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0 && !(d.passes == 4 && v > 128)) BN = v;
     }
     pl->BN = BN;
     pl->two_cta = two;
@@ -756,7 +834,8 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     choose_tile(d.B, d.H, d.W, &TW, &TH, &TB, d.pool != 0);
     TcParams& p = pl->p;
     p.bias = d.bias;
-    p.y_hi = d.y.hi; p.y_lo = d.y.lo; p.Cy_total = d.Cy_total; p.cy_off = d.cy_off;
+    p.y_hi = d.y.hi; p.y_lo = d.y.lo; p.y_l8 = d.y.l8; p.y_h8 = d.y.h8; p.Cy_total = d.Cy_total; p.cy_off = d.cy_off;
+    p.corr_scale = d.corr_scale;
     p.yf = d.yf; p.Cyf_total = d.Cyf_total; p.cyf_off = d.cyf_off;
     p.B = d.B; p.H = d.H; p.W = d.W; p.k = d.k; p.pad = d.k / 2; p.cin_chunks = d.Cin_pad / BK;
     p.TW = TW; p.TH = TH; p.TB = TB;
@@ -771,7 +850,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     p.err_flag = nullptr;
     // <= ~108 accumulating MMAs per TMEM partial sum (9 K blocks x 4 K steps x 3 passes); BN = 256 keeps everything in
     // TMEM (its 256 fp32 partial sums per thread would not fit the register file)
-    p.chunk_kb = d.passes == 3 ? 9 : 27;
+    p.chunk_kb = d.passes >= 3 ? 9 : 27;
     if (const char* e = getenv("H3D_TC_CHUNK_KB")) { const int v = atoi(e); if (v > 0) p.chunk_kb = v; }
     if (BN > 128 && !two) p.chunk_kb = 1 << 30;
     pl->grid = two ? 2 * std::min(p.num_tiles, tc_num_sms() / 2) : std::min(p.num_tiles, tc_num_sms());
@@ -782,7 +861,13 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if (ok && d.passes == 3)
         ok = encode_act_map(&pl->map_x_lo, d.x.lo, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB) &&
              encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, w_box_rows);
+    if (ok && d.passes == 4)   // e4m3 planes: x residual (slot "lo"), x coarse, w coarse (slot "lo"), w residual
+        ok = encode_act_map(&pl->map_x_lo, d.x.l8, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB, 1) &&
+             encode_act_map(&pl->map_x_h8, d.x.h8, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB, 1) &&
+             encode_w_map(&pl->map_w_lo, d.w.h8, Ktot, d.Cout_pad, w_box_rows, 1) &&
+             encode_w_map(&pl->map_w_l8, d.w.l8, Ktot, d.Cout_pad, w_box_rows, 1);
     if (ok && d.passes == 1) { pl->map_x_lo = pl->map_x_hi; pl->map_w_lo = pl->map_w_hi; }
+    if (ok && d.passes != 4) { pl->map_x_h8 = pl->map_x_hi; pl->map_w_l8 = pl->map_w_hi; }
     if (!ok) { delete pl; return nullptr; }
     return pl;
 }
@@ -810,6 +895,8 @@ int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
         return fp16 ? launch_inst<BN_, P_, true>(pl, s) : launch_inst<BN_, P_, false>(pl, s);
     switch (key) {
         CASE(64, 1) CASE(64, 3) CASE(128, 1) CASE(128, 3) CASE(256, 1) CASE(256, 3)
+        case 64 * 10 + 4: return launch_inst<64, 4, true>(pl, s);      // fp16 + e4m3 corrections
+        case 128 * 10 + 4: return launch_inst<128, 4, true>(pl, s);
     }
 #undef CASE
     set_error("tc_conv: no kernel instance for BN=%d passes=%d", pl->BN, pl->d.passes);

@@ -6,6 +6,7 @@
 // __fmul_rn/__fadd_rn/__fsub_rn so that nvcc cannot contract to FMA: the TF-1.3 CPU kernels the
 // oracle restates use separate multiply and add.
 #include "common.cuh"
+#include "split_fmt.cuh"
 
 namespace h3d {
 
@@ -251,7 +252,30 @@ __global__ void split_to_f32_kernel(const uint16_t* __restrict__ hi, const uint1
         y[i] = v;
     }
 }
+__global__ void f32_to_f8c_kernel(const float* __restrict__ x, uint16_t* __restrict__ h16, uint8_t* __restrict__ l8, uint8_t* __restrict__ h8,
+                                  int64_t rows, int C, int Cpad) {
+    const int64_t total = rows * Cpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cpad);
+        const F8cPlanes p = f32_to_f8c(c < C ? x[(i / Cpad) * C + c] : 0.f);
+        h16[i] = p.h16; l8[i] = p.l8; h8[i] = p.h8;
+    }
+}
+__global__ void f8c_to_f32_kernel(const uint16_t* __restrict__ h16, const uint8_t* __restrict__ l8, float* __restrict__ y, int64_t rows, int C,
+                                  int Cpad) {
+    const int64_t total = rows * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = (i / C) * Cpad + (i % C);
+        y[i] = __half2float(__ushort_as_half(h16[j])) + e4m3_to_f32(l8[j]) * (1.0f / kF8XLoScale);
+    }
+}
+
 int launch_f32_to_split(const float* x, Split y, int64_t rows, int C, int Cpad, Half16 t, cudaStream_t s) {
+    if (y.l8) {
+        f32_to_f8c_kernel<<<(int)std::min<int64_t>(ceil_div64(rows * Cpad, 256), 148 * 32), 256, 0, s>>>(x, y.hi, y.l8, y.h8, rows, C, Cpad);
+        H3D_CHECK_LAUNCH();
+        return H3D_OK;
+    }
     const int blocks = (int)std::min<int64_t>(ceil_div64(rows * Cpad, 256), 148 * 32);
     if (t == Half16::FP16) f32_to_split_kernel<true><<<blocks, 256, 0, s>>>(x, y.hi, y.lo, rows, C, Cpad);
     else f32_to_split_kernel<false><<<blocks, 256, 0, s>>>(x, y.hi, y.lo, rows, C, Cpad);
@@ -259,6 +283,11 @@ int launch_f32_to_split(const float* x, Split y, int64_t rows, int C, int Cpad, 
     return H3D_OK;
 }
 int launch_split_to_f32(Split x, float* y, int64_t rows, int C, int Cpad, Half16 t, cudaStream_t s) {
+    if (x.l8) {
+        f8c_to_f32_kernel<<<(int)std::min<int64_t>(ceil_div64(rows * C, 256), 148 * 32), 256, 0, s>>>(x.hi, x.l8, y, rows, C, Cpad);
+        H3D_CHECK_LAUNCH();
+        return H3D_OK;
+    }
     const int blocks = (int)std::min<int64_t>(ceil_div64(rows * C, 256), 148 * 32);
     if (t == Half16::FP16) split_to_f32_kernel<true><<<blocks, 256, 0, s>>>(x.hi, x.lo, y, rows, C, Cpad);
     else split_to_f32_kernel<false><<<blocks, 256, 0, s>>>(x.hi, x.lo, y, rows, C, Cpad);

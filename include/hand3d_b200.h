@@ -45,6 +45,7 @@ extern "C" {
 #define H3D_PREC_FP16X3 2     /* tcgen05, fp16 hi/lo split, 3 MMA passes, fp32 accumulate (fp32 parity) */
 #define H3D_PREC_FP16 3       /* tcgen05, fp16 single pass, fp32 accumulate (BASELINE config 5, 1e-2)   */
 #define H3D_PREC_BF16 4       /* tcgen05, bf16 single pass                                              */
+#define H3D_PREC_FP16_F8C 5   /* tcgen05, fp16 main pass + two fp8 (e4m3) correction passes, fp32 accumulate (fp32 parity) */
 
 /* PosePriorNetwork variants (nets/PosePriorNetwork.py:64-93). */
 #define H3D_VARIANT_DIRECT 0

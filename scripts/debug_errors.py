@@ -17,8 +17,10 @@ def stats(a, ref):
 
 def main():
     wd = Wt.synthetic_weights(0)
-    img = Wt.synthetic_images(2, 320, 320, seed=1)
-    crop = Wt.synthetic_images(2, 256, 256, seed=11)
+    import os
+    nimg = int(os.environ.get("ERR_IMAGES", "2"))
+    img = Wt.synthetic_images(nimg, 320, 320, seed=1)
+    crop = Wt.synthetic_images(nimg, 256, 256, seed=11)
     ref_seg64 = O.inference_detection(img, wd, dtype=np.float64)[-1]
     ref_seg32 = O.inference_detection(img, wd)[-1]
     ref_pose64 = O.inference_pose2d(crop, wd, dtype=np.float64)
@@ -26,7 +28,7 @@ def main():
     out = {"oracle_fp32": {"seg": stats(ref_seg32, ref_seg64), "pose": [stats(a, b) for a, b in zip(ref_pose32, ref_pose64)]}}
     ctx = runtime.default_context()
     ctx.load_weights(wd)
-    for prec in ["fp32_ffma", "bf16x3", "fp16x3", "fp16", "bf16"]:
+    for prec in sys.argv[1:] or ["fp32_ffma", "bf16x3", "fp16x3", "fp16_f8c", "fp16", "bf16"]:
         ctx.set_precision(prec)
         seg = ctx.handsegnet(torch.from_numpy(img).cuda()).cpu().numpy()
         pose = [p.cpu().numpy() for p in ctx.posenet(torch.from_numpy(crop).cuda())]

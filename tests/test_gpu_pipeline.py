@@ -12,8 +12,8 @@ from oracle import tf1_ops as T
 
 pytestmark = pytest.mark.gpu
 f32 = np.float32
-PARITY_MODES = ["fp32_ffma", "bf16x3", "fp16x3"]
-TOL = {"fp32_ffma": 1e-3, "bf16x3": 1e-3, "fp16x3": 1e-3, "fp16": 1e-2}
+PARITY_MODES = ["fp32_ffma", "bf16x3", "fp16x3", "fp16_f8c"]
+TOL = {"fp32_ffma": 1e-3, "bf16x3": 1e-3, "fp16x3": 1e-3, "fp16_f8c": 1e-3, "fp16": 1e-2}
 
 
 @pytest.fixture(scope="module")
