@@ -197,14 +197,17 @@ static int pack_conv_weights(const float* w, const float* bias, int k, int Cin, 
                 const int ci = perm.empty() ? (cj < Cin ? cj : -1) : perm[cj];
                 if (ci < 0) continue;
                 const float v = w[((int64_t)tap * Cin + ci) * Cout + co];
-                const uint16_t h = host_h16(v, t);
                 const int64_t idx = (int64_t)co * Ktot + (int64_t)tap * Cin_pad + cj;
+                if (f8c) {   // all three planes pre-scaled so that every operand product carries 2^(10+b) (see split_fmt.cuh)
+                    const uint16_t h = host_h16(std::ldexp(v, kF8XMainShift + b), t);
+                    hi[idx] = h;
+                    h8[idx] = f32_to_e4m3(std::ldexp(v, b));
+                    l8[idx] = f32_to_e4m3(std::ldexp(v - std::ldexp(host_f32(h, t), -(kF8XMainShift + b)), 12 + b));
+                    continue;
+                }
+                const uint16_t h = host_h16(v, t);
                 hi[idx] = h;
                 if (want_lo) lo[idx] = host_h16(v - host_f32(h, t), t);
-                if (f8c) {
-                    h8[idx] = f32_to_e4m3(std::ldexp(v, b));
-                    l8[idx] = f32_to_e4m3(std::ldexp(v - host_f32(h, t), 12 + b));
-                }
             }
     std::vector<float> bv((size_t)Cout_pad, 0.f);
     for (int co = 0; co < Cout; ++co) bv[co] = bias[co];

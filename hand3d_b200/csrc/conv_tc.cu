@@ -43,15 +43,12 @@ __host__ __device__ constexpr int stage_bytes(int BN, int PASSES) { return (PASS
 __host__ __device__ constexpr int num_stages(int BN, int PASSES) {
     return kSmemBudget / stage_bytes(BN, PASSES) > 8 ? 8 : kSmemBudget / stage_bytes(BN, PASSES);
 }
-__host__ __device__ constexpr int tmem_cols(int BN, int PASSES = 1) {   // two accumulator stages (x2 in mode 4: main + correction)
-    return (PASSES == 4 ? 4 : 2) * BN <= 32 ? 32 : (PASSES == 4 ? 4 : 2) * BN <= 64 ? 64 : (PASSES == 4 ? 4 : 2) * BN <= 128 ? 128
-           : (PASSES == 4 ? 4 : 2) * BN <= 256 ? 256 : 512;
-}
+__host__ __device__ constexpr int tmem_cols(int BN) { return 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512; }
 
 struct TcParams {
     const float* bias;
     uint16_t* y_hi; uint16_t* y_lo; uint8_t* y_l8; uint8_t* y_h8; int Cy_total, cy_off;
-    float corr_scale;   // mode 4: weight of the fp8 correction accumulator
+    float corr_scale;   // mode 4: 2^-(10+b), un-does the pre-scaling of the operand planes
     float* yf; int Cyf_total, cyf_off;
     int B, H, W, k, pad, cin_chunks;
     int TW, TH, TB, tiles_w, tiles_h, n_tiles, num_tiles;
@@ -168,6 +165,13 @@ __device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t adesc,
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f8_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs (mask 0b11)
 __device__ __forceinline__ void tc_commit_2cta(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -218,10 +222,17 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         const float4 bv = __ldg(bp + q);
-        f[4 * q + 0] = a[4 * q + 0] + bv.x;
-        f[4 * q + 1] = a[4 * q + 1] + bv.y;
-        f[4 * q + 2] = a[4 * q + 2] + bv.z;
-        f[4 * q + 3] = a[4 * q + 3] + bv.w;
+        if (PASSES == 4) {   // un-do the operand pre-scaling (exact power of two)
+            f[4 * q + 0] = fmaf(a[4 * q + 0], p.corr_scale, bv.x);
+            f[4 * q + 1] = fmaf(a[4 * q + 1], p.corr_scale, bv.y);
+            f[4 * q + 2] = fmaf(a[4 * q + 2], p.corr_scale, bv.z);
+            f[4 * q + 3] = fmaf(a[4 * q + 3], p.corr_scale, bv.w);
+        } else {
+            f[4 * q + 0] = a[4 * q + 0] + bv.x;
+            f[4 * q + 1] = a[4 * q + 1] + bv.y;
+            f[4 * q + 2] = a[4 * q + 2] + bv.z;
+            f[4 * q + 3] = a[4 * q + 3] + bv.w;
+        }
     }
     if (p.leaky) {
 #pragma unroll
@@ -315,15 +326,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_x_h8, const __grid_constant__ CUtensorMap map_w_l8, const TcParams p) {
     // mode 4 operand planes: x_hi = fp16(x), x_lo -> l8 (x residual, e4m3), x_h8 (x, e4m3); w_hi = fp16(w), w_lo -> wh8 (w, e4m3),
-    // w_l8 (w residual, e4m3).  Passes: fp16 x_hi*w_hi -> main accumulator; e4m3 l8*wh8 + x_h8*w_l8 -> correction accumulator.
+    // w_l8 (w residual, e4m3), all pre-scaled so that the three passes fp16 x_hi*w_hi, e4m3 l8*wh8, e4m3 x_h8*w_l8 carry the
+    // same power-of-two factor and share one accumulator (split_fmt.cuh); the epilogue multiplies by p.corr_scale.
     constexpr int STAGES = num_stages(BN, PASSES);
     constexpr int STAGE_BYTES = stage_bytes(BN, PASSES);
     constexpr int B_TILE_BYTES = BN * BK * 2;
     constexpr int A8_TILE_BYTES = BM * BK, B8_TILE_BYTES = BN * BK;       // e4m3 tiles: 64-byte rows
     constexpr uint32_t IDESC = make_idesc(BN, FP16);
-    constexpr int ACC_COLS = (PASSES == 4 ? 2 : 1) * BN;                   // TMEM columns per accumulator stage
+    constexpr int ACC_COLS = BN;                                           // TMEM columns per accumulator stage
     static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
-    static_assert(PASSES != 4 || (FP16 && BN <= 128), "fp8-correction mode: fp16 main plane, two accumulators per stage (BN <= 128)");
+    static_assert(PASSES != 4 || FP16, "fp8-correction mode uses an fp16 main plane");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -345,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN, PASSES)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -415,15 +427,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                                 tc_mma_f16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
                             }
                         }
-                        if (PASSES == 4) {   // two e4m3 correction passes (K = 32 per MMA: 32 bytes per row) into the second accumulator
+                        if (PASSES == 4) {   // two e4m3 correction passes (K = 32 per MMA: 32 bytes per row), same accumulator
                             const uint64_t a_l8 = make_smem_desc64(sa + A_TILE_BYTES), a_h8 = make_smem_desc64(sa + A_TILE_BYTES + A8_TILE_BYTES);
                             const uint64_t b_h8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
                             const uint64_t b_l8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES);
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 const uint64_t koff = (uint64_t)((j * 32) >> 4);
-                                tc_mma_f8(d_tmem + BN, a_l8 + koff, b_h8 + koff, IDESC, (uint32_t)((kb > kb0) | (j != 0)));
-                                tc_mma_f8(d_tmem + BN, a_h8 + koff, b_l8 + koff, IDESC, 1u);
+                                tc_mma_f8(d_tmem, a_l8 + koff, b_h8 + koff, IDESC, 1u);
+                                tc_mma_f8(d_tmem, a_h8 + koff, b_l8 + koff, IDESC, 1u);
                             }
                         }
                         tc_commit(&empty_bar[stage]);   // frees the smem stage once the MMAs above have read it
@@ -470,12 +482,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
 #pragma unroll
                             for (int q = 0; q < 32; ++q) racc[c0 + q] += __uint_as_float(v[q]);
                         }
-                        if (PASSES == 4) {   // + corr_scale * (fp8 correction accumulator)
-                            tc_ld_32x32b_x32(taddr + BN + c0, v);
-                            tc_wait_ld();
-#pragma unroll
-                            for (int q = 0; q < 32; ++q) racc[c0 + q] = fmaf(p.corr_scale, __uint_as_float(v[q]), racc[c0 + q]);
-                        }
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -511,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN, PASSES)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)) : "memory");
     }
 }
 
@@ -533,11 +539,14 @@ __host__ __device__ constexpr int num_stages2(int BN, int PASSES) {
 template <int BN, int PASSES, bool FP16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
-                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                const __grid_constant__ CUtensorMap map_x_h8, const __grid_constant__ CUtensorMap map_w_l8, const TcParams p) {
     constexpr int STAGES = num_stages2(BN, PASSES);
     constexpr int STAGE_BYTES = stage_bytes2(BN, PASSES);
     constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;
+    constexpr int A8_TILE_BYTES = BM * BK, B8_TILE_BYTES = (BN / 2) * BK;   // e4m3 tiles (mode 4): 64-byte rows
     constexpr uint32_t IDESC = make_idesc(BN, FP16, 256);
+    static_assert(PASSES != 4 || FP16, "fp8-correction mode uses an fp16 main plane");
     constexpr int COLS = BN / 2;                       // accumulator columns drained by one epilogue warp
     static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
 
@@ -556,7 +565,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
 
     if (warp == 8 && lane == 0) {
         prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w_hi);
-        if (PASSES == 3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
+        if (PASSES >= 3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
+        if (PASSES == 4) { prefetch_tmap(&map_x_h8); prefetch_tmap(&map_w_l8); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -586,10 +596,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                             uint8_t* st = smem + stage * STAGE_BYTES;
                             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
                             tma_load_4d_2sm(&map_x_hi, st, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
-                            tma_load_2d_2sm(&map_w_hi, st + (PASSES == 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
+                            tma_load_2d_2sm(&map_w_hi, st + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
                             if (PASSES == 3) {
                                 tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
                                 tma_load_2d_2sm(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
+                            }
+                            if (PASSES == 4) {
+                                tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                tma_load_4d_2sm(&map_x_h8, st + A_TILE_BYTES + A8_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                tma_load_2d_2sm(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
+                                tma_load_2d_2sm(&map_w_l8, st + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES, &full_bar[stage], kcol, n0);
                             }
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
@@ -615,7 +631,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                         const uint64_t a_hi = make_smem_desc(sa);
                         const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
-                        const uint64_t b_hi = make_smem_desc(sa + (PASSES == 3 ? 2 : 1) * A_TILE_BYTES);
+                        const uint64_t b_hi = make_smem_desc(sa + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES);
                         const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
                         for (int j = 0; j < BK / UMMA_K; ++j) {
@@ -624,6 +640,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                             if (PASSES == 3) {
                                 tc_mma_f16_2cta(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
                                 tc_mma_f16_2cta(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+                            }
+                        }
+                        if (PASSES == 4) {
+                            const uint64_t a_l8 = make_smem_desc64(sa + A_TILE_BYTES), a_h8 = make_smem_desc64(sa + A_TILE_BYTES + A8_TILE_BYTES);
+                            const uint64_t b_h8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                            const uint64_t b_l8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t koff = (uint64_t)((j * 32) >> 4);
+                                tc_mma_f8_2cta(d_tmem, a_l8 + koff, b_h8 + koff, IDESC, 1u);
+                                tc_mma_f8_2cta(d_tmem, a_h8 + koff, b_l8 + koff, IDESC, 1u);
                             }
                         }
                         tc_commit_2cta(&empty_bar[stage]);   // frees this smem stage in both CTAs
@@ -792,7 +819,8 @@ int launch_inst2(const TcConvPlan* pl, cudaStream_t s) {
         H3D_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, PASSES, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    conv_tc2_kernel<BN, PASSES, FP16><<<pl->grid, kThreads2, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
+    conv_tc2_kernel<BN, PASSES, FP16><<<pl->grid, kThreads2, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->map_x_h8,
+                                                                        pl->map_w_l8, pl->p);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }
@@ -821,11 +849,10 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     // shared-memory traffic either way and the single-CTA kernel is as fast or faster).  H3D_TC_2CTA=0/1 forces one kernel.
     bool two = d.Cout_pad % 256 == 0;
     if (const char* e = getenv("H3D_TC_2CTA")) two = atoi(e) != 0;
-    if (d.passes == 4) two = false;   // two accumulators per stage: BN <= 128, single-CTA kernel
     if (two) BN = d.Cout_pad % 256 == 0 ? 256 : (d.Cout_pad % 128 == 0 ? 128 : 64);   // CTA pair: UMMA 256 x BN
     if (const char* e = getenv("H3D_TC_BN")) {
         const int v = atoi(e);
-        if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0 && !(d.passes == 4 && v > 128)) BN = v;
+        if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
     }
     pl->BN = BN;
     pl->two_cta = two;
@@ -887,6 +914,9 @@ int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
         return fp16 ? launch_inst2<BN_, P_, true>(pl, s) : launch_inst2<BN_, P_, false>(pl, s);
         switch (key) {
             CASE2(64, 1) CASE2(64, 3) CASE2(128, 1) CASE2(128, 3) CASE2(256, 1) CASE2(256, 3)
+            case 64 * 10 + 4: return launch_inst2<64, 4, true>(pl, s);
+            case 128 * 10 + 4: return launch_inst2<128, 4, true>(pl, s);
+            case 256 * 10 + 4: return launch_inst2<256, 4, true>(pl, s);
         }
 #undef CASE2
     }
@@ -897,6 +927,7 @@ int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
         CASE(64, 1) CASE(64, 3) CASE(128, 1) CASE(128, 3) CASE(256, 1) CASE(256, 3)
         case 64 * 10 + 4: return launch_inst<64, 4, true>(pl, s);      // fp16 + e4m3 corrections
         case 128 * 10 + 4: return launch_inst<128, 4, true>(pl, s);
+        case 256 * 10 + 4: return launch_inst<256, 4, true>(pl, s);
     }
 #undef CASE
     set_error("tc_conv: no kernel instance for BN=%d passes=%d", pl->BN, pl->d.passes);

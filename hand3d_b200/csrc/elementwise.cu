@@ -266,7 +266,7 @@ __global__ void f8c_to_f32_kernel(const uint16_t* __restrict__ h16, const uint8_
     const int64_t total = rows * C;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t j = (i / C) * Cpad + (i % C);
-        y[i] = __half2float(__ushort_as_half(h16[j])) + e4m3_to_f32(l8[j]) * (1.0f / kF8XLoScale);
+        y[i] = __half2float(__ushort_as_half(h16[j])) * (1.0f / kF8XMainScale) + e4m3_to_f32(l8[j]) * (1.0f / kF8XLoScale);
     }
 }
 
