@@ -545,7 +545,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
 // TMA loads; empty[s] / tmem_full[a] are signalled in both CTAs by multicast commits; tmem_empty[a] lives in the leader
 // and collects one arrive per epilogue warp of both CTAs.
 constexpr int kThreads2 = 32 * 10;
-__host__ __device__ constexpr int stage_bytes2(int BN, int PASSES) { return (PASSES == 3 ? 2 : 1) * (A_TILE_BYTES + (BN / 2) * BK * 2); }
+__host__ __device__ constexpr int stage_bytes2(int BN, int PASSES) { return (PASSES >= 3 ? 2 : 1) * (A_TILE_BYTES + (BN / 2) * BK * 2); }
 __host__ __device__ constexpr int num_stages2(int BN, int PASSES) {
     return kSmemBudget / stage_bytes2(BN, PASSES) > 8 ? 8 : kSmemBudget / stage_bytes2(BN, PASSES);
 }
