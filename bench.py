@@ -27,13 +27,13 @@ GFLOP_PER_IMAGE = 142.258408192          # conv + FC FLOPs of the full pipeline 
 METRIC = "images/sec full pipeline 320x320"
 
 
-def measured_traffic():
+def measured_traffic(precision="bf16x3"):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/*_summary.json), or None."""
     best = None
     pdir = os.path.join(ROOT, "profiles")
     if os.path.isdir(pdir):
         for fn in sorted(os.listdir(pdir)):
-            if fn.endswith("_summary.json"):
+            if fn.endswith("_summary.json") and (("f8c" in fn) == (precision == "fp16_f8c")):
                 try:
                     d = json.load(open(os.path.join(pdir, fn)))
                     if "tc_conv" in d:
@@ -303,7 +303,7 @@ def run_ours(args):
     if d["ms"] > 0:
         achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
         peak = peaks["tflops_sustained"] if dominant == "tc_conv" else 75.0
-        tr = measured_traffic() if dominant == "tc_conv" else None
+        tr = measured_traffic(args.precision) if (dominant == "tc_conv" and args.precision in ("bf16x3", "fp16_f8c")) else None
         roof = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all layers)" if dominant == "tc_conv" else "conv_direct_kernel (fp32 FFMA)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": tr[1]["dram_bytes_per_launch"] if tr else None,

@@ -56,7 +56,6 @@ struct TcParams {
     int pool;       // fuse NetworkOps.max_pool (2x2 / 2) into the epilogue: outputs are [B, H/2, W/2, C]
     int chunk_kb;   // K blocks accumulated inside the tensor core before the epilogue folds the partial sum into fp32 registers
     int leaky;
-    int order_kinds;   // experiment (H3D_F8C_ORDER=1): wait for completion between MMAs of different kinds on one accumulator
     int* err_flag;
 };
 
@@ -351,7 +350,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    uint64_t* order_bar = reinterpret_cast<uint64_t*>(tmem_slot + 2);   // experiment: serialise MMAs of different kinds
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = p.k * p.k * p.cin_chunks;
@@ -362,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
         if (PASSES == 4) { prefetch_tmap(&map_x_h8); prefetch_tmap(&map_w_l8); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kNumEpilogueWarps); }
-        mbar_init(order_bar, 1);
+
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -412,7 +410,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc_it = 0;
-            uint32_t order_phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 for (int kb0 = 0; kb0 < kblocks; kb0 += p.chunk_kb, ++acc_it) {
                     const int acc = acc_it & 1;
@@ -437,10 +434,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                                 tc_mma_f16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
                             }
                         }
-                        if (PASSES == 4 && p.order_kinds) {   // experiment: f16 MMAs complete before the e4m3 MMAs start
-                            tc_commit(order_bar); mbar_wait(order_bar, order_phase, p.err_flag, 5); order_phase ^= 1; tc_fence_after();
-                        }
-                        if (PASSES == 4 && p.order_kinds != 2) {   // two e4m3 correction passes (K = 32 per MMA: 32 bytes per row), same accumulator
+                        if (PASSES == 4) {   // two e4m3 correction passes (K = 32 per MMA: 32 bytes per row), same accumulator
                             const uint64_t a_l8 = make_smem_desc64(sa + A_TILE_BYTES), a_h8 = make_smem_desc64(sa + A_TILE_BYTES + A8_TILE_BYTES);
                             const uint64_t b_h8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
                             const uint64_t b_l8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES);
@@ -450,7 +444,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                                 tc_mma_f8(d_tmem, a_l8 + koff, b_h8 + koff, IDESC, 1u);
                                 tc_mma_f8(d_tmem, a_h8 + koff, b_l8 + koff, IDESC, 1u);
                             }
-                            if (p.order_kinds) { tc_commit(order_bar); mbar_wait(order_bar, order_phase, p.err_flag, 6); order_phase ^= 1; tc_fence_after(); }
                         }
                         tc_commit(&empty_bar[stage]);   // frees the smem stage once the MMAs above have read it
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -886,7 +879,6 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     p.num_tiles = p.tiles_w * p.tiles_h * tiles_b * p.n_tiles;
     if (two) p.num_tiles = ceil_div(p.tiles_w * p.tiles_h * tiles_b, 2) * p.n_tiles;   // work items = pixel-tile PAIRS x N tiles
     p.leaky = d.leaky;
-    p.order_kinds = getenv("H3D_F8C_ORDER") ? atoi(getenv("H3D_F8C_ORDER")) : 0;
     p.n_valid = d.Cout;
     p.pool = d.pool;
     p.err_flag = nullptr;
