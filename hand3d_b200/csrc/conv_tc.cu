@@ -528,185 +528,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     }
 }
 
-// ------------------------------------------------------------------------------------------ halo-reuse kernel (3x3)
-// EXPERIMENTAL (H3D_TC_HALO=1): the A operand is loaded ONCE per 64-channel chunk as a haloed pixel patch and reused by all
-// k*k taps instead of being re-fetched per tap (9x less A traffic through L2 / TMA / shared-memory writes).
-//   * pixel tile 8 (w) x 16 (h); the patch {64 ch, 16 px pitch, 16 + k - 1 rows} lands in shared memory as 128-byte rows with a
-//     16-pixel pitch, so image row hy starts 2048 B after row hy-1 and every 8-pixel run is one 1024-byte swizzle group;
-//   * the A operand of tap (kh, kw) is the SAME buffer viewed through a shifted UMMA descriptor: start address
-//     base + (kh*16 + kw)*128 B, stride between 8-row groups SBO = 2048 B, and matrix base offset (descriptor bits 49-51)
-//     = (start >> 7) & 7 = kw so that the 128-byte swizzle phase matches what TMA wrote;
-//   * weights stream per tap through their own ring; K order is chunk-major (chunk, tap), so one accumulation chunk
-//     (fp32 register fold in the epilogue) = one channel chunk.
-constexpr int HALO_TW = 8, HALO_TH = 16, HALO_PITCH = 16;
-__host__ __device__ constexpr int halo_rows(int KS) { return HALO_TH + KS - 1; }
-__host__ __device__ constexpr int halo_plane_bytes(int KS) { return halo_rows(KS) * HALO_PITCH * 128; }
-__host__ __device__ constexpr int halo_b_stages(int BN, int PASSES, int KS) {
-    return (kSmemBudget - 2 * (PASSES == 3 ? 2 : 1) * halo_plane_bytes(KS)) / ((PASSES == 3 ? 2 : 1) * BN * BK * 2);
-}
-__device__ __forceinline__ uint64_t make_smem_desc_halo(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((HALO_PITCH * 128) >> 4) << 32) | (1ull << 46) |
-           ((uint64_t)((saddr >> 7) & 7u) << 49) | (2ull << 61);
-}
-
-template <int BN, int PASSES, bool FP16, int KS>
-__global__ void __launch_bounds__(kThreads, 1)
-conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
-                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
-    static_assert(PASSES == 1 || PASSES == 3, "halo kernel: 16-bit planes only");
-    constexpr int NPL = PASSES == 3 ? 2 : 1;
-    constexpr int A_PLANE = halo_plane_bytes(KS), A_BUF = NPL * A_PLANE;
-    constexpr int B_TILE_BYTES = BN * BK * 2, B_STAGE = NPL * B_TILE_BYTES;
-    constexpr int SB = halo_b_stages(BN, PASSES, KS) > 6 ? 6 : halo_b_stages(BN, PASSES, KS);
-    constexpr uint32_t IDESC = make_idesc(BN, FP16);
-    static_assert(SB >= 2, "weight ring needs two stages");
-
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_b = smem + 2 * A_BUF;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + SB * B_STAGE);
-    uint64_t* a_empty = a_full + 2;
-    uint64_t* b_full = a_empty + 2;
-    uint64_t* b_empty = b_full + SB;
-    uint64_t* tfull_bar = b_empty + SB;
-    uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int TAPS = KS * KS;
-
-    if (warp == 4 && lane == 0) {
-        prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w_hi);
-        if (PASSES == 3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kNumEpilogueWarps); }
-        for (int i = 0; i < SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 4) {
-        if (lane == 0) {
-            int ab = 0; uint32_t aph = 0; int sb = 0; uint32_t bph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * HALO_TW - p.pad, h0 = th * HALO_TH - p.pad, n0 = nt * BN;
-                for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                    mbar_wait(&a_empty[ab], aph ^ 1, p.err_flag, 1);
-                    uint8_t* sa = smem + ab * A_BUF;
-                    mbar_expect_tx(&a_full[ab], A_BUF);
-                    tma_load_4d(&map_x_hi, sa, &a_full[ab], cc * BK, w0, h0, tb);
-                    if (PASSES == 3) tma_load_4d(&map_x_lo, sa + A_PLANE, &a_full[ab], cc * BK, w0, h0, tb);
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        mbar_wait(&b_empty[sb], bph ^ 1, p.err_flag, 7);
-                        uint8_t* st = smem_b + sb * B_STAGE;
-                        mbar_expect_tx(&b_full[sb], B_STAGE);
-                        const int kcol = (tap * p.cin_chunks + cc) * BK;
-                        tma_load_2d(&map_w_hi, st, &b_full[sb], kcol, n0);
-                        if (PASSES == 3) tma_load_2d(&map_w_lo, st + B_TILE_BYTES, &b_full[sb], kcol, n0);
-                        if (++sb == SB) { sb = 0; bph ^= 1; }
-                    }
-                    if (++ab == 2) { ab = 0; aph ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 5) {
-        if (lane == 0) {
-            int ab = 0; uint32_t aph = 0; int sb = 0; uint32_t bph = 0;
-            int acc_it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                for (int cc = 0; cc < p.cin_chunks; ++cc, ++acc_it) {
-                    const int acc = acc_it & 1;
-                    mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
-                    mbar_wait(&a_full[ab], aph, p.err_flag, 3);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                    const uint32_t sa = smem_u32(smem + ab * A_BUF);
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        mbar_wait(&b_full[sb], bph, p.err_flag, 8);
-                        tc_fence_after();
-                        const int kh = tap / KS, kw = tap - kh * KS;
-                        const uint32_t a_off = (uint32_t)((kh * HALO_PITCH + kw) * 128);
-                        const uint32_t sbb = smem_u32(smem_b + sb * B_STAGE);
-                        const uint64_t b_hi = make_smem_desc(sbb), b_lo = make_smem_desc(sbb + B_TILE_BYTES);
-#pragma unroll
-                        for (int j = 0; j < BK / UMMA_K; ++j) {
-                            const uint64_t a_hi = make_smem_desc_halo(sa + a_off + j * 32);
-                            const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
-                            tc_mma_f16(d_tmem, a_hi, b_hi + koff, IDESC, (uint32_t)((tap != 0) | (j != 0)));
-                            if (PASSES == 3) {
-                                const uint64_t a_lo = make_smem_desc_halo(sa + A_PLANE + a_off + j * 32);
-                                tc_mma_f16(d_tmem, a_hi, b_lo + koff, IDESC, 1u);
-                                tc_mma_f16(d_tmem, a_lo, b_hi + koff, IDESC, 1u);
-                            }
-                        }
-                        tc_commit(&b_empty[sb]);
-                        if (++sb == SB) { sb = 0; bph ^= 1; }
-                    }
-                    tc_commit(&a_empty[ab]);
-                    tc_commit(&tfull_bar[acc]);
-                    if (++ab == 2) { ab = 0; aph ^= 1; }
-                }
-            }
-        }
-    } else {
-        const int row = threadIdx.x;
-        const int w_l = row % HALO_TW, h_l = row / HALO_TW;
-        int acc_it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-            const int w = tw * HALO_TW + w_l, h = th * HALO_TH + h_l, b = tb, n0 = nt * BN;
-            bool valid = (w < p.W) && (h < p.H) && (b < p.B);
-            int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
-            if (p.pool) {
-                valid = valid && ((w & 1) == 0) && ((h & 1) == 0);
-                pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-            }
-            static_assert(BN <= 128, "halo kernel folds partial sums in registers");
-            float racc[BN];
-            for (int cc = 0; cc < p.cin_chunks; ++cc, ++acc_it) {
-                const int acc = acc_it & 1;
-                mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, p.err_flag, 4);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld_32x32b_x32(taddr + c0, v);
-                    tc_wait_ld();
-                    if (cc == 0) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) racc[c0 + q] = __uint_as_float(v[q]);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) racc[c0 + q] += __uint_as_float(v[q]);
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            }
-#pragma unroll
-            for (int c0 = 0; c0 < BN; c0 += 32) epilogue_store32<PASSES, FP16>(p, &racc[c0], pix, n0 + c0, valid);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)) : "memory");
-    }
-}
-
 // ------------------------------------------------------------------------------------------ CTA-pair kernel
 // Same algorithm on a cluster of two CTAs (two SMs of one TPC) with tcgen05 cta_group::2: one UMMA covers M = 256 pixels
 // (CTA r owns pixel tile 2*pair + r and TMEM rows of it) x N = BN channels; each CTA stages its own A tile and HALF of the
@@ -964,7 +785,7 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s);
 
 struct TcConvPlan {
     bool two_cta = false;
-    bool halo = false;
+
     TcConvDesc d;
     CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo, map_x_h8, map_w_l8;
     TcParams p;
@@ -998,21 +819,6 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s) {
 }  // namespace
 
 namespace {
-template <int BN, int PASSES, bool FP16>
-int launch_halo(const TcConvPlan* pl, cudaStream_t s) {
-    constexpr int KS = 3;
-    constexpr int NPL = PASSES == 3 ? 2 : 1;
-    constexpr int SB = halo_b_stages(BN, PASSES, KS) > 6 ? 6 : halo_b_stages(BN, PASSES, KS);
-    constexpr int smem = 2 * NPL * halo_plane_bytes(KS) + SB * NPL * BN * BK * 2 + 1024 + 256;
-    static bool attr = false;
-    if (!attr) {
-        H3D_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<BN, PASSES, FP16, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
-    conv_tc_halo_kernel<BN, PASSES, FP16, KS><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
-    H3D_CHECK_LAUNCH();
-    return H3D_OK;
-}
 template <int BN, int PASSES, bool FP16>
 int launch_inst2(const TcConvPlan* pl, cudaStream_t s) {
     constexpr int smem = num_stages2(BN, PASSES) * stage_bytes2(BN, PASSES) + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -1056,16 +862,12 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
         const int v = atoi(e);
         if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
     }
-    bool halo = false;
-    if (const char* e = getenv("H3D_TC_HALO")) halo = atoi(e) != 0 && d.k == 3 && d.passes != 4;
-    if (halo) { two = false; if (BN > 128) BN = 128; }
     pl->BN = BN;
     pl->two_cta = two;
-    pl->halo = halo;
+
     int TW, TH, TB;
     if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool needs even H and W"); delete pl; return nullptr; }
     choose_tile(d.B, d.H, d.W, &TW, &TH, &TB, d.pool != 0);
-    if (halo) { TW = HALO_TW; TH = HALO_TH; TB = 1; }
     TcParams& p = pl->p;
     p.bias = d.bias;
     p.y_hi = d.y.hi; p.y_lo = d.y.lo; p.y_l8 = d.y.l8; p.y_h8 = d.y.h8; p.Cy_total = d.Cy_total; p.cy_off = d.cy_off;
@@ -1090,16 +892,6 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     pl->grid = two ? 2 * std::min(p.num_tiles, tc_num_sms() / 2) : std::min(p.num_tiles, tc_num_sms());
     const int w_box_rows = two ? BN / 2 : BN;
     const int Ktot = d.k * d.k * d.Cin_pad;
-    if (halo) {   // one haloed patch {64 ch, 16 px, 16 + k - 1 rows} per channel chunk instead of one box per tap
-        const bool okh = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, HALO_PITCH, halo_rows(d.k), 1) &&
-                         encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, BN) &&
-                         (d.passes != 3 || (encode_act_map(&pl->map_x_lo, d.x.lo, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, HALO_PITCH, halo_rows(d.k), 1) &&
-                                            encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, BN)));
-        if (!okh) { delete pl; return nullptr; }
-        if (d.passes == 1) { pl->map_x_lo = pl->map_x_hi; pl->map_w_lo = pl->map_w_hi; }
-        pl->map_x_h8 = pl->map_x_hi; pl->map_w_l8 = pl->map_w_hi;
-        return pl;
-    }
     bool ok = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB) &&
               encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, w_box_rows);
     if (ok && d.passes == 3)
@@ -1125,14 +917,6 @@ int64_t tc_conv_flops(const TcConvPlan* p) {
 int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
     const bool fp16 = pl->d.half == Half16::FP16;
     const int key = pl->BN * 10 + pl->d.passes;
-    if (pl->halo) {
-        switch (key) {
-            case 64 * 10 + 1: return fp16 ? launch_halo<64, 1, true>(pl, s) : launch_halo<64, 1, false>(pl, s);
-            case 64 * 10 + 3: return fp16 ? launch_halo<64, 3, true>(pl, s) : launch_halo<64, 3, false>(pl, s);
-            case 128 * 10 + 1: return fp16 ? launch_halo<128, 1, true>(pl, s) : launch_halo<128, 1, false>(pl, s);
-            case 128 * 10 + 3: return fp16 ? launch_halo<128, 3, true>(pl, s) : launch_halo<128, 3, false>(pl, s);
-        }
-    }
     if (pl->two_cta) {
 #define CASE2(BN_, P_)                                                                 \
     case BN_ * 10 + P_:                                                                \
