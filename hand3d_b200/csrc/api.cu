@@ -115,9 +115,18 @@ struct StagePlan {
     std::vector<int> kinds;             // StepKind per step (profiling)
     std::vector<int64_t> step_flops;    // algorithmic FLOPs per step
     std::vector<TcConvPlan*> tc;
+    std::vector<int> lane;              // per step: 0 = caller's stream, 1 = the context's side stream (independent branch)
+    std::vector<char> join_before;      // per step: wait for the side stream before this step
+    int cur_lane = 0;                   // lane given to steps as they are appended (see seal())
     int B = 0, H = 0, W = 0, variant = -1;
     int64_t flops = 0;
     ~StagePlan() { for (auto* p : tc) tc_conv_plan_destroy(p); }
+    // label every step appended since the last call with the current lane
+    void seal(bool join = false) {
+        const size_t first = lane.size();
+        while (lane.size() < steps.size()) { lane.push_back(cur_lane); join_before.push_back(0); }
+        if (join && first < steps.size()) join_before[first] = 1;
+    }
 };
 
 }  // namespace h3d
@@ -144,6 +153,10 @@ struct h3d_ctx {
         int64_t seg_off, pose_off, lift_off, total;
     } lay;
     void drop_plans() { seg.reset(); pose.reset(); lift.reset(); }
+    // independent branches (PosePrior || ViewpointNet, x8 up-sampling || lifting) run on two private streams that fork from
+    // and join back into the caller's stream with events (capturable into a CUDA graph)
+    cudaStream_t side = nullptr, side2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     // optional per-kernel-class timing (CUDA events on the launch stream around every plan step)
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; int kind; int64_t flops; };
@@ -285,8 +298,9 @@ static void layout(h3d_ctx::Layout& L, char* base, int B, int H, int W) {
     a.off += 2 * align_up((int64_t)B * Hc * Wc * 64 * 4, 1024) + 2 * align_up((int64_t)B * (Hc / 8) * (Wc / 8) * 192 * 4, 1024) +
              align_up((int64_t)B * (Hc / 8) * (Wc / 8) * 512 * 4, 1024) + 8192;
     a.off = align_up(a.off, 1024); L.lift_off = a.off;
-    a.off += 2 * align_up((int64_t)B * 32 * 32 * 64 * 4, 1024) + 4 * align_up((int64_t)B * 4100 * 4, 1024) +
-             align_up(fc_scratch_floats(B, 4098, 512) * 4, 1024) + align_up(kConvSplitKScratchFloats * 4, 1024) + 16384;
+    // lifting: input planes + two ping-pong slots per branch (PosePrior, ViewpointNet), FC buffers and scratch per branch
+    a.off += 5 * align_up((int64_t)B * 32 * 32 * 64 * 4, 1024) + 2 * 5 * align_up((int64_t)B * 4100 * 4, 1024) +
+             2 * align_up(fc_scratch_floats(B, 4098, 512) * 4, 1024) + 2 * align_up(kConvSplitKScratchFloats * 4, 1024) + 65536;
     L.total = align_up(a.off, 1024);
 }
 
@@ -384,7 +398,7 @@ static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const L
     pl->tc.push_back(tp);
     pl->steps.push_back([tp](const Ext&, cudaStream_t s) { return tc_conv_launch(tp, s); });
     pl->launches.push_back(1);
-    const int64_t fl = 2ll * B * H * W * l.k * l.k * l.cin * l.cout;
+    const int64_t fl = 2ll * B * H * W * l.k * l.k * l.cin * l.cout / (pool == 2 ? 4 : 1);
     pl->flops += fl;
     tag(pl, KIND_TC, fl);
     return H3D_OK;
@@ -571,69 +585,127 @@ static int add_fc(h3d_ctx* ctx, StagePlan* pl, const std::string& name, const fl
     return H3D_OK;
 }
 
+// PosePrior (+ ViewpointNet for the 'proposed' variant): two 6-layer stride-1 / stride-2 conv pyramids on the 32x32 score map
+// and their FC stacks.  With a 3-pass tensor-core precision the pyramids run on the tcgen05 kernel (stride 2 = odd pixels of
+// the stride-1 result, Cin / Cout padded to 64 with zero channels); otherwise on the fp32 CUDA-core kernel.  The two networks
+// are independent until the final rotation, so ViewpointNet is put on the context's side stream.
 static int build_lifting(h3d_ctx* ctx, int B, int variant) {
     auto pl = std::make_unique<StagePlan>();
     pl->B = B; pl->variant = variant;
     Arena a; a.base = ctx->ws + ctx->lay.lift_off;
-    float* bufA = a.alloc<float>((int64_t)B * 32 * 32 * 64);
-    float* bufB = a.alloc<float>((int64_t)B * 32 * 32 * 64);
-    float* xcat = a.alloc<float>((int64_t)B * 4100);
-    float* t1 = a.alloc<float>((int64_t)B * 512);
-    float* t2 = a.alloc<float>((int64_t)B * 512);
-    float* t3 = a.alloc<float>((int64_t)B * 64);
+    const int passes = passes_of(ctx->precision);
+    const Half16 half = half_of(ctx->precision);
+    const bool tc_lift = is_tc(ctx->precision) && passes == 3 && !getenv("H3D_LIFT_DIRECT");
+    const int64_t slot_bytes = align_up((int64_t)B * 32 * 32 * 64 * 4, 1024);
+    char* slot_in = a.alloc<char>(slot_bytes);
+    struct Branch { char* slot[2]; float *xcat, *t1, *t2, *t3, *fcs, *cvs; } br[2];
+    for (auto& b : br) {
+        b.slot[0] = a.alloc<char>(slot_bytes); b.slot[1] = a.alloc<char>(slot_bytes);
+        b.xcat = a.alloc<float>((int64_t)B * 4100);
+        b.t1 = a.alloc<float>((int64_t)B * 512); b.t2 = a.alloc<float>((int64_t)B * 512); b.t3 = a.alloc<float>((int64_t)B * 64);
+        b.fcs = a.alloc<float>(fc_scratch_floats(B, 4098, 512));   // upper bound over all FC layers of the stage
+        b.cvs = a.alloc<float>(kConvSplitKScratchFloats);
+    }
     float* can = a.alloc<float>((int64_t)B * 63);
     float* uxyz = a.alloc<float>((int64_t)B * 4);
-    float* fcs = a.alloc<float>(fc_scratch_floats(B, 4098, 512));   // upper bound over all FC layers of the stage
-    float* cvs = a.alloc<float>(kConvSplitKScratchFloats);
+    H3D_REQUIRE(ctx->lay.lift_off + a.off <= ctx->lay.total, "lifting workspace region too small (internal error)");
     int rc;
-    auto pyramid = [&](const std::string& scope, const LayerSpec* L) -> int {
+    Act xin;   // tensor-core path: the 21-channel score map as split planes with 64 channels (43 zero)
+    if (tc_lift) {
+        xin = slot_view(slot_in, (int64_t)B * 32 * 32 * 64, 64, true, passes);
+        const Split xs = xin.s;
+        pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_f32_to_split(e.in, xs, (int64_t)B * 32 * 32, 21, 64, half, s); });
+        pl->launches.push_back(1);
+        pl->seal();
+    }
+    // returns the flattened NHWC fp32 feature map [B, 4*4*C] in *feat
+    auto pyramid = [&](const std::string& scope, const LayerSpec* L, const Branch& b, float** feat) -> int {
         int h = 32, w = 32;
-        float* bufs[2] = {bufA, bufB};
-        const float* in = nullptr; int cin_total = 21;
+        if (!tc_lift) {
+            float* bufs[2] = {(float*)b.slot[0], (float*)b.slot[1]};
+            const float* in = nullptr; int cin_total = 21;
+            for (int i = 0; i < 6; ++i) {
+                float* out = bufs[i & 1];
+                int rc2 = add_direct(ctx, pl.get(), scope, L[i], B, h, w, in, cin_total, 0, out, L[i].cout, 0, Split(), 0, 0, b.cvs);
+                if (rc2) return rc2;
+                h = ceil_div(h, L[i].stride); w = ceil_div(w, L[i].stride);
+                in = out; cin_total = L[i].cout;
+            }
+            *feat = bufs[1];
+            return H3D_OK;
+        }
+        Act in = xin;
         for (int i = 0; i < 6; ++i) {
-            float* out = bufs[i & 1];
-            int rc2 = add_direct(ctx, pl.get(), scope, L[i], B, h, w, in, cin_total, 0, out, L[i].cout, 0, Split(), 0, 0, cvs);
+            const LayerSpec& l = L[i];
+            const int Cin_pad = (int)align_up(l.cin, 64), Cout_pad = (int)align_up(l.cout, 64);
+            const int ho = h / l.stride, wo = w / l.stride;
+            const bool last = i == 5;
+            Act out = slot_view(b.slot[i & 1], (int64_t)B * ho * wo * Cout_pad, Cout_pad, true, passes);
+            float* yf = last ? (float*)b.slot[i & 1] : nullptr;
+            int rc2 = add_tc(ctx, pl.get(), scope, l, B, h, w, in.s, in.C, Cin_pad, {}, last ? Split() : out.s, Cout_pad, 0, yf, l.cout, 0,
+                             l.stride == 2 ? 2 : 0);
             if (rc2) return rc2;
-            h = ceil_div(h, L[i].stride); w = ceil_div(w, L[i].stride);
-            in = out; cin_total = L[i].cout;
+            if (last) *feat = yf;
+            h = ho; w = wo; in = out;
         }
         return H3D_OK;
     };
-    // PosePrior (nets/ColorHandPose3DNetwork.py:249-272; bottleneck nets/PosePriorNetwork.py:113-116)
-    if ((rc = pyramid("PosePrior", kPosePrior))) return rc;
-    pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(bufB, e.hand_side, xcat, B, 2048, s); });
-    pl->launches.push_back(1);
-    if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_rel0", xcat, t1, fcs, B, 2050, 512, 1))) return rc;
-    if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_rel1", t1, t2, fcs, B, 512, 512, 1))) return rc;
+    // ---- PosePrior on the caller's stream (nets/ColorHandPose3DNetwork.py:249-272; bottleneck nets/PosePriorNetwork.py:113-116)
     const bool bott = variant == H3D_VARIANT_BOTTLENECK;
     auto xyz = ctx->host_w.find("PosePrior/fc_xyz/weights");
     if (xyz == ctx->host_w.end()) { set_error("weights PosePrior/fc_xyz not loaded"); return H3D_EWEIGHTS; }
     const int xyz_in = (int)xyz->second.shape[0];
-    if (bott) {
-        H3D_REQUIRE(xyz_in == 30, "bottleneck variant needs PosePrior/fc_xyz/weights of shape [30,63]");
-        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_bottleneck", t2, t3, fcs, B, 512, 30, 0))) return rc;
-        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", t3, can, fcs, B, 30, 63, 0))) return rc;
-    } else {
-        H3D_REQUIRE(xyz_in == 512, "PosePrior/fc_xyz/weights must have shape [512,63] for this variant");
-        if ((rc = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", t2, can, fcs, B, 512, 63, 0))) return rc;
-    }
-    if (variant == H3D_VARIANT_PROPOSED) {
-        // ViewpointNet (nets/ColorHandPose3DNetwork.py:274-309) + Rodrigues / flip / rotate (:239-247,311-334)
-        if ((rc = ensure_vp_heads(ctx))) return rc;
-        if ((rc = pyramid("ViewpointNet", kViewpoint))) return rc;
-        pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(bufB, e.hand_side, xcat, B, 4096, s); });
+    auto pose_prior = [&]() -> int {
+        const Branch& b = br[0];
+        float* feat = nullptr;
+        int rc2;
+        if ((rc2 = pyramid("PosePrior", kPosePrior, b, &feat))) return rc2;
+        float* xcat = b.xcat;
+        pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(feat, e.hand_side, xcat, B, 2048, s); });
         pl->launches.push_back(1);
-        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp0", xcat, t1, fcs, B, 4098, 256, 1))) return rc;
-        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp1", t1, t2, fcs, B, 256, 128, 1))) return rc;
+        if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_rel0", b.xcat, b.t1, b.fcs, B, 2050, 512, 1))) return rc2;
+        if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_rel1", b.t1, b.t2, b.fcs, B, 512, 512, 1))) return rc2;
+        if (bott) {
+            H3D_REQUIRE(xyz_in == 30, "bottleneck variant needs PosePrior/fc_xyz/weights of shape [30,63]");
+            if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_bottleneck", b.t2, b.t3, b.fcs, B, 512, 30, 0))) return rc2;
+            if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", b.t3, can, b.fcs, B, 30, 63, 0))) return rc2;
+        } else {
+            H3D_REQUIRE(xyz_in == 512, "PosePrior/fc_xyz/weights must have shape [512,63] for this variant");
+            if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", b.t2, can, b.fcs, B, 512, 63, 0))) return rc2;
+        }
+        return H3D_OK;
+    };
+    if (variant == H3D_VARIANT_PROPOSED) {
+        // ---- ViewpointNet on the side stream (nets/ColorHandPose3DNetwork.py:274-309), enqueued first so that both branches
+        //      are in flight while the host builds the second one
+        if ((rc = ensure_vp_heads(ctx))) return rc;
+        const Branch& b = br[1];
+        float* feat = nullptr;
+        pl->cur_lane = 1;
+        if ((rc = pyramid("ViewpointNet", kViewpoint, b, &feat))) return rc;
+        float* xcat = b.xcat;
+        pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(feat, e.hand_side, xcat, B, 4096, s); });
+        pl->launches.push_back(1);
+        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp0", b.xcat, b.t1, b.fcs, B, 4098, 256, 1))) return rc;
+        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp1", b.t1, b.t2, b.fcs, B, 256, 128, 1))) return rc;
         const float* hw = ctx->vp_head_w; const float* hb = ctx->vp_head_b;
+        float* t2 = b.t2; float* fcs = b.fcs;
         pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_fc(t2, hw, hb, uxyz, fcs, B, 128, 3, 0, 128, s); });
         pl->launches.push_back(2);
         tag(pl.get(), KIND_FC, 2ll * B * 128 * 3);
+        pl->seal();
+        pl->cur_lane = 0;
+    }
+    if ((rc = pose_prior())) return rc;
+    pl->seal();
+    if (variant == H3D_VARIANT_PROPOSED) {
+        // Rodrigues / flip / rotate (:239-247,311-334): needs both branches
         pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
             if (e.out2) H3D_CUDA(cudaMemcpyAsync(e.out2, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
             return launch_rotate_canonical(can, uxyz, e.hand_side, B, e.out3, e.out, s);
         });
         pl->launches.push_back(1);
+        pl->seal(true);
     } else if (variant == H3D_VARIANT_LOCAL) {
         // nets/PosePriorNetwork.py:70-75: the network predicts bone-relative coordinates; assemble xyz by forward kinematics
         pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
@@ -641,6 +713,7 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
             return launch_bone_rel_trafo_inv(can, e.out, B, s);
         });
         pl->launches.push_back(1);
+        pl->seal();
     } else {
         pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
             H3D_CUDA(cudaMemcpyAsync(e.out, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
@@ -648,27 +721,46 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
             return H3D_OK;
         });
         pl->launches.push_back(0);
+        pl->seal();
     }
     ctx->lift = std::move(pl);
     return H3D_OK;
 }
 
 static int run_plan(h3d_ctx* ctx, StagePlan* pl, const Ext& e, cudaStream_t s) {
+    bool forked = false;
+    auto join = [&]() -> int {
+        if (!forked) return H3D_OK;
+        H3D_CUDA(cudaEventRecord(ctx->ev_join, ctx->side));
+        H3D_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+        forked = false;
+        return H3D_OK;
+    };
+    const bool lanes = !getenv("H3D_NO_SIDE_STREAM");
     for (size_t i = 0; i < pl->steps.size(); ++i) {
+        int rc;
+        const int ln = (lanes && i < pl->lane.size()) ? pl->lane[i] : 0;
+        if (i < pl->join_before.size() && pl->join_before[i] && (rc = join())) return rc;
+        if (ln == 1 && !forked) {   // the branch starts from everything enqueued on the caller's stream so far
+            H3D_CUDA(cudaEventRecord(ctx->ev_fork, s));
+            H3D_CUDA(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            forked = true;
+        }
+        cudaStream_t st = ln == 1 ? ctx->side : s;
         h3d_ctx::ProfRec pr;
         const bool prof = ctx->profiling && pl->launches[i] > 0;
         if (prof) {
             H3D_CUDA(cudaEventCreate(&pr.a)); H3D_CUDA(cudaEventCreate(&pr.b));
             pr.kind = i < pl->kinds.size() ? pl->kinds[i] : KIND_OTHER;
             pr.flops = i < pl->step_flops.size() ? pl->step_flops[i] : 0;
-            H3D_CUDA(cudaEventRecord(pr.a, s));
+            H3D_CUDA(cudaEventRecord(pr.a, st));
         }
-        int rc = pl->steps[i](e, s);
-        if (rc) return rc;
-        if (prof) { H3D_CUDA(cudaEventRecord(pr.b, s)); ctx->prof.push_back(pr); }
+        rc = pl->steps[i](e, st);
+        if (rc) { join(); return rc; }
+        if (prof) { H3D_CUDA(cudaEventRecord(pr.b, st)); ctx->prof.push_back(pr); }
         ctx->launches += pl->launches[i];
     }
-    return H3D_OK;
+    return join();
 }
 
 static int check_device() {
@@ -712,6 +804,16 @@ int h3d_create(h3d_ctx** out, int device) {
     h3d_ctx* c = new h3d_ctx();
     c->device = device;
     memset(&c->lay, 0, sizeof(c->lay));
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->side2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("h3d_create: cannot create the side streams (%s)", cudaGetErrorString(cudaGetLastError()));
+        h3d_destroy(c);
+        return H3D_ECUDA;
+    }
     *out = c;
     return H3D_OK;
 }
@@ -723,6 +825,10 @@ int h3d_destroy(h3d_ctx* ctx) {
     for (auto& kv : ctx->packed) free_packed(kv.second);
     if (ctx->vp_head_w) cudaFree(ctx->vp_head_w);
     if (ctx->vp_head_b) cudaFree(ctx->vp_head_b);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->side2) cudaStreamDestroy(ctx->side2);
+    for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_fork2, ctx->ev_join2})
+        if (e) cudaEventDestroy(e);
     delete ctx;
     return H3D_OK;
 }
@@ -892,18 +998,29 @@ int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_sid
     ctx->launches += 1;
     // PoseNet2D (nets/...:89-90)
     if ((rc = h3d_posenet_forward(ctx, crop, B, 256, 256, nullptr, nullptr, nullptr, stream))) return rc;
-    // PosePrior + ViewpointNet on the 32x32 map (nets/...:93)
-    if (with_pose3d)
-        if ((rc = h3d_lifting_forward(ctx, L.s[2], hand_side, B, H3D_VARIANT_PROPOSED, keypoint_coord3d, nullptr, nullptr, stream))) return rc;
-    // x8 up-sampling (nets/...:96-97) and detect_keypoints (utils/general.py:331-344), fused when both are requested
+    // x8 up-sampling (nets/...:96-97) and detect_keypoints (utils/general.py:331-344), fused when both are requested; it only
+    // reads the 32x32 score map, so it runs on a side stream concurrently with the lifting stage
+    const bool overlap = with_pose3d && !getenv("H3D_NO_SIDE_STREAM");
+    cudaStream_t us = s;
+    if (overlap) {
+        H3D_CUDA(cudaEventRecord(ctx->ev_fork2, s));
+        H3D_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork2, 0));
+        us = ctx->side2;
+    }
     if (keypoints_uv) {
         nl = 0;
-        if ((rc = launch_resize_argmax21(L.s[2], kps, B, 32, 32, 256, 256, L.argmax_scratch, keypoints_uv, s, &nl))) return rc;
+        if ((rc = launch_resize_argmax21(L.s[2], kps, B, 32, 32, 256, 256, L.argmax_scratch, keypoints_uv, us, &nl))) return rc;
         ctx->launches += nl;
     } else {
-        if ((rc = launch_resize_bilinear_tf1(L.s[2], kps, B, 32, 32, 21, 256, 256, s))) return rc;
+        if ((rc = launch_resize_bilinear_tf1(L.s[2], kps, B, 32, 32, 21, 256, 256, us))) return rc;
         ctx->launches += 1;
     }
+    if (overlap) H3D_CUDA(cudaEventRecord(ctx->ev_join2, ctx->side2));
+    // PosePrior + ViewpointNet on the 32x32 map (nets/...:93)
+    if (with_pose3d)
+        rc = h3d_lifting_forward(ctx, L.s[2], hand_side, B, H3D_VARIANT_PROPOSED, keypoint_coord3d, nullptr, nullptr, stream);
+    if (overlap) H3D_CUDA(cudaStreamWaitEvent(s, ctx->ev_join2, 0));   // join even when the lifting stage failed
+    if (rc) return rc;
     return H3D_OK;
 }
 
@@ -933,15 +1050,21 @@ int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const floa
 
 int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y, int B, int H, int W,
                   int Cin, int Cout, int ksize, int leaky, int precision, void* stream) {
+    return h3d_conv2d_tc_strided(ctx, x, host_w_hwio, host_bias, y, B, H, W, Cin, Cout, ksize, 1, leaky, precision, stream);
+}
+
+int h3d_conv2d_tc_strided(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y, int B, int H, int W,
+                          int Cin, int Cout, int ksize, int stride, int leaky, int precision, void* stream) {
     H3D_OP_PROLOGUE(ctx);
     H3D_REQUIRE(precision >= H3D_PREC_BF16X3 && precision <= H3D_PREC_FP16_F8C, "h3d_conv2d_tc: precision must be a tensor-core mode");
+    H3D_REQUIRE(stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0), "h3d_conv2d_tc: stride must be 1, or 2 with even H and W");
     const Half16 half = half_of(precision);
     const int passes = passes_of(precision);
     const int Cin_pad = (int)align_up(Cin, 64), Cout_pad = (int)align_up(Cout, 64);
     PackedW pw;
     int rc = pack_conv_weights(host_w_hwio, host_bias, ksize, Cin, Cout, Cin_pad, Cout_pad, {}, half, passes, &pw);
     if (rc) return rc;
-    const int64_t rows = (int64_t)B * H * W;
+    const int64_t rows = (int64_t)B * H * W, rows_out = rows / (stride * stride);
     Split xs, ys;
     TcConvPlan* tp = nullptr;
     auto cleanup = [&]() {
@@ -951,10 +1074,10 @@ int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const 
         free_packed(pw);
     };
     auto fail = [&](int code) { cleanup(); return code; };
-    if (cudaMalloc(&xs.hi, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.hi, rows * Cout_pad * 2) != cudaSuccess ||
-        (passes == 3 && (cudaMalloc(&xs.lo, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.lo, rows * Cout_pad * 2) != cudaSuccess)) ||
+    if (cudaMalloc(&xs.hi, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.hi, rows_out * Cout_pad * 2) != cudaSuccess ||
+        (passes == 3 && (cudaMalloc(&xs.lo, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.lo, rows_out * Cout_pad * 2) != cudaSuccess)) ||
         (passes == 4 && (cudaMalloc(&xs.l8, rows * Cin_pad) != cudaSuccess || cudaMalloc(&xs.h8, rows * Cin_pad) != cudaSuccess ||
-                         cudaMalloc(&ys.l8, rows * Cout_pad) != cudaSuccess || cudaMalloc(&ys.h8, rows * Cout_pad) != cudaSuccess))) {
+                         cudaMalloc(&ys.l8, rows_out * Cout_pad) != cudaSuccess || cudaMalloc(&ys.h8, rows_out * Cout_pad) != cudaSuccess))) {
         set_error("h3d_conv2d_tc: out of device memory");
         return fail(H3D_ECUDA);
     }
@@ -962,11 +1085,11 @@ int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const 
     TcConvDesc d;
     d.x = xs; d.Cin_total = Cin_pad; d.Cin_pad = Cin_pad; d.w = pw.w; d.bias = pw.bias; d.Cout = Cout; d.Cout_pad = Cout_pad;
     d.y = ys; d.Cy_total = Cout_pad; d.cy_off = 0; d.yf = nullptr; d.Cyf_total = 0; d.cyf_off = 0;
-    d.B = B; d.H = H; d.W = W; d.k = ksize; d.leaky = leaky; d.passes = passes; d.half = half; d.corr_scale = pw.corr_scale;
+    d.B = B; d.H = H; d.W = W; d.k = ksize; d.leaky = leaky; d.passes = passes; d.half = half; d.corr_scale = pw.corr_scale; d.pool = stride == 2 ? 2 : 0;
     tp = tc_conv_plan_create(d);
     if (!tp) return fail(H3D_ECUDA);
     if ((rc = tc_conv_launch(tp, s))) return fail(rc);
-    if ((rc = launch_split_to_f32(ys, y, rows, Cout, Cout_pad, half, s))) return fail(rc);
+    if ((rc = launch_split_to_f32(ys, y, rows_out, Cout, Cout_pad, half, s))) return fail(rc);
     ctx->launches += 3;
     cudaError_t e = cudaStreamSynchronize(s);
     cleanup();

@@ -132,7 +132,7 @@ struct TcConvDesc {
     int passes;  // 1, 3, or 4 = fp16 main pass + two fp8 (e4m3) correction passes (needs the l8 / h8 planes)
     float corr_scale = 0.f;   // passes == 4: 2^-(10 + b), un-does the scales of the fp8 operands (b: per-layer weight shift)
     Half16 half;
-    int pool = 0;  // fuse the following 2x2/2 max-pool: outputs are [B, H/2, W/2, C]
+    int pool = 0;  // 1: fuse the following 2x2/2 max-pool; 2: stride-2 'SAME' convolution (even H, W); outputs are [B, H/2, W/2, C]
 };
 TcConvPlan* tc_conv_plan_create(const TcConvDesc& d);   // nullptr on failure (h3d_last_error set)
 void tc_conv_plan_destroy(TcConvPlan* p);

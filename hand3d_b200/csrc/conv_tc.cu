@@ -53,7 +53,8 @@ struct TcParams {
     int B, H, W, k, pad, cin_chunks;
     int TW, TH, TB, tiles_w, tiles_h, n_tiles, num_tiles;
     int n_valid;    // number of real output channels (Cout); channels [n_valid, Cout_pad) are padding and never stored
-    int pool;       // fuse NetworkOps.max_pool (2x2 / 2) into the epilogue: outputs are [B, H/2, W/2, C]
+    int pool;       // 1: fuse NetworkOps.max_pool (2x2 / 2) into the epilogue; 2: stride-2 'SAME' convolution (store the odd pixels
+                    // of the stride-1 result); outputs are [B, H/2, W/2, C] in both modes
     int chunk_kb;   // K blocks accumulated inside the tensor core before the epilogue folds the partial sum into fp32 registers
     int leaky;
     int* err_flag;
@@ -238,7 +239,7 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
 #pragma unroll
         for (int q = 0; q < 32; ++q) f[q] = fmaxf(f[q], kNegSlope * f[q]);
     }
-    if (p.pool) {
+    if (p.pool == 1) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
             f[q] = fmaxf(f[q], __shfl_xor_sync(0xFFFFFFFFu, f[q], 1));
@@ -246,32 +247,29 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
         }
     }
     if (!valid) return;
-    if (n + 32 > p.n_valid) {   // score-map heads (Cout = 2 / 21 padded to 64): masked scalar tail
-        if (n >= p.n_valid) return;
-        const int cnt = p.n_valid - n;
-        if (p.yf) {
+    if (n + 32 > p.n_valid) {   // Cout not a multiple of 32 (score-map heads 2 / 21, lifting 32-channel layers): masked scalar tail
+        const int cnt = p.n_valid - n;   // <= 0: this 32-channel group is padding only
+        if (p.yf && cnt > 0) {
             float* dst = p.yf + pix * p.Cyf_total + p.cyf_off + n;
 #pragma unroll
             for (int q = 0; q < 32; ++q)
                 if (q < cnt) dst[q] = f[q];
         }
-        if (p.y_hi) {
+        if (p.y_hi) {   // the split planes carry Cout_pad channels: padding channels are written as zeros (they are the next layer's K padding)
             const int64_t off = pix * p.Cy_total + p.cy_off + n;
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-                if (q < cnt) {
-                    if (PASSES == 4) {   // fp16 plane pre-scaled by 2^5 + e4m3 planes (split_fmt.cuh)
-                        const F8cPlanes pl = f32_to_f8c(f[q]);
-                        p.y_hi[off + q] = pl.h16; p.y_l8[off + q] = pl.l8; p.y_h8[off + q] = pl.h8;
-                        continue;
-                    }
-                    const uint32_t h2 = pack_hi2<FP16>(f[q], 0.f);
-                    p.y_hi[off + q] = (uint16_t)(h2 & 0xFFFFu);
-                    if (PASSES == 3 && p.y_lo) {
-                        const float2 r = unpack2<FP16>(h2);
-                        p.y_lo[off + q] = (uint16_t)(pack_hi2<FP16>(f[q] - r.x, 0.f) & 0xFFFFu);
-                    }
-
+                const float v = q < cnt ? f[q] : 0.f;
+                if (PASSES == 4) {   // fp16 plane pre-scaled by 2^5 + e4m3 planes (split_fmt.cuh)
+                    const F8cPlanes pl = f32_to_f8c(v);
+                    p.y_hi[off + q] = pl.h16; p.y_l8[off + q] = pl.l8; p.y_h8[off + q] = pl.h8;
+                    continue;
+                }
+                const uint32_t h2 = pack_hi2<FP16>(v, 0.f);
+                p.y_hi[off + q] = (uint16_t)(h2 & 0xFFFFu);
+                if (PASSES == 3 && p.y_lo) {
+                    const float2 r = unpack2<FP16>(h2);
+                    p.y_lo[off + q] = (uint16_t)(pack_hi2<FP16>(v - r.x, 0.f) & 0xFFFFu);
                 }
             }
         }
@@ -463,8 +461,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
             const int w = tw * p.TW + w_l, h = th * p.TH + h_l, b = tb * p.TB + b_l, n0 = nt * BN;
             bool valid = (w < p.W) && (h < p.H) && (b < p.B);
             int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
-            if (p.pool) {   // pooled output pixel; only the even-(w, h) lane of each 2x2 window stores
-                valid = valid && ((w & 1) == 0) && ((h & 1) == 0);
+            if (p.pool) {   // 1: pooled output pixel, the even-(w, h) lane of each 2x2 window stores; 2: stride-2 'SAME' conv on an
+                            // even-sized map = the stride-1 result at the odd pixels (TF pads 0 before / 1 after)
+                const int par = p.pool == 2 ? 1 : 0;
+                valid = valid && ((w & 1) == par) && ((h & 1) == par);
                 pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
             }
             // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the number of
@@ -680,7 +680,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             bool valid = (w < p.W) && (h < p.H) && (b < p.B);
             int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
             if (p.pool) {
-                valid = valid && ((w & 1) == 0) && ((h & 1) == 0);
+                const int par = p.pool == 2 ? 1 : 0;
+                valid = valid && ((w & 1) == par) && ((h & 1) == par);
                 pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
             }
             float racc[COLS];
@@ -842,7 +843,8 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     const bool padded_out = d.Cout % 32 != 0;   // masked scalar tail in the epilogue: no alignment requirement there
     if (d.y.hi && ((d.Cy_total % 8) || (d.cy_off % 8))) { set_error("tc_conv: split output channel offset/stride must be multiples of 8"); return nullptr; }
     if (d.yf && !padded_out && ((d.Cyf_total % 4) || (d.cyf_off % 4))) { set_error("tc_conv: fp32 output channel offset/stride must be multiples of 4"); return nullptr; }
-    if (padded_out && d.pool) { set_error("tc_conv: fused pooling needs Cout %% 32 == 0"); return nullptr; }
+    if (padded_out && d.pool == 1) { set_error("tc_conv: fused pooling needs Cout %% 32 == 0"); return nullptr; }
+    if (d.pool < 0 || d.pool > 2) { set_error("tc_conv: pool mode must be 0 (none), 1 (max-pool) or 2 (stride 2)"); return nullptr; }
     if (d.passes == 3 && (!d.x.lo || !d.w.lo)) { set_error("tc_conv: 3-pass mode needs lo planes"); return nullptr; }
     if (d.passes == 4 && (!d.x.l8 || !d.x.h8 || !d.w.l8 || !d.w.h8 || d.half != Half16::FP16 || d.corr_scale <= 0.f)) {
         set_error("tc_conv: fp8-correction mode needs fp16 + e4m3 l8/h8 planes for activations and weights and a correction scale");
@@ -866,8 +868,8 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     pl->two_cta = two;
 
     int TW, TH, TB;
-    if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool needs even H and W"); delete pl; return nullptr; }
-    choose_tile(d.B, d.H, d.W, &TW, &TH, &TB, d.pool != 0);
+    if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool / stride 2 needs even H and W"); delete pl; return nullptr; }
+    choose_tile(d.B, d.H, d.W, &TW, &TH, &TB, d.pool == 1);
     TcParams& p = pl->p;
     p.bias = d.bias;
     p.y_hi = d.y.hi; p.y_lo = d.y.lo; p.y_l8 = d.y.l8; p.y_h8 = d.y.h8; p.Cy_total = d.Cy_total; p.cy_off = d.cy_off;

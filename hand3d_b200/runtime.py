@@ -204,14 +204,17 @@ class Context:
                                            _stream()), "h3d_conv2d_f32")
         return y
 
-    def conv2d_tc(self, x, w_host, b_host, leaky=False, precision="bf16x3"):
+    def conv2d_tc(self, x, w_host, b_host, leaky=False, precision="bf16x3", stride=1):
         x = _chk_f32(x, "x", 4)
         w = np.ascontiguousarray(w_host, np.float32); b = np.ascontiguousarray(b_host, np.float32)
         B, H, W, Cin = x.shape
         k, _, _, Cout = w.shape
-        y = torch.empty((B, H, W, Cout), dtype=torch.float32, device=x.device)
-        _lib.check(self.lib.h3d_conv2d_tc(self.h, _ptr(x), w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), _ptr(y),
-                                          B, H, W, Cin, Cout, k, int(leaky), PRECISIONS[precision], _stream()), "h3d_conv2d_tc")
+        if stride not in (1, 2) or (stride == 2 and (H % 2 or W % 2)):
+            raise ValueError("conv2d_tc: stride must be 1, or 2 with even H and W")
+        y = torch.empty((B, H // stride, W // stride, Cout), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.h3d_conv2d_tc_strided(self.h, _ptr(x), w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), _ptr(y),
+                                                  B, H, W, Cin, Cout, k, stride, int(leaky), PRECISIONS[precision], _stream()),
+                   "h3d_conv2d_tc_strided")
         return y
 
     def max_pool(self, x):

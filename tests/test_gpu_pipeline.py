@@ -81,21 +81,30 @@ def test_posenet_stage(net, ctx, pose_ref, prec):
         assert err < TOL[prec], "PoseNet %s stage %d: max abs err %.3e" % (prec, i, err)
 
 
+# fp32_ffma: fp32 CUDA-core pyramids; bf16x3 / fp16x3: tcgen05 pyramids (stride 2 = odd pixels of the stride-1 result), branches on two streams
+@pytest.mark.parametrize("prec", ["fp32_ffma", "bf16x3", "fp16x3"])
 @pytest.mark.parametrize("variant", ["proposed", "direct"])
-def test_lifting_stage(ctx, wd, variant):
+def test_lifting_stage(ctx, wd, variant, prec):
     rng = np.random.default_rng(13)
     B = 5
     sm = rng.normal(size=(B, 32, 32, 21)).astype(f32)
     hs = Wt.synthetic_hand_side(B, seed=3)
-    out, can, rot = ctx.lifting(_dev(sm), _dev(hs), variant)
+    ctx.set_precision(prec)
+    try:
+        out, can, rot = ctx.lifting(_dev(sm), _dev(hs), variant)
+        out2, can2, rot2 = ctx.lifting(_dev(sm), _dev(hs), variant)     # second call: same plan, same streams
+    finally:
+        ctx.set_precision("bf16x3")
+    tol = 1e-4 if prec == "fp32_ffma" else 3e-4
     if variant == "proposed":
         r_out, r_can, r_R = O.inference_pose3d(sm, hs, wd)
-        np.testing.assert_allclose(rot.cpu().numpy(), r_R, atol=1e-4)
+        np.testing.assert_allclose(rot.cpu().numpy(), r_R, atol=tol)
     else:
         r_can = O.inference_pose3d_can(sm, hs, wd)
         r_out = r_can
-    np.testing.assert_allclose(can.cpu().numpy(), r_can, atol=1e-4)
-    np.testing.assert_allclose(out.cpu().numpy(), r_out, atol=1e-4)
+    np.testing.assert_allclose(can.cpu().numpy(), r_can, atol=tol)
+    np.testing.assert_allclose(out.cpu().numpy(), r_out, atol=tol)
+    assert torch.equal(out, out2) and torch.equal(can, can2)            # deterministic across calls (no atomics, no stream races)
 
 
 def test_pose_prior_network_variants(wd):

@@ -42,6 +42,41 @@ def test_conv2d_tc_vs_oracle(ctx, case, prec):
     assert err < TOL[prec], "max abs err %.3e (tolerance %.1e)" % (err, TOL[prec])
 
 
+STRIDED = [  # B,H,W,Cin,Cout: the stride-2 layers of the lifting pyramids (nets/ColorHandPose3DNetwork.py:255-258,291-294)
+    (2, 32, 32, 32, 32),      # conv_pose_0_2: Cin / Cout padded 32 -> 64
+    (3, 16, 16, 64, 64),      # conv_pose_1_2 / conv_vp_0_2 geometry
+    (5, 8, 8, 128, 128),      # conv_pose_2_2: (8,8,2) tiles, ragged batch
+    (2, 8, 8, 256, 256),      # conv_vp_2_2: CTA-pair kernel
+    (1, 12, 20, 21, 40),      # odd channel counts, partial tiles
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3", "fp16"])
+@pytest.mark.parametrize("case", STRIDED)
+def test_conv2d_tc_stride2_vs_oracle(ctx, case, prec):
+    """stride 2 'SAME' on an even-sized map (pads 0 before / 1 after) = the odd pixels of the stride-1 result."""
+    B, H, W, Cin, Cout = case
+    rng = np.random.default_rng(13)
+    x = rng.normal(size=(B, H, W, Cin)).astype(f32)
+    w = (rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin)).astype(f32)
+    b = rng.normal(size=Cout).astype(f32)
+    y = ctx.conv2d_tc(torch.from_numpy(x).cuda(), w, b, leaky=True, precision=prec, stride=2).cpu().numpy()
+    ref = T.leaky_relu(T.conv2d_same(x, w, b, 2, np.float64))
+    assert y.shape == ref.shape
+    err = np.abs(y - ref).max()
+    assert err < TOL[prec], "max abs err %.3e (tolerance %.1e)" % (err, TOL[prec])
+
+
+def test_conv2d_tc_padded_planes_chain(ctx):
+    """Cout = 32 feeding a second layer: the padding channels of the split planes must be exact zeros (they are the next K)."""
+    rng = np.random.default_rng(14)
+    x = rng.normal(size=(2, 16, 16, 21)).astype(f32)
+    w1 = (rng.normal(size=(3, 3, 21, 32)) / np.sqrt(9 * 21)).astype(f32); b1 = rng.normal(size=32).astype(f32)
+    y1 = ctx.conv2d_tc(torch.from_numpy(x).cuda(), w1, b1, leaky=True, precision="fp16x3")
+    ref = T.leaky_relu(T.conv2d_same(x, w1, b1, 1, np.float64))
+    assert np.abs(y1.cpu().numpy() - ref).max() < TOL["fp16x3"]
+
+
 def test_conv2d_tc_identity_weights(ctx):
     """Delta kernel = identity: any layout / swizzle / descriptor mistake shows up as permuted channels or pixels."""
     B, H, W, C = 1, 16, 16, 64
