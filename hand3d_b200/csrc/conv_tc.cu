@@ -528,6 +528,181 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------ 64 -> 64 channel 3x3 kernel
+// conv1_2 of both networks (64 -> 64 channels at full resolution, 11 % of the FLOPs) is the one layer shape where the generic
+// kernel is bound by L2 -> shared-memory traffic instead of the tensor pipe: with N = 64 every 128-pixel A tile is used for only
+// 64 output channels, and the tile is fetched again for each of the 9 filter taps together with the tap's weights (432 KB per
+// tile, ~48 B/clk/SM = the measured L2 cap of the chip).  This specialisation removes 72 % of that traffic:
+//   * all weights of the layer (9 taps x [W_hi ; W_lo] = 144 KB) are loaded into shared memory ONCE per persistent CTA;
+//   * the activations are fetched as three column-shifted patches {64 ch, 16, TH + 2 = 10 rows} per tile (one per kw); the
+//     three row taps kh of a patch are the same bytes read through UMMA descriptors whose start address is advanced by
+//     kh x 2048 B (= one 16-pixel patch row = two 1024-byte swizzle atoms, so the swizzle phase is unchanged);
+//   * N-stacking: hi*hi and hi*lo are ONE UMMA with N = 128 (B = [W_hi ; W_lo], TMEM columns 0-63 / 64-127), lo*hi is a
+//     second UMMA with N = 64 into columns 0-63: the A operand is read twice instead of three times (the remaining bound is
+//     shared-memory read bandwidth).  The epilogue adds the two column halves in fp32 registers.
+// Tiles are fixed at 16 x 8 pixels of one image; everything after the accumulator (bias, leaky ReLU, 2x2 max-pool or
+// stride-2 sub-sampling, hi/lo split, masked heads) is the shared epilogue_store32.
+constexpr int C64_TW = 16, C64_TH = 8, C64_PH = C64_TH + 2;
+constexpr int C64_PATCH_BYTES = C64_PH * C64_TW * BK * 2;                 // 20480: one plane of one patch
+constexpr int C64_ROW_BYTES = C64_TW * BK * 2;                            // 2048: one patch row
+__host__ __device__ constexpr int c64_w_tap_bytes(int PASSES) { return (PASSES == 3 ? 128 : 64) * BK * 2; }
+__host__ __device__ constexpr int c64_a_stage_bytes(int PASSES) { return (PASSES == 3 ? 2 : 1) * C64_PATCH_BYTES; }
+__host__ __device__ constexpr int c64_a_stages(int PASSES) { return PASSES == 3 ? 2 : 4; }
+__host__ __device__ constexpr int c64_smem_bytes(int PASSES) {
+    return 9 * c64_w_tap_bytes(PASSES) + c64_a_stages(PASSES) * c64_a_stage_bytes(PASSES) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+template <int PASSES, bool FP16>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+    static_assert(PASSES == 1 || PASSES == 3, "conv_c64_kernel: one 16-bit pass or the hi/lo 3-pass split");
+    constexpr int W_TAP_BYTES = c64_w_tap_bytes(PASSES);
+    constexpr int W_BYTES = 9 * W_TAP_BYTES;
+    constexpr int A_STAGE_BYTES = c64_a_stage_bytes(PASSES);
+    constexpr int STAGES = c64_a_stages(PASSES);
+    constexpr int ACC_COLS = PASSES == 3 ? 128 : 64;
+    constexpr uint32_t IDESC_MAIN = make_idesc(ACC_COLS, FP16);   // A_hi x [W_hi ; W_lo]  (or A x W for one pass)
+    constexpr uint32_t IDESC_N64 = make_idesc(64, FP16);          // A_lo x W_hi
+    static_assert(c64_smem_bytes(PASSES) <= 227 * 1024, "conv_c64_kernel: shared memory budget");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* wsm = smem;                                  // [9 taps][W_hi 64 rows | W_lo 64 rows] x 128 B, swizzled
+    uint8_t* asm_ = smem + W_BYTES;                       // [STAGES][hi patch | lo patch]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(asm_ + STAGES * A_STAGE_BYTES);
+    uint64_t* a_empty = a_full + STAGES;
+    uint64_t* tfull_bar = a_empty + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* w_full = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 4 && lane == 0) {
+        prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w_hi);
+        if (PASSES == 3) { prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kNumEpilogueWarps); }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * ACC_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, W_BYTES);
+            for (int t = 0; t < 9; ++t) {
+                tma_load_2d(&map_w_hi, wsm + t * W_TAP_BYTES, w_full, t * BK, 0);
+                if (PASSES == 3) tma_load_2d(&map_w_lo, wsm + t * W_TAP_BYTES + 64 * BK * 2, w_full, t * BK, 0);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * C64_TW - 1, h0 = th * C64_TH - 1;
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 1);
+                    uint8_t* st = asm_ + stage * A_STAGE_BYTES;
+                    mbar_expect_tx(&a_full[stage], A_STAGE_BYTES);
+                    tma_load_4d(&map_x_hi, st, &a_full[stage], 0, w0 + kw, h0, tb);
+                    if (PASSES == 3) tma_load_4d(&map_x_lo, st + C64_PATCH_BYTES, &a_full[stage], 0, w0 + kw, h0, tb);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            mbar_wait(w_full, 0, p.err_flag, 5);
+            tc_fence_after();
+            const uint32_t wb = smem_u32(wsm);
+            int stage = 0; uint32_t phase = 0;
+            int acc_it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+                const int acc = acc_it & 1;
+                mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(&a_full[stage], phase, p.err_flag, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(asm_ + stage * A_STAGE_BYTES);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint64_t a_hi = make_smem_desc(sa + kh * C64_ROW_BYTES);
+                        const uint64_t a_lo = make_smem_desc(sa + C64_PATCH_BYTES + kh * C64_ROW_BYTES);
+                        const uint64_t b = make_smem_desc(wb + (kh * 3 + kw) * W_TAP_BYTES);
+#pragma unroll
+                        for (int j = 0; j < BK / UMMA_K; ++j) {
+                            const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                            tc_mma_f16(d_tmem, a_hi + koff, b + koff, IDESC_MAIN, (uint32_t)((kw | kh | j) != 0));
+                            if (PASSES == 3) tc_mma_f16(d_tmem, a_lo + koff, b + koff, IDESC_N64, 1u);
+                        }
+                    }
+                    tc_commit(&a_empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31) ================================
+        const int row = threadIdx.x;
+        const int w_l = row % C64_TW, h_l = row / C64_TW;
+        int acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+            const int w = tw * C64_TW + w_l, h = th * C64_TH + h_l;
+            bool valid = (w < p.W) && (h < p.H);
+            int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
+            if (p.pool) {
+                const int par = p.pool == 2 ? 1 : 0;
+                valid = valid && ((w & 1) == par) && ((h & 1) == par);
+                pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+            }
+            const int acc = acc_it & 1;
+            mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, p.err_flag, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+            float racc[64];
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t v[32];
+                tc_ld_32x32b_x32(taddr + c0, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) racc[c0 + q] = __uint_as_float(v[q]);
+                if (PASSES == 3) {   // + the hi*lo products of the stacked half
+                    tc_ld_32x32b_x32(taddr + 64 + c0, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) racc[c0 + q] += __uint_as_float(v[q]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            epilogue_store32<PASSES, FP16>(p, &racc[0], pix, 0, valid);
+            epilogue_store32<PASSES, FP16>(p, &racc[32], pix, 32, valid);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ CTA-pair kernel
 // Same algorithm on a cluster of two CTAs (two SMs of one TPC) with tcgen05 cta_group::2: one UMMA covers M = 256 pixels
 // (CTA r owns pixel tile 2*pair + r and TMEM rows of it) x N = BN channels; each CTA stages its own A tile and HALF of the
@@ -786,6 +961,7 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s);
 
 struct TcConvPlan {
     bool two_cta = false;
+    bool c64 = false;      // 64 -> 64 channel 3x3 specialisation (conv_c64_kernel)
 
     TcConvDesc d;
     CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo, map_x_h8, map_w_l8;
@@ -814,6 +990,21 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s) {
     }
     conv_tc_kernel<BN, PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->map_x_h8,
                                                                       pl->map_w_l8, pl->p);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+}  // namespace
+
+namespace {
+template <int PASSES, bool FP16>
+int launch_c64(const TcConvPlan* pl, cudaStream_t s) {
+    constexpr int smem = c64_smem_bytes(PASSES);
+    static bool attr = false;
+    if (!attr) {
+        H3D_CUDA(cudaFuncSetAttribute(conv_c64_kernel<PASSES, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    conv_c64_kernel<PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }
@@ -864,12 +1055,18 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
         const int v = atoi(e);
         if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
     }
+    // 64 -> 64 channels, 3x3 (conv1_2 of both networks, small lifting layers): weights-resident / patch-reuse kernel
+    bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad == 64 && (d.passes == 1 || d.passes == 3);
+    if (const char* e = getenv("H3D_TC_C64")) c64 = c64 && atoi(e) != 0;
+    if (c64) { two = false; BN = 64; }
     pl->BN = BN;
     pl->two_cta = two;
+    pl->c64 = c64;
 
     int TW, TH, TB;
     if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool / stride 2 needs even H and W"); delete pl; return nullptr; }
     choose_tile(d.B, d.H, d.W, &TW, &TH, &TB, d.pool == 1);
+    if (c64) { TW = C64_TW; TH = C64_TH; TB = 1; }
     TcParams& p = pl->p;
     p.bias = d.bias;
     p.y_hi = d.y.hi; p.y_lo = d.y.lo; p.y_l8 = d.y.l8; p.y_h8 = d.y.h8; p.Cy_total = d.Cy_total; p.cy_off = d.cy_off;
@@ -894,10 +1091,11 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     pl->grid = two ? 2 * std::min(p.num_tiles, tc_num_sms() / 2) : std::min(p.num_tiles, tc_num_sms());
     const int w_box_rows = two ? BN / 2 : BN;
     const int Ktot = d.k * d.k * d.Cin_pad;
-    bool ok = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB) &&
+    const int box_h = c64 ? C64_PH : TH;   // the 64 -> 64 kernel fetches the tile rows plus the halo rows in one box
+    bool ok = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, box_h, TB) &&
               encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, w_box_rows);
     if (ok && d.passes == 3)
-        ok = encode_act_map(&pl->map_x_lo, d.x.lo, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB) &&
+        ok = encode_act_map(&pl->map_x_lo, d.x.lo, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, box_h, TB) &&
              encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, w_box_rows);
     if (ok && d.passes == 4)   // e4m3 planes: x residual (slot "lo"), x coarse, w coarse (slot "lo"), w residual
         ok = encode_act_map(&pl->map_x_lo, d.x.l8, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB, 1) &&
@@ -919,6 +1117,10 @@ int64_t tc_conv_flops(const TcConvPlan* p) {
 int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
     const bool fp16 = pl->d.half == Half16::FP16;
     const int key = pl->BN * 10 + pl->d.passes;
+    if (pl->c64) {
+        if (pl->d.passes == 3) return fp16 ? launch_c64<3, true>(pl, s) : launch_c64<3, false>(pl, s);
+        return fp16 ? launch_c64<1, true>(pl, s) : launch_c64<1, false>(pl, s);
+    }
     if (pl->two_cta) {
 #define CASE2(BN_, P_)                                                                 \
     case BN_ * 10 + P_:                                                                \

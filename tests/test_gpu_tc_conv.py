@@ -19,6 +19,8 @@ CASES = [  # B,H,W,Cin,Cout,k
     (1, 24, 40, 192, 128, 7),   # 7x7, 3 channel chunks, partial tiles
     (2, 20, 12, 100, 72, 3),    # channel padding on both sides
     (1, 64, 64, 256, 512, 3),   # long K loop, pipeline wrap-around, many tiles per CTA
+    (2, 20, 40, 64, 64, 3),     # 64 -> 64 specialisation (weights-resident, patch re-use): ragged rows and columns, several tiles
+    (3, 64, 64, 64, 64, 3),     # 64 -> 64: more tiles than fit one wave of the A ring
 ]
 
 
