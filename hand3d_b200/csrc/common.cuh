@@ -114,6 +114,9 @@ int launch_fc(const float* x, const float* w, const float* bias, float* y, float
 int launch_concat_handside(const float* feat, const float* hand_side, float* out, int B, int feat_n, cudaStream_t s);
 
 // ---------------------------------------------------------------- kernels (conv_tc.cu)
+// first layer (Cin = 3, 3x3, 64 output channels) on the tensor cores, writing split planes (hi, lo optional)
+int launch_conv_c3_tc(const float* x, const float* w, const float* bias, Split y, int Cs_total, int cs_off, int B, int H, int W, int leaky,
+                      Half16 half, cudaStream_t s);
 struct TcConvPlan;  // opaque: tensor maps + launch geometry of one tensor-core conv layer
 struct TcConvDesc {
     // input activations (split planes) [B,H,W,Cin_total]; channels [0,Cin_pad) are read (Cin_pad % 64 == 0)

@@ -247,7 +247,7 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
         }
     }
     if (!valid) return;
-    if (n + 32 > p.n_valid) {   // Cout not a multiple of 32 (score-map heads 2 / 21, lifting 32-channel layers): masked scalar tail
+    if (n + 32 > p.n_valid) {   // Cout not a multiple of 32 (score-map heads 2 / 21, lifting 32-channel layers): masked scalar fp32 tail
         const int cnt = p.n_valid - n;   // <= 0: this 32-channel group is padding only
         if (p.yf && cnt > 0) {
             float* dst = p.yf + pix * p.Cyf_total + p.cyf_off + n;
@@ -255,27 +255,11 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
             for (int q = 0; q < 32; ++q)
                 if (q < cnt) dst[q] = f[q];
         }
-        if (p.y_hi) {   // the split planes carry Cout_pad channels: padding channels are written as zeros (they are the next layer's K padding)
-            const int64_t off = pix * p.Cy_total + p.cy_off + n;
+        // the split planes carry Cout_pad channels: padding channels are written as exact zeros (they are the next layer's K padding)
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const float v = q < cnt ? f[q] : 0.f;
-                if (PASSES == 4) {   // fp16 plane pre-scaled by 2^5 + e4m3 planes (split_fmt.cuh)
-                    const F8cPlanes pl = f32_to_f8c(v);
-                    p.y_hi[off + q] = pl.h16; p.y_l8[off + q] = pl.l8; p.y_h8[off + q] = pl.h8;
-                    continue;
-                }
-                const uint32_t h2 = pack_hi2<FP16>(v, 0.f);
-                p.y_hi[off + q] = (uint16_t)(h2 & 0xFFFFu);
-                if (PASSES == 3 && p.y_lo) {
-                    const float2 r = unpack2<FP16>(h2);
-                    p.y_lo[off + q] = (uint16_t)(pack_hi2<FP16>(v - r.x, 0.f) & 0xFFFFu);
-                }
-            }
-        }
-        return;
-    }
-    if (p.yf) {
+        for (int q = 0; q < 32; ++q)
+            if (q >= cnt) f[q] = 0.f;
+    } else if (p.yf) {
         float4* dst = reinterpret_cast<float4*>(p.yf + pix * p.Cyf_total + p.cyf_off + n);
 #pragma unroll
         for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
@@ -578,6 +562,10 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Cout = 64 * n_tiles: CTA c keeps the weights of the 64-channel group c % n_tiles resident and walks the pixel tiles
+    // c / n_tiles, + gridDim / n_tiles, ... (p.num_tiles counts pixel tiles; the grid is a multiple of n_tiles)
+    const int n0 = (int)(blockIdx.x % p.n_tiles) * 64;
+    const int cta0 = (int)(blockIdx.x / p.n_tiles), cta_step = (int)(gridDim.x / p.n_tiles);
 
     if (warp == 4 && lane == 0) {
         prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w_hi);
@@ -601,11 +589,11 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         if (lane == 0) {
             mbar_expect_tx(w_full, W_BYTES);
             for (int t = 0; t < 9; ++t) {
-                tma_load_2d(&map_w_hi, wsm + t * W_TAP_BYTES, w_full, t * BK, 0);
-                if (PASSES == 3) tma_load_2d(&map_w_lo, wsm + t * W_TAP_BYTES + 64 * BK * 2, w_full, t * BK, 0);
+                tma_load_2d(&map_w_hi, wsm + t * W_TAP_BYTES, w_full, t * BK, n0);
+                if (PASSES == 3) tma_load_2d(&map_w_lo, wsm + t * W_TAP_BYTES + 64 * BK * 2, w_full, t * BK, n0);
             }
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = cta0; tile < p.num_tiles; tile += cta_step) {
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / (p.tiles_w * p.tiles_h);
                 const int w0 = tw * C64_TW - 1, h0 = th * C64_TH - 1;
                 for (int kw = 0; kw < 3; ++kw) {
@@ -626,7 +614,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             const uint32_t wb = smem_u32(wsm);
             int stage = 0; uint32_t phase = 0;
             int acc_it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+            for (int tile = cta0; tile < p.num_tiles; tile += cta_step, ++acc_it) {
                 const int acc = acc_it & 1;
                 mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
                 tc_fence_after();
@@ -658,7 +646,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         const int row = threadIdx.x;
         const int w_l = row % C64_TW, h_l = row / C64_TW;
         int acc_it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+        for (int tile = cta0; tile < p.num_tiles; tile += cta_step, ++acc_it) {
             const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
             const int w = tw * C64_TW + w_l, h = th * C64_TH + h_l;
             bool valid = (w < p.W) && (h < p.H);
@@ -690,8 +678,8 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            epilogue_store32<PASSES, FP16>(p, &racc[0], pix, 0, valid);
-            epilogue_store32<PASSES, FP16>(p, &racc[32], pix, 32, valid);
+            epilogue_store32<PASSES, FP16>(p, &racc[0], pix, n0, valid);
+            epilogue_store32<PASSES, FP16>(p, &racc[32], pix, n0 + 32, valid);
         }
     }
 
@@ -700,6 +688,189 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     if (warp == 5) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ first layer (Cin = 3) on tensor cores
+// conv1_1 of both networks: 3 -> 64 channels, K = 27.  There is nothing for TMA to fetch (3-channel fp32 pixels), so the A
+// operand is BUILT in shared memory: four producer warps stage the 18 x 10 x 3 input patch of a 16 x 8 pixel tile, then every
+// producer thread writes the 27 neighbourhood values of "its" pixel (+ 5 zeros) as hi / lo 16-bit rows in the canonical
+// K-major SWIZZLE_128B layout (byte bits [4,7) ^= bits [7,10); rows keep the 128-byte pitch of the other kernels, only the first
+// 64 bytes = 32 K values are ever read).  The 64 x 27 weights are converted and stored the same way once per CTA
+// ([W_hi ; W_lo] stacked: 128 rows).  Per tile the issuer runs 2 K steps x { A_hi x [W_hi ; W_lo] (N = 128),
+// A_lo x W_hi (N = 64) }; eight epilogue warps add the column halves, apply bias / leaky ReLU and store the split planes.
+// The kernel is bound by its 8 bytes / output value of HBM writes (the FFMA kernel it replaces ran at a quarter of that).
+constexpr int C3T_THREADS = 32 * 13;                 // warps 0-7 epilogue, 8-11 producers, 12 MMA issuer
+constexpr int C3T_STAGES = 2;                        // x 2 CTAs per SM: the kernel is latency bound, not capacity bound
+constexpr int C3T_A_STAGE_BYTES = 2 * A_TILE_BYTES;  // hi + lo tile, 128 rows x 128 B each
+constexpr int C3T_B_BYTES = 128 * BK * 2;            // [W_hi ; W_lo] x 128 B
+constexpr int C3T_PW = C64_TW + 2, C3T_PH = C64_TH + 2;
+constexpr int C3T_PATCH_FLOATS = C3T_PH * C3T_PW * 3;   // 540
+constexpr int C3T_SMEM = C3T_B_BYTES + C3T_STAGES * C3T_A_STAGE_BYTES + 2 * C3T_PATCH_FLOATS * 4 + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// byte offset of 16-byte chunk c (0..7) of row r in a K-major SWIZZLE_128B tile whose base is 1024-byte aligned
+__device__ __forceinline__ uint32_t sw128_chunk(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+template <bool FP16>
+__global__ void __launch_bounds__(C3T_THREADS, 2)
+conv_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, const TcParams p) {
+    constexpr uint32_t IDESC_N128 = make_idesc(128, FP16);
+    constexpr uint32_t IDESC_N64 = make_idesc(64, FP16);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bsm = smem;                                   // weights
+    uint8_t* asm_ = smem + C3T_B_BYTES;                    // [STAGES][A_hi | A_lo]
+    float* patch = reinterpret_cast<float*>(asm_ + C3T_STAGES * C3T_A_STAGE_BYTES);   // [2][PH][PW][3]
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(patch + 2 * C3T_PATCH_FLOATS);
+    uint64_t* a_empty = a_full + C3T_STAGES;
+    uint64_t* tfull_bar = a_empty + C3T_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C3T_STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 8 && warp < 12) {
+        // ================================ producers: build B once, then one A tile per iteration ================================
+        const int t = threadIdx.x - 256;                   // 0..127 = tile row = pixel of the tile
+        {   // weights: row n = output channel (t < 64: hi plane, t >= 64: lo plane of channel t - 64), k = (kh*3 + kw)*3 + ci
+            const int co = t & 63;
+            uint32_t pk[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                float v0 = 0.f, v1 = 0.f;
+                if (2 * k2 < 27) v0 = __ldg(w + (2 * k2) * 64 + co);
+                if (2 * k2 + 1 < 27) v1 = __ldg(w + (2 * k2 + 1) * 64 + co);
+                const uint32_t h = pack_hi2<FP16>(v0, v1);
+                if (t < 64) pk[k2] = h;
+                else { const float2 r = unpack2<FP16>(h); pk[k2] = pack_hi2<FP16>(v0 - r.x, v1 - r.y); }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(bsm + sw128_chunk(t, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        const int w_l = t % C64_TW, h_l = t / C64_TW;
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        // haloed input patch of a tile -> registers (5 independent loads per thread), zero outside the image ('SAME' padding);
+        // the loads of tile i+1 are issued before tile i is converted, so their latency is hidden behind the build
+        constexpr int PRE = (C3T_PATCH_FLOATS + 127) / 128;
+        float pre[PRE];
+        auto load_patch = [&](int tile) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+            const int x0 = tw * C64_TW - 1, y0 = th * C64_TH - 1;
+            const float* xb = x + (int64_t)b * p.H * p.W * 3;
+#pragma unroll
+            for (int j = 0; j < PRE; ++j) {
+                const int i = t + j * 128;
+                const int r = i / (C3T_PW * 3), rem = i - r * (C3T_PW * 3);
+                const int gy = y0 + r, gx = x0 + rem / 3;
+                float v = 0.f;
+                if (i < C3T_PATCH_FLOATS && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(xb + ((int64_t)gy * p.W + x0) * 3 + rem);
+                pre[j] = v;
+            }
+        };
+        if ((int)blockIdx.x < p.num_tiles) load_patch(blockIdx.x);
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            float* pb = patch + (it & 1) * C3T_PATCH_FLOATS;
+#pragma unroll
+            for (int j = 0; j < PRE; ++j)
+                if (t + j * 128 < C3T_PATCH_FLOATS) pb[t + j * 128] = pre[j];
+            named_bar_sync(1, 128);
+            if (tile + (int)gridDim.x < p.num_tiles) load_patch(tile + gridDim.x);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                float v0 = 0.f, v1 = 0.f;
+                if (2 * k2 < 27) { const int k = 2 * k2; v0 = pb[(h_l + k / 9) * (C3T_PW * 3) + w_l * 3 + (k % 9)]; }
+                if (2 * k2 + 1 < 27) { const int k = 2 * k2 + 1; v1 = pb[(h_l + k / 9) * (C3T_PW * 3) + w_l * 3 + (k % 9)]; }
+                hi[k2] = pack_hi2<FP16>(v0, v1);
+                const float2 r = unpack2<FP16>(hi[k2]);
+                lo[k2] = pack_hi2<FP16>(v0 - r.x, v1 - r.y);
+            }
+            mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 1);
+            uint8_t* st = asm_ + stage * C3T_A_STAGE_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4*>(st + sw128_chunk(t, c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                *reinterpret_cast<uint4*>(st + A_TILE_BYTES + sw128_chunk(t, c)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+            fence_proxy_async_smem();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            mbar_arrive(&a_full[stage]);
+            if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 12) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint64_t bdesc = make_smem_desc(smem_u32(bsm));
+            int stage = 0; uint32_t phase = 0; int acc_it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+                const int acc = acc_it & 1;
+                mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+                mbar_wait(&a_full[stage], phase, p.err_flag, 3);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                const uint32_t sa = smem_u32(asm_ + stage * C3T_A_STAGE_BYTES);
+                const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {                // K = 32 (27 taps x channels + 5 zeros)
+                    const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                    tc_mma_f16(d_tmem, a_hi + koff, bdesc + koff, IDESC_N128, (uint32_t)(j != 0));
+                    tc_mma_f16(d_tmem, a_lo + koff, bdesc + koff, IDESC_N64, 1u);
+                }
+                tc_commit(&a_empty[stage]);
+                tc_commit(&tfull_bar[acc]);
+                if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue: warps 0-7, lane quadrant = warp % 4, channel half = warp / 4 ================================
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        const int w_l = row % C64_TW, h_l = row / C64_TW;
+        int acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+            const int wx = tw * C64_TW + w_l, hy = th * C64_TH + h_l;
+            const bool valid = (wx < p.W) && (hy < p.H);
+            const int64_t pix = ((int64_t)b * p.H + hy) * p.W + wx;
+            const int acc = acc_it & 1;
+            mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, p.err_flag, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + ch * 32);
+            uint32_t v[32], v2[32];
+            tc_ld_32x32b_x32(taddr, v);
+            tc_ld_32x32b_x32(taddr + 64, v2);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            float racc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) racc[i] = __uint_as_float(v[i]) + __uint_as_float(v2[i]);
+            if (p.y_lo) epilogue_store32<3, FP16>(p, racc, pix, ch * 32, valid);
+            else epilogue_store32<1, FP16>(p, racc, pix, ch * 32, valid);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
     }
 }
 
@@ -1056,7 +1227,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
         if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
     }
     // 64 -> 64 channels, 3x3 (conv1_2 of both networks, small lifting layers): weights-resident / patch-reuse kernel
-    bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad == 64 && (d.passes == 1 || d.passes == 3);
+    bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad <= 128 && (d.passes == 1 || d.passes == 3);
     if (const char* e = getenv("H3D_TC_C64")) c64 = c64 && atoi(e) != 0;
     if (c64) { two = false; BN = 64; }
     pl->BN = BN;
@@ -1089,6 +1260,10 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if (const char* e = getenv("H3D_TC_CHUNK_KB")) { const int v = atoi(e); if (v > 0) p.chunk_kb = v; }
     if (BN > 128 && !two) p.chunk_kb = 1 << 30;
     pl->grid = two ? 2 * std::min(p.num_tiles, tc_num_sms() / 2) : std::min(p.num_tiles, tc_num_sms());
+    if (c64) {   // work items = pixel tiles; CTAs are split evenly over the 64-channel groups
+        p.num_tiles = p.tiles_w * p.tiles_h * tiles_b;
+        pl->grid = p.n_tiles * std::max(1, std::min(p.num_tiles, tc_num_sms() / p.n_tiles));
+    }
     const int w_box_rows = two ? BN / 2 : BN;
     const int Ktot = d.k * d.k * d.Cin_pad;
     const int box_h = c64 ? C64_PH : TH;   // the 64 -> 64 kernel fetches the tile rows plus the halo rows in one box
@@ -1145,6 +1320,33 @@ int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
 #undef CASE
     set_error("tc_conv: no kernel instance for BN=%d passes=%d", pl->BN, pl->d.passes);
     return H3D_EINVAL;
+}
+
+// conv1_1 (3 -> 64 channels, 3x3, stride 1) on the tensor cores: x fp32 [B,H,W,3], w fp32 HWIO [3,3,3,64] and bias [64] on the
+// device, output split planes y (hi, and lo when present) [B,H,W,Cs_total] at channel offset cs_off.
+int launch_conv_c3_tc(const float* x, const float* w, const float* bias, Split y, int Cs_total, int cs_off, int B, int H, int W, int leaky,
+                      Half16 half, cudaStream_t s) {
+    H3D_REQUIRE(x && w && bias && y.hi && !y.l8 && (Cs_total % 8) == 0 && (cs_off % 8) == 0, "conv_c3_tc: bad argument");
+    TcParams p{};
+    p.bias = bias;
+    p.y_hi = y.hi; p.y_lo = y.lo; p.Cy_total = Cs_total; p.cy_off = cs_off;
+    p.corr_scale = 1.f;
+    p.B = B; p.H = H; p.W = W; p.k = 3; p.pad = 1; p.cin_chunks = 1;
+    p.TW = C64_TW; p.TH = C64_TH; p.TB = 1;
+    p.tiles_w = ceil_div(W, C64_TW); p.tiles_h = ceil_div(H, C64_TH); p.n_tiles = 1;
+    p.num_tiles = p.tiles_w * p.tiles_h * B;
+    p.n_valid = 64; p.pool = 0; p.chunk_kb = 1; p.leaky = leaky; p.err_flag = nullptr;
+    const int grid = std::min(p.num_tiles, 2 * tc_num_sms());   // two co-resident CTAs per SM (86 KB, 72 registers, 256 TMEM columns each)
+    static bool attr = false;
+    if (!attr) {
+        H3D_CUDA(cudaFuncSetAttribute(conv_c3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3T_SMEM));
+        H3D_CUDA(cudaFuncSetAttribute(conv_c3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3T_SMEM));
+        attr = true;
+    }
+    if (half == Half16::FP16) conv_c3_tc_kernel<true><<<grid, C3T_THREADS, C3T_SMEM, s>>>(x, w, p);
+    else conv_c3_tc_kernel<false><<<grid, C3T_THREADS, C3T_SMEM, s>>>(x, w, p);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
 }
 
 }  // namespace h3d

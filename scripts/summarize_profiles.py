@@ -34,29 +34,52 @@ def main():
     os.makedirs("profiles", exist_ok=True)
     out = {}
     if os.path.exists(a.launches):
-        rows = read_ncu_csv(a.launches)
-        names = [(short(r["Kernel Name"]), float(r["Metric Value"].replace(",", "")) / 1e3, r["Grid Size"]) for r in rows]
-        ends = [i for i, (n, _, _) in enumerate(names) if "CatArray" in n]
+        # one row per (launch, metric): duration always, DRAM bytes / tensor-pipe activity when the stage collected them
+        by_id = collections.OrderedDict()
+        for r in read_ncu_csv(a.launches):
+            d = by_id.setdefault(r["ID"], {"name": short(r["Kernel Name"]), "grid": r["Grid Size"]})
+            d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+        names = [(d["name"], d.get("gpu__time_duration.sum", 0.0) / 1e3, d["grid"], d) for d in by_id.values()]
+        ends = [i for i, (n, _, _, _) in enumerate(names) if "CatArray" in n]
         s, e = (ends[2] + 1, ends[3] + 1) if len(ends) > 3 else (0, len(names))
         step = names[s:e]
+        have_dram = any("dram__bytes_read.sum" in d for _, _, _, d in step)
         agg = collections.OrderedDict()
-        for n, v, g in step:
-            agg.setdefault(n, [0.0, 0])
-            agg[n][0] += v; agg[n][1] += 1
-        tot = sum(v for _, v, _ in step)
+        for n, v, g, d in step:
+            a_ = agg.setdefault(n, [0.0, 0, 0.0, 0.0])
+            a_[0] += v; a_[1] += 1
+            a_[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+            a_[3] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * v
+        tot = sum(v for _, v, _, _ in step)
         with open("profiles/%s_launches.md" % a.tag, "w") as f:
-            f.write("# %s: every launch of one bench step (ncu --metrics gpu__time_duration.sum --clock-control none)\n\n" % a.tag)
+            f.write("# %s: every launch of one bench step (ncu --metrics gpu__time_duration.sum[,dram__bytes_*,sm__pipe_tensor_cycles_active] --clock-control none)\n\n" % a.tag)
             f.write("Command: `ncu ... python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (B = 32, 320x320, bf16x3). "
-                    "Per-launch times are cold-cache and serialised: compare SHARES.\n\n")
-            f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
-            for n, (v, c) in sorted(agg.items(), key=lambda x: -x[1][0]):
-                f.write("| `%s` | %d | %.1f | %.1f %% |\n" % (n, c, v, 100 * v / tot))
-            f.write("| **sum** | %d | %.1f | 100 %% |\n\n" % (len(step), tot))
-            f.write("## launch list\n\n| # | kernel | grid | us |\n|---:|---|---|---:|\n")
-            for i, (n, v, g) in enumerate(step):
-                f.write("| %d | `%s` | %s | %.1f |\n" % (i, n, g, v))
-        out["launches"] = {"step_us": tot, "by_kernel_us": {n: v for n, (v, c) in agg.items()}}
-    if os.path.exists(a.dram):
+                    "Per-launch times are cold-cache and serialised: compare SHARES.  HBM GB/s = (DRAM read + write bytes) / duration "
+                    "(measured peak copy bandwidth of this pool: 6576 GB/s, MEASURED_PEAKS.json).\n\n")
+            f.write("| kernel | launches | total us | share | DRAM MB | HBM GB/s | tensor pipe active % (time-weighted) |\n|---|---:|---:|---:|---:|---:|---:|\n")
+            for n, (v, c, byt, tp) in sorted(agg.items(), key=lambda x: -x[1][0]):
+                f.write("| `%s` | %d | %.1f | %.1f %% | %s | %s | %s |\n" % (
+                    n, c, v, 100 * v / tot, "%.1f" % (byt / 1e6) if have_dram else "-",
+                    "%.0f" % (byt / 1e3 / v) if have_dram and v > 0 else "-", "%.1f" % (tp / v) if have_dram and v > 0 else "-"))
+            f.write("| **sum** | %d | %.1f | 100 %% | %s | | |\n\n" % (len(step), tot, "%.1f" % (sum(x[2] for x in agg.values()) / 1e6) if have_dram else "-"))
+            f.write("## launch list\n\n| # | kernel | grid | us | DRAM read MB | DRAM write MB | HBM GB/s | tensor pipe % |\n|---:|---|---|---:|---:|---:|---:|---:|\n")
+            for i, (n, v, g, d) in enumerate(step):
+                rd, wr = d.get("dram__bytes_read.sum", 0.0), d.get("dram__bytes_write.sum", 0.0)
+                f.write("| %d | `%s` | %s | %.1f | %s | %s | %s | %s |\n" % (
+                    i, n, g, v, "%.2f" % (rd / 1e6) if have_dram else "-", "%.2f" % (wr / 1e6) if have_dram else "-",
+                    "%.0f" % ((rd + wr) / 1e3 / v) if have_dram and v > 0 else "-",
+                    "%.1f" % d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) if have_dram else "-"))
+        out["launches"] = {"step_us": tot, "by_kernel_us": {n: x[0] for n, x in agg.items()}}
+        if have_dram:
+            tc = [(n, v, d) for n, v, _, d in step if re.match(r"conv_(tc|c64)", n)]
+            byt = sum(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for _, _, d in tc)
+            t = sum(v for _, v, _ in tc)
+            tw = sum(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * v for _, v, d in tc) / max(t, 1e-9)
+            out["tc_conv"] = {"launches_per_step": len(tc), "dram_bytes_per_step": byt, "dram_bytes_per_launch": byt / max(len(tc), 1),
+                              "time_us_per_step": t, "tensor_pipe_active_pct_time_weighted": tw}
+            out["hbm_kernels"] = {n: {"us": x[0], "dram_mb": x[2] / 1e6, "gb_per_s": x[2] / 1e3 / x[0] if x[0] > 0 else 0.0}
+                                  for n, x in agg.items() if not re.match(r"conv_(tc|c64)", n)}
+    if os.path.exists(a.dram) and "tc_conv" not in out:
         rows = read_ncu_csv(a.dram)
         by = collections.OrderedDict()
         for r in rows:
@@ -91,7 +114,7 @@ def main():
                     "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg.per_second",
                     "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"]
             with open("profiles/%s_tc_conv_ncu_full.md" % a.tag, "w") as f:
-                f.write("# %s: `ncu --set full --clock-control none --import-source on -k regex:conv_tc` (3 launches of the dominant kernel)\n\n" % a.tag)
+                f.write("# %s: `ncu --set full --clock-control none --import-source on -k regex:conv_(tc|c64)` (the first tensor-core launches of one step: conv1_2 .. conv4_4 of HandSegNet)\n\n" % a.tag)
                 for r in rows[2:]:
                     f.write("| metric | value | unit |\n|---|---:|---|\n")
                     for k in keys:

@@ -21,6 +21,7 @@ CASES = [  # B,H,W,Cin,Cout,k
     (1, 64, 64, 256, 512, 3),   # long K loop, pipeline wrap-around, many tiles per CTA
     (2, 20, 40, 64, 64, 3),     # 64 -> 64 specialisation (weights-resident, patch re-use): ragged rows and columns, several tiles
     (3, 64, 64, 64, 64, 3),     # 64 -> 64: more tiles than fit one wave of the A ring
+    (2, 24, 48, 64, 128, 3),    # 64 -> 128 (conv2_1): two 64-channel groups, CTAs split between them
 ]
 
 
