@@ -655,22 +655,50 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
     auto xyz = ctx->host_w.find("PosePrior/fc_xyz/weights");
     if (xyz == ctx->host_w.end()) { set_error("weights PosePrior/fc_xyz not loaded"); return H3D_EWEIGHTS; }
     const int xyz_in = (int)xyz->second.shape[0];
+    // FC layers on the tensor-core kernel: a fully connected layer is a 1x1 convolution over B "images" of 1x1 pixels (tile =
+    // 128 batch rows, K = in_features padded to 64, weights [in,out] = HWIO [1,1,in,out]); activations stay split planes
+    struct Planes { Split s; int stride; };
+    auto carve_planes = [&](char*& cur, int width) -> Planes {
+        Planes pz; pz.stride = (int)align_up(width, 64);
+        const int64_t bytes = align_up((int64_t)B * pz.stride * 2, 1024);
+        pz.s.hi = (uint16_t*)cur; pz.s.lo = (uint16_t*)(cur + bytes);
+        cur += 2 * bytes;
+        return pz;
+    };
+    auto fc_tc = [&](const std::string& scope, const char* name, int in_f, int out_f, int leaky, const Planes& x, const Planes* y, float* yf) -> int {
+        LayerSpec l{name, 1, 1, in_f, out_f, leaky};
+        return add_tc(ctx, pl.get(), scope, l, B, 1, 1, x.s, x.stride, (int)align_up(in_f, 64), {}, y ? y->s : Split(), y ? y->stride : 0, 0, yf,
+                      out_f, 0, 0);
+    };
     auto pose_prior = [&]() -> int {
         const Branch& b = br[0];
         float* feat = nullptr;
         int rc2;
         if ((rc2 = pyramid("PosePrior", kPosePrior, b, &feat))) return rc2;
+        if (bott) H3D_REQUIRE(xyz_in == 30, "bottleneck variant needs PosePrior/fc_xyz/weights of shape [30,63]");
+        else H3D_REQUIRE(xyz_in == 512, "PosePrior/fc_xyz/weights must have shape [512,63] for this variant");
+        if (tc_lift) {   // slot[0] (layer-4 output, dead by now) holds the FC activations
+            char* cur = b.slot[0];
+            const Planes xp = carve_planes(cur, 2050), p1 = carve_planes(cur, 512), p2 = carve_planes(cur, 512), p3 = carve_planes(cur, 64);
+            pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside_split(feat, e.hand_side, xp.s, B, 2048, xp.stride, half, s); });
+            pl->launches.push_back(1);
+            if ((rc2 = fc_tc("PosePrior", "fc_rel0", 2050, 512, 1, xp, &p1, nullptr))) return rc2;
+            if ((rc2 = fc_tc("PosePrior", "fc_rel1", 512, 512, 1, p1, &p2, nullptr))) return rc2;
+            if (bott) {
+                if ((rc2 = fc_tc("PosePrior", "fc_bottleneck", 512, 30, 0, p2, &p3, nullptr))) return rc2;
+                return fc_tc("PosePrior", "fc_xyz", 30, 63, 0, p3, nullptr, can);
+            }
+            return fc_tc("PosePrior", "fc_xyz", 512, 63, 0, p2, nullptr, can);
+        }
         float* xcat = b.xcat;
         pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(feat, e.hand_side, xcat, B, 2048, s); });
         pl->launches.push_back(1);
         if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_rel0", b.xcat, b.t1, b.fcs, B, 2050, 512, 1))) return rc2;
         if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_rel1", b.t1, b.t2, b.fcs, B, 512, 512, 1))) return rc2;
         if (bott) {
-            H3D_REQUIRE(xyz_in == 30, "bottleneck variant needs PosePrior/fc_xyz/weights of shape [30,63]");
             if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_bottleneck", b.t2, b.t3, b.fcs, B, 512, 30, 0))) return rc2;
             if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", b.t3, can, b.fcs, B, 30, 63, 0))) return rc2;
         } else {
-            H3D_REQUIRE(xyz_in == 512, "PosePrior/fc_xyz/weights must have shape [512,63] for this variant");
             if ((rc2 = add_fc(ctx, pl.get(), "PosePrior/fc_xyz", b.t2, can, b.fcs, B, 512, 63, 0))) return rc2;
         }
         return H3D_OK;
@@ -683,11 +711,20 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
         float* feat = nullptr;
         pl->cur_lane = 1;
         if ((rc = pyramid("ViewpointNet", kViewpoint, b, &feat))) return rc;
-        float* xcat = b.xcat;
-        pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(feat, e.hand_side, xcat, B, 4096, s); });
-        pl->launches.push_back(1);
-        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp0", b.xcat, b.t1, b.fcs, B, 4098, 256, 1))) return rc;
-        if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp1", b.t1, b.t2, b.fcs, B, 256, 128, 1))) return rc;
+        if (tc_lift) {
+            char* cur = b.slot[0];
+            const Planes xp = carve_planes(cur, 4098), p1 = carve_planes(cur, 256);
+            pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside_split(feat, e.hand_side, xp.s, B, 4096, xp.stride, half, s); });
+            pl->launches.push_back(1);
+            if ((rc = fc_tc("ViewpointNet", "fc_vp0", 4098, 256, 1, xp, &p1, nullptr))) return rc;
+            if ((rc = fc_tc("ViewpointNet", "fc_vp1", 256, 128, 1, p1, nullptr, b.t2))) return rc;   // fp32 [B,128] for the three 128 -> 1 heads
+        } else {
+            float* xcat = b.xcat;
+            pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside(feat, e.hand_side, xcat, B, 4096, s); });
+            pl->launches.push_back(1);
+            if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp0", b.xcat, b.t1, b.fcs, B, 4098, 256, 1))) return rc;
+            if ((rc = add_fc(ctx, pl.get(), "ViewpointNet/fc_vp1", b.t1, b.t2, b.fcs, B, 256, 128, 1))) return rc;
+        }
         const float* hw = ctx->vp_head_w; const float* hb = ctx->vp_head_b;
         float* t2 = b.t2; float* fcs = b.fcs;
         pl->steps.push_back([=](const Ext&, cudaStream_t s) { return launch_fc(t2, hw, hb, uxyz, fcs, B, 128, 3, 0, 128, s); });

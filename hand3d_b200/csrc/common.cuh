@@ -112,6 +112,8 @@ int launch_fc(const float* x, const float* w, const float* bias, float* y, float
               int x_stride, cudaStream_t s);
 // gathers [conv_feat(b, :feat) , hand_side(b, :2)] -> xcat [B, feat+2]
 int launch_concat_handside(const float* feat, const float* hand_side, float* out, int B, int feat_n, cudaStream_t s);
+// same as 16-bit split planes [B, Kpad] (Kpad % 64 == 0, zero padded): input of the tensor-core FC stack
+int launch_concat_handside_split(const float* feat, const float* hand_side, Split out, int B, int feat_n, int Kpad, Half16 t, cudaStream_t s);
 
 // ---------------------------------------------------------------- kernels (conv_tc.cu)
 // first layer (Cin = 3, 3x3, 64 output channels) on the tensor cores, writing split planes (hi, lo optional)

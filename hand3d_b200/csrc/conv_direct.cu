@@ -466,6 +466,28 @@ __global__ void concat_handside_kernel(const float* __restrict__ feat, const flo
         out[i] = c < n ? feat[(int64_t)b * n + c] : hs[2 * b + (c - n)];
     }
 }
+// same, emitting the 16-bit split planes [B, Kpad] (zero padded) that feed the tensor-core FC stack
+template <bool FP16>
+__global__ void concat_handside_split_kernel(const float* __restrict__ feat, const float* __restrict__ hs, uint16_t* __restrict__ hi,
+                                             uint16_t* __restrict__ lo, int B, int n, int Kpad) {
+    const int64_t total = (int64_t)B * Kpad;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Kpad);
+        const int b = (int)(i / Kpad);
+        const float v = c < n ? feat[(int64_t)b * n + c] : (c < n + 2 ? hs[2 * b + (c - n)] : 0.f);
+        const uint16_t h = to_h16<FP16>(v);
+        hi[i] = h;
+        if (lo) lo[i] = to_h16<FP16>(v - from_h16<FP16>(h));
+    }
+}
+int launch_concat_handside_split(const float* feat, const float* hand_side, Split out, int B, int feat_n, int Kpad, Half16 t, cudaStream_t s) {
+    H3D_REQUIRE(out.hi && !out.l8 && Kpad >= feat_n + 2, "concat_handside_split: bad argument");
+    const int blocks = (int)std::min<int64_t>(ceil_div64((int64_t)B * Kpad, 256), 1024);
+    if (t == Half16::FP16) concat_handside_split_kernel<true><<<blocks, 256, 0, s>>>(feat, hand_side, out.hi, out.lo, B, feat_n, Kpad);
+    else concat_handside_split_kernel<false><<<blocks, 256, 0, s>>>(feat, hand_side, out.hi, out.lo, B, feat_n, Kpad);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
 int launch_concat_handside(const float* feat, const float* hand_side, float* out, int B, int feat_n, cudaStream_t s) {
     const int64_t total = (int64_t)B * (feat_n + 2);
     concat_handside_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 1024), 256, 0, s>>>(feat, hand_side, out, B, feat_n);

@@ -260,9 +260,15 @@ __device__ __forceinline__ void epilogue_store32(const TcParams& p, const float*
         for (int q = 0; q < 32; ++q)
             if (q >= cnt) f[q] = 0.f;
     } else if (p.yf) {
-        float4* dst = reinterpret_cast<float4*>(p.yf + pix * p.Cyf_total + p.cyf_off + n);
+        if (((p.Cyf_total | p.cyf_off) & 3) == 0) {
+            float4* dst = reinterpret_cast<float4*>(p.yf + pix * p.Cyf_total + p.cyf_off + n);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        } else {   // row stride not a multiple of 16 bytes (e.g. the 63-wide fc_xyz output): scalar stores
+            float* dst = p.yf + pix * p.Cyf_total + p.cyf_off + n;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) dst[q] = f[q];
+        }
     }
     if (p.y_hi) {
         const int64_t off = pix * p.Cy_total + p.cy_off + n;
