@@ -1228,6 +1228,9 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     bool two = d.Cout_pad % 256 == 0;
     if (const char* e = getenv("H3D_TC_2CTA")) two = atoi(e) != 0;
     if (two) BN = d.Cout_pad % 256 == 0 ? 256 : (d.Cout_pad % 128 == 0 ? 128 : 64);   // CTA pair: UMMA 256 x BN
+    // FC-like shapes (one or two pixel tiles: the FC stacks of the lifting networks run as 1x1 convolutions over batch rows) are
+    // weight-streaming problems: N = 64 tiles on single CTAs spread the weight matrix over 4-8x more SMs
+    if ((int64_t)d.B * d.H * d.W <= 2 * BM) { two = false; BN = 64; }
     if (const char* e = getenv("H3D_TC_BN")) {
         const int v = atoi(e);
         if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;

@@ -24,9 +24,9 @@ for s in $STAGES; do
     ref)   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?" ;;
     ncu)   timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv \
              python bench.py --steps 1 --warmup 3 --batch ${NCU_BATCH:-32} --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?" ;;
-    ncudram) timeout 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -k "regex:conv_(tc|c64)" -s ${TC_SKIP:-171} -c ${TC_COUNT:-57} --csv --log-file gpurun_out/tc_dram.csv \
+    ncudram) timeout 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed --clock-control none -k "regex:conv_(tc|c64)" -s ${TC_SKIP:-186} -c ${TC_COUNT:-62} --csv --log-file gpurun_out/tc_dram.csv \
              python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncudram.log 2>&1; echo "ncudram rc=$?" ;;
-    ncufull) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:conv_(tc|c64)" -s ${NCU_SKIP:-171} -c ${NCU_COUNT:-11} -o gpurun_out/prof_tc -f \
+    ncufull) timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:conv_(tc|c64)" -s ${NCU_SKIP:-186} -c ${NCU_COUNT:-11} -o gpurun_out/prof_tc -f \
              python bench.py --steps 1 --warmup 3 --batch ${NCU_BATCH:-32} --no-cpu-baseline > gpurun_out/ncufull.log 2>&1; echo "ncufull rc=$?" ;;
   esac
 done
