@@ -57,6 +57,7 @@ struct TcParams {
                     // of the stride-1 result); outputs are [B, H/2, W/2, C] in both modes
     int chunk_kb;   // K blocks accumulated inside the tensor core before the epilogue folds the partial sum into fp32 registers
     int leaky;
+    int stack;      // N-stacked passes (generic single-CTA kernel, 3-pass, BN <= 128); 0 = three separate UMMAs per K step
     int* err_flag;
 };
 
@@ -327,7 +328,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     constexpr int B_TILE_BYTES = BN * BK * 2;
     constexpr int A8_TILE_BYTES = BM * BK, B8_TILE_BYTES = BN * BK;       // e4m3 tiles: 64-byte rows
     constexpr uint32_t IDESC = make_idesc(BN, FP16);
-    constexpr int ACC_COLS = BN;                                           // TMEM columns per accumulator stage
+    // N-stacking (3-pass, BN <= 128): hi*hi and hi*lo are ONE UMMA with N = 2 BN over the adjacent [W_hi ; W_lo] tiles of the stage
+    // (TMEM columns [0,BN) and [BN,2BN)), lo*hi a second one with N = BN into columns [0,BN): the A operand is read from shared
+    // memory twice instead of three times per K step (the single-CTA kernel is shared-memory-read bound); the epilogue adds the halves.
+    constexpr bool STACK = (PASSES == 3) && (BN <= 128);
+    constexpr uint32_t IDESC_STACK = make_idesc(STACK ? 2 * BN : BN, FP16);
+    constexpr int ACC_COLS = STACK ? 2 * BN : BN;                          // TMEM columns per accumulator stage
+    constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
+    static_assert(2 * ACC_COLS <= 512, "TMEM: two accumulator stages must fit 512 columns");
     static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
     static_assert(PASSES != 4 || FP16, "fp8-correction mode uses an fp16 main plane");
 
@@ -352,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -416,10 +424,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
 #pragma unroll
                         for (int j = 0; j < BK / UMMA_K; ++j) {
                             const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);   // advance the start address by 32 B per K step
-                            tc_mma_f16(d_tmem, a_hi + koff, b_hi + koff, IDESC, (uint32_t)((kb > kb0) | (j != 0)));
-                            if (PASSES == 3) {
-                                tc_mma_f16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
+                            if (STACK && p.stack) {
+                                tc_mma_f16(d_tmem, a_hi + koff, b_hi + koff, IDESC_STACK, (uint32_t)((kb > kb0) | (j != 0)));
                                 tc_mma_f16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+                            } else {
+                                tc_mma_f16(d_tmem, a_hi + koff, b_hi + koff, IDESC, (uint32_t)((kb > kb0) | (j != 0)));
+                                if (PASSES == 3) {
+                                    tc_mma_f16(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
+                                    tc_mma_f16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+                                }
                             }
                         }
                         if (PASSES == 4) {   // two e4m3 correction passes (K = 32 per MMA: 32 bytes per row), same accumulator
@@ -479,6 +492,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
 #pragma unroll
                             for (int q = 0; q < 32; ++q) racc[c0 + q] += __uint_as_float(v[q]);
                         }
+                        if (STACK && p.stack) {   // + the hi*lo products of the stacked half
+                            tc_ld_32x32b_x32(taddr + BN + c0, v);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) racc[c0 + q] += __uint_as_float(v[q]);
+                        }
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -514,7 +533,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -1262,6 +1281,8 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     p.leaky = d.leaky;
     p.n_valid = d.Cout;
     p.pool = d.pool;
+    p.stack = 1;
+    if (const char* e = getenv("H3D_TC_STACK")) p.stack = atoi(e) != 0;
     p.err_flag = nullptr;
     // <= ~108 accumulating MMAs per TMEM partial sum (9 K blocks x 4 K steps x 3 passes); BN = 256 keeps everything in
     // TMEM (its 256 fp32 partial sums per thread would not fit the register file)
