@@ -22,6 +22,7 @@ CASES = [  # B,H,W,Cin,Cout,k
     (2, 20, 40, 64, 64, 3),     # 64 -> 64 specialisation (weights-resident, patch re-use): ragged rows and columns, several tiles
     (3, 64, 64, 64, 64, 3),     # 64 -> 64: more tiles than fit one wave of the A ring
     (2, 24, 48, 64, 128, 3),    # 64 -> 128 (conv2_1): two 64-channel groups, CTAs split between them
+    (4, 80, 80, 128, 256, 3),   # enough tiles (200) for the CTA-pair kernel to be chosen by the policy itself
 ]
 
 
@@ -36,6 +37,23 @@ def ctx():
 def test_conv2d_tc_vs_oracle(ctx, case, prec):
     B, H, W, Cin, Cout, k = case
     rng = np.random.default_rng(11)
+    x = rng.normal(size=(B, H, W, Cin)).astype(f32)
+    w = (rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(f32)
+    b = rng.normal(size=Cout).astype(f32)
+    y = ctx.conv2d_tc(torch.from_numpy(x).cuda(), w, b, leaky=True, precision=prec).cpu().numpy()
+    ref = T.leaky_relu(T.conv2d_same(x, w, b, 1, np.float64))
+    err = np.abs(y - ref).max()
+    assert err < TOL[prec], "max abs err %.3e (tolerance %.1e)" % (err, TOL[prec])
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16", "fp16_f8c"])
+@pytest.mark.parametrize("case", [CASES[3], CASES[4], CASES[6]])
+def test_conv2d_tc_forced_cta_pair(ctx, case, prec, monkeypatch):
+    """Small problems normally fall back to single-CTA tiles; H3D_TC_2CTA=1 forces the cta_group::2 kernel onto them
+    (ragged pairs, odd tile counts, N = 128 / 256 pair tiles)."""
+    monkeypatch.setenv("H3D_TC_2CTA", "1")
+    B, H, W, Cin, Cout, k = case
+    rng = np.random.default_rng(15)
     x = rng.normal(size=(B, H, W, Cin)).astype(f32)
     w = (rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(f32)
     b = rng.normal(size=Cout).astype(f32)
