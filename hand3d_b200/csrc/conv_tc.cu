@@ -1247,14 +1247,11 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     bool two = d.Cout_pad % 256 == 0;
     if (const char* e = getenv("H3D_TC_2CTA")) two = atoi(e) != 0;
     if (two) BN = d.Cout_pad % 256 == 0 ? 256 : (d.Cout_pad % 128 == 0 ? 128 : 64);   // CTA pair: UMMA 256 x BN
-    // Small problems (lifting pyramids, the FC stacks = 1x1 convolutions over batch rows, single-image calls): when the tile count
-    // would leave more than half of the SMs idle, narrower N tiles on single CTAs spread the work (and the weight stream) wider
-    if (!getenv("H3D_TC_2CTA") && !getenv("H3D_TC_BN")) {   // (the environment overrides exist for tests and tuning)
-        const int64_t m_tiles = ceil_div64((int64_t)d.B * d.H * d.W, BM);
-        auto work = [&](int bn, bool pair) { return (pair ? (m_tiles + 1) / 2 : m_tiles) * (d.Cout_pad / bn); };
-        if (work(BN, two) < tc_num_sms() / 2) { two = false; BN = d.Cout_pad % 128 == 0 ? 128 : 64; }
-        if (work(BN, two) < tc_num_sms() / 2) BN = 64;
-    }
+    // Small maps (lifting pyramids from 16x16 down, the FC stacks = 1x1 convolutions over batch rows): too few pixel tiles to fill
+    // the machine with wide tiles, so N = 64 tiles on single CTAs spread the work (and the weight stream) over 4-8x more SMs.  The
+    // rule depends on the layer geometry only, never on the batch size: the arithmetic of an image must not depend on how a batch
+    // is cut (tests/test_gpu_properties.py: bit-identical results under sharding).
+    if (!getenv("H3D_TC_2CTA") && (int64_t)d.H * d.W <= 256) { two = false; BN = 64; }
     if (const char* e = getenv("H3D_TC_BN")) {
         const int v = atoi(e);
         if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
