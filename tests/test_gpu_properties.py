@@ -83,3 +83,21 @@ def test_single_image_and_odd_batch_shapes(ctx):
         one = _run(ctx, img[:1], hs[:1])
         for k in DISCRETE + CONV:
             np.testing.assert_array_equal(one[k][0], r[k][0], err_msg=k)
+
+
+def test_cuda_graph_replay_matches_eager(ctx):
+    """The whole forward pass (incl. the branches forked onto the context's side streams) captures into one CUDA graph;
+    replays on refreshed inputs are bit-identical to eager calls."""
+    B = 4
+    imgs = [Wt.synthetic_images(B, 320, 320, seed=31 + i) for i in range(2)]
+    hs = Wt.synthetic_hand_side(B, seed=33)
+    ti, th = torch.from_numpy(imgs[0]).cuda(), torch.from_numpy(hs).cuda()
+    replay, res = ctx.capture_pipeline(ti, th, True, outputs="keypoints")
+    for img in imgs[::-1] + imgs:
+        ti.copy_(torch.from_numpy(img))
+        replay()
+        torch.cuda.synchronize()
+        got = {k: v.clone() for k, v in res.items() if v is not None}
+        ref = ctx.pipeline(ti, th, True, outputs="keypoints")
+        for k in ("keypoints_uv", "keypoint_coord3d", "center", "scale_crop"):
+            assert torch.equal(got[k], ref[k]), k
