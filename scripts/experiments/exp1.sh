@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."; mkdir -p gpurun_out; export PYTHONPATH=$PWD
+cd "$(dirname "$0")/../.."; mkdir -p gpurun_out; export PYTHONPATH=$PWD
 run() { name=$1; shift; env "$@" timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/exp_$name.json 2> gpurun_out/exp_$name.err; echo "$name rc=$?"; python - <<PY
 import json
 d=json.load(open("gpurun_out/exp_$name.json"))

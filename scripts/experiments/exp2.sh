@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."; mkdir -p gpurun_out; export PYTHONPATH=$PWD
+cd "$(dirname "$0")/../.."; mkdir -p gpurun_out; export PYTHONPATH=$PWD
 timeout 600 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke.log
 export H3D_TC_2CTA=1
 timeout 600 python -m pytest tests/test_gpu_tc_conv.py -q -m gpu --timeout 120 -x > gpurun_out/tc2.log 2>&1; echo "tc2 rc=$?"; tail -15 gpurun_out/tc2.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."; mkdir -p gpurun_out; export PYTHONPATH=$PWD
+cd "$(dirname "$0")/../.."; mkdir -p gpurun_out; export PYTHONPATH=$PWD
 timeout 600 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_properties.py -q -m gpu --timeout 600 -x > gpurun_out/pp.log 2>&1; echo "pipe+prop rc=$?"; tail -4 gpurun_out/pp.log
 run() { name=$1; shift; timeout 600 python bench.py --no-cpu-baseline "$@" > gpurun_out/exp_$name.json 2> gpurun_out/exp_$name.err; echo "$name rc=$?"; python - <<PY
 import json

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."; mkdir -p gpurun_out; export PYTHONPATH=$PWD
+cd "$(dirname "$0")/../.."; mkdir -p gpurun_out; export PYTHONPATH=$PWD
 timeout 600 python -m pytest tests/test_gpu_tc_conv.py -q -m gpu --timeout 120 -k "f8c or identity" > gpurun_out/tc_f8c.log 2>&1; echo "tc f8c rc=$?"; tail -30 gpurun_out/tc_f8c.log | cut -c1-200
 ERR_IMAGES=4 timeout 900 python scripts/debug_errors.py bf16x3 fp16x3 fp16_f8c > gpurun_out/errors_f8c.log 2>&1; echo "errors rc=$?"
 python - <<'PY'

@@ -1,6 +1,6 @@
 #!/bin/bash
 # first layer on tensor cores + 64->128 patch-reuse: tests, then A/B of the bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 timeout 900 python -m pytest tests/test_gpu_tc_conv.py tests/test_golden.py -q -m gpu --timeout 300 -x > gpurun_out/tc_c3.log 2>&1; echo "tc rc=$?"; tail -15 gpurun_out/tc_c3.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 timeout 900 python -m pytest tests/test_gpu_pipeline.py tests/test_golden.py -q -m gpu --timeout 600 -x -k "handsegnet or posenet_stage or golden" > gpurun_out/pipe_c3.log 2>&1; echo "pipe rc=$?"; tail -5 gpurun_out/pipe_c3.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 64 -> 64 channel specialisation: tests, then A/B of the bench (H3D_TC_C64=0 restores the generic kernel)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 timeout 900 python -m pytest tests/test_gpu_tc_conv.py -q -m gpu --timeout 300 -x > gpurun_out/tc_c64.log 2>&1; echo "tc rc=$?"; tail -15 gpurun_out/tc_c64.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 timeout 900 python -m pytest tests/test_gpu_pipeline.py tests/test_golden.py tests/test_gpu_tc_conv.py -q -m gpu --timeout 600 -x -k "lifting or pose_prior or golden or case0 or case1" > gpurun_out/pipe_fc.log 2>&1; echo "pipe rc=$?"; tail -4 gpurun_out/pipe_fc.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # lifting on tensor cores + side streams: tests, then A/B of the bench (H3D_LIFT_DIRECT / H3D_NO_SIDE_STREAM restore the old behaviour)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 timeout 600 python -m pytest tests/test_gpu_tc_conv.py -q -m gpu --timeout 300 -k "stride2 or padded or identity or case0-bf16x3" > gpurun_out/tc_s2.log 2>&1; echo "tc_s2 rc=$?"; tail -15 gpurun_out/tc_s2.log
