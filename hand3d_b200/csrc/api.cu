@@ -251,9 +251,9 @@ static void free_packed(PackedW& p) {
 }
 
 static int get_packed(h3d_ctx* ctx, const std::string& scope, const LayerSpec& l, int Cin_pad, const std::vector<int>& perm,
-                      const PackedW** out) {
+                      const PackedW** out, int force_passes = 0) {
     const Half16 t = half_of(ctx->precision);
-    const int passes = passes_of(ctx->precision);
+    const int passes = force_passes ? force_passes : passes_of(ctx->precision);
     const std::string key = scope + "/" + l.name + (t == Half16::FP16 ? "|h" : "|b") + std::to_string(passes);
     auto it = ctx->packed.find(key);
     if (it == ctx->packed.end()) {
@@ -383,14 +383,15 @@ static int add_direct(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, con
 
 static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec& l, int B, int H, int W, Split x,
                   int Cin_total, int Cin_pad, const std::vector<int>& perm, Split y, int Cy_total, int cy_off, float* yf,
-                  int Cyf_total, int cyf_off, int pool = 0) {
+                  int Cyf_total, int cyf_off, int pool = 0, int force_passes = 0) {
     const PackedW* pw;
-    int rc = get_packed(ctx, scope, l, Cin_pad, perm, &pw);
+    int rc = get_packed(ctx, scope, l, Cin_pad, perm, &pw, force_passes);
     if (rc) return rc;
     TcConvDesc d;
     d.x = x; d.Cin_total = Cin_total; d.Cin_pad = Cin_pad; d.w = pw->w; d.bias = pw->bias; d.Cout = l.cout; d.Cout_pad = pw->Cout_pad;
     d.y = y; d.Cy_total = Cy_total; d.cy_off = cy_off; d.yf = yf; d.Cyf_total = Cyf_total; d.cyf_off = cyf_off;
-    d.B = B; d.H = H; d.W = W; d.k = l.k; d.leaky = l.leaky; d.passes = passes_of(ctx->precision); d.half = half_of(ctx->precision);
+    d.B = B; d.H = H; d.W = W; d.k = l.k; d.leaky = l.leaky; d.passes = force_passes ? force_passes : passes_of(ctx->precision);
+    d.half = half_of(ctx->precision);
     d.corr_scale = pw->corr_scale;
     d.pool = pool;
     TcConvPlan* tp = tc_conv_plan_create(d);
@@ -593,9 +594,11 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
     auto pl = std::make_unique<StagePlan>();
     pl->B = B; pl->variant = variant;
     Arena a; a.base = ctx->ws + ctx->lay.lift_off;
-    const int passes = passes_of(ctx->precision);
+    // the lifting stage is 0.15 % of the FLOPs: on the tensor path it always runs 3-pass (hi / lo planes), also in the single-pass
+    // modes, whose error budget (1e-2) is spent on the trunks; the fp8-correction mode keeps the fp32 CUDA-core kernels
+    const int passes = 3;
     const Half16 half = half_of(ctx->precision);
-    const bool tc_lift = is_tc(ctx->precision) && passes == 3 && !getenv("H3D_LIFT_DIRECT");
+    const bool tc_lift = is_tc(ctx->precision) && passes_of(ctx->precision) != 4 && !getenv("H3D_LIFT_DIRECT");
     const int64_t slot_bytes = align_up((int64_t)B * 32 * 32 * 64 * 4, 1024);
     char* slot_in = a.alloc<char>(slot_bytes);
     struct Branch { char* slot[2]; float *xcat, *t1, *t2, *t3, *fcs, *cvs; } br[2];
@@ -643,7 +646,7 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
             Act out = slot_view(b.slot[i & 1], (int64_t)B * ho * wo * Cout_pad, Cout_pad, true, passes);
             float* yf = last ? (float*)b.slot[i & 1] : nullptr;
             int rc2 = add_tc(ctx, pl.get(), scope, l, B, h, w, in.s, in.C, Cin_pad, {}, last ? Split() : out.s, Cout_pad, 0, yf, l.cout, 0,
-                             l.stride == 2 ? 2 : 0);
+                             l.stride == 2 ? 2 : 0, passes);
             if (rc2) return rc2;
             if (last) *feat = yf;
             h = ho; w = wo; in = out;
@@ -668,7 +671,7 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
     auto fc_tc = [&](const std::string& scope, const char* name, int in_f, int out_f, int leaky, const Planes& x, const Planes* y, float* yf) -> int {
         LayerSpec l{name, 1, 1, in_f, out_f, leaky};
         return add_tc(ctx, pl.get(), scope, l, B, 1, 1, x.s, x.stride, (int)align_up(in_f, 64), {}, y ? y->s : Split(), y ? y->stride : 0, 0, yf,
-                      out_f, 0, 0);
+                      out_f, 0, 0, passes);
     };
     auto pose_prior = [&]() -> int {
         const Branch& b = br[0];
