@@ -1097,7 +1097,8 @@ int h3d_conv2d_tc_strided(h3d_ctx* ctx, const float* x, const float* host_w_hwio
                           int Cin, int Cout, int ksize, int stride, int leaky, int precision, void* stream) {
     H3D_OP_PROLOGUE(ctx);
     H3D_REQUIRE(precision >= H3D_PREC_BF16X3 && precision <= H3D_PREC_FP16_F8C, "h3d_conv2d_tc: precision must be a tensor-core mode");
-    H3D_REQUIRE(stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0), "h3d_conv2d_tc: stride must be 1, or 2 with even H and W");
+    H3D_REQUIRE(stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0 && ksize >= 3),
+                "h3d_conv2d_tc: stride must be 1, or 2 with even H and W and ksize >= 3 (for ksize 1 TF's 'SAME' samples the even pixels)");
     const Half16 half = half_of(precision);
     const int passes = passes_of(precision);
     const int Cin_pad = (int)align_up(Cin, 64), Cout_pad = (int)align_up(Cout, 64);

@@ -209,8 +209,8 @@ class Context:
         w = np.ascontiguousarray(w_host, np.float32); b = np.ascontiguousarray(b_host, np.float32)
         B, H, W, Cin = x.shape
         k, _, _, Cout = w.shape
-        if stride not in (1, 2) or (stride == 2 and (H % 2 or W % 2)):
-            raise ValueError("conv2d_tc: stride must be 1, or 2 with even H and W")
+        if stride not in (1, 2) or (stride == 2 and (H % 2 or W % 2 or k < 3)):
+            raise ValueError("conv2d_tc: stride must be 1, or 2 with even H and W and a kernel size >= 3")
         y = torch.empty((B, H // stride, W // stride, Cout), dtype=torch.float32, device=x.device)
         _lib.check(self.lib.h3d_conv2d_tc_strided(self.h, _ptr(x), w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), _ptr(y),
                                                   B, H, W, Cin, Cout, k, stride, int(leaky), PRECISIONS[precision], _stream()),

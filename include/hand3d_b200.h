@@ -126,7 +126,7 @@ H3D_API int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, co
  * ksize in {1,3,7}); host_w_hwio / host_bias are HOST pointers (packed per call: test / tuning entry). */
 H3D_API int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y,
                   int B, int H, int W, int Cin, int Cout, int ksize, int leaky, int precision, void* stream);
-/* Same with the `stride` argument of NetworkOps.conv (utils/general.py:36-53): 1, or 2 with even H and W (the lifting
+/* Same with the `stride` argument of NetworkOps.conv (utils/general.py:36-53): 1, or 2 with even H and W and ksize >= 3 (the lifting
  * pyramids, nets/ColorHandPose3DNetwork.py:255-258,291-294); y [B,H/stride,W/stride,Cout].  TF 'SAME' pads 0 before / 1 after
  * for stride 2 on an even size, i.e. the result is the stride-1 output at the odd pixels. */
 H3D_API int h3d_conv2d_tc_strided(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y,
