@@ -865,8 +865,8 @@ int h3d_destroy(h3d_ctx* ctx) {
     for (auto& kv : ctx->packed) free_packed(kv.second);
     if (ctx->vp_head_w) cudaFree(ctx->vp_head_w);
     if (ctx->vp_head_b) cudaFree(ctx->vp_head_b);
-    if (ctx->side) cudaStreamDestroy(ctx->side);
-    if (ctx->side2) cudaStreamDestroy(ctx->side2);
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }      // branches always join the caller's stream;
+    if (ctx->side2) { cudaStreamSynchronize(ctx->side2); cudaStreamDestroy(ctx->side2); }   // the syncs only matter after a failed call
     for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_fork2, ctx->ev_join2})
         if (e) cudaEventDestroy(e);
     delete ctx;
@@ -1047,15 +1047,20 @@ int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_sid
         H3D_CUDA(cudaStreamWaitEvent(ctx->side2, ctx->ev_fork2, 0));
         us = ctx->side2;
     }
+    int rc_up;
     if (keypoints_uv) {
         nl = 0;
-        if ((rc = launch_resize_argmax21(L.s[2], kps, B, 32, 32, 256, 256, L.argmax_scratch, keypoints_uv, us, &nl))) return rc;
+        rc_up = launch_resize_argmax21(L.s[2], kps, B, 32, 32, 256, 256, L.argmax_scratch, keypoints_uv, us, &nl);
         ctx->launches += nl;
     } else {
-        if ((rc = launch_resize_bilinear_tf1(L.s[2], kps, B, 32, 32, 21, 256, 256, us))) return rc;
+        rc_up = launch_resize_bilinear_tf1(L.s[2], kps, B, 32, 32, 21, 256, 256, us);
         ctx->launches += 1;
     }
     if (overlap) H3D_CUDA(cudaEventRecord(ctx->ev_join2, ctx->side2));
+    if (rc_up) {   // never leave the side stream un-joined
+        if (overlap) cudaStreamWaitEvent(s, ctx->ev_join2, 0);
+        return rc_up;
+    }
     // PosePrior + ViewpointNet on the 32x32 map (nets/...:93)
     if (with_pose3d)
         rc = h3d_lifting_forward(ctx, L.s[2], hand_side, B, H3D_VARIANT_PROPOSED, keypoint_coord3d, nullptr, nullptr, stream);
