@@ -27,6 +27,8 @@ SIGNATURES = {
     "h3d_destroy": (_i, [_p]),
     "h3d_set_precision": (_i, [_p, _i]),
     "h3d_get_precision": (_i, [_p]),
+    "h3d_set_tuning": (_i, [_p, C.c_char_p, _i]),
+    "h3d_check_errors": (_i, [_p, C.POINTER(_i)]),
     "h3d_launch_count": (_i64, [_p]),
     "h3d_profile_begin": (_i, [_p]),
     "h3d_profile_end": (_i, [_p, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64)]),
@@ -38,21 +40,29 @@ SIGNATURES = {
     "h3d_posenet_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "h3d_lifting_forward": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "h3d_pipeline_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "h3d_pose2d_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "h3d_conv2d_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "h3d_conv2d_tc": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "h3d_conv2d_tc_strided": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "h3d_pack_conv_weights": (_i, [_p, _p, _p, _i, _i, _i, _i, C.POINTER(_p)]),
+    "h3d_free_packed_conv": (_i, [_p, _p]),
+    "h3d_conv2d_tc_packed": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "h3d_leaky_relu_f32": (_i, [_p, _p, _p, _i64, _p]),
     "h3d_maxpool2x2_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "h3d_fully_connected_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "h3d_resize_bilinear_tf1": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "h3d_avgpool8": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "h3d_seg_postprocess": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "h3d_calc_center_bb": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "h3d_crop_image_from_xy": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "h3d_detect_keypoints": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
-    "h3d_gather_records_p2p": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, C.c_uint64, _i, _i, C.c_uint32, _i64, _p]),
+    "h3d_pack_records": (_i, [_p, _p, _p, _p, _p, _i, _p, _p]),
+    "h3d_gather_records_p2p": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, C.c_uint64, _i, _i, C.c_uint32, _i64, _p]),
     "h3d_decode_records": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "h3d_eval_keypoint_dist": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "h3d_bone_rel_trafo_inv": (_i, [_p, _p, _p, _i, _p]),
     "h3d_rotate_canonical": (_i, [_p, _p, _p, _p, _i, _p, _p, _p]),
+    "h3d_flip_right_hand": (_i, [_p, _p, _p, _i, _p, _p]),
 }
 
 _lib = None

@@ -157,6 +157,14 @@ struct h3d_ctx {
     // and join back into the caller's stream with events (capturable into a CUDA graph)
     cudaStream_t side = nullptr, side2 = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    // Device-visible error word in pinned host memory: a bounded barrier wait that times out stores its code here (system-scope
+    // atomic) before trapping, and the gather kernel stores 100 + peer when a peer never signals.  Readable by the host even
+    // after the trap has poisoned the CUDA context (h3d_check_errors).
+    int* err_flag = nullptr;
+    // Operator entry points borrow scratch from here instead of allocating per call: grown geometrically on demand, old blocks
+    // are retired (not freed) until h3d_destroy, so no call ever synchronises or frees.
+    char* op_scratch = nullptr; int64_t op_scratch_bytes = 0;
+    std::vector<void*> retired;
     // optional per-kernel-class timing (CUDA events on the launch stream around every plan step)
     bool profiling = false;
     struct ProfRec { cudaEvent_t a, b; int kind; int64_t flops; };
@@ -248,6 +256,28 @@ static void free_packed(PackedW& p) {
     if (p.w.h8) cudaFree(p.w.h8);
     if (p.bias) cudaFree(p.bias);
     p = PackedW();
+}
+
+// RAII: make ctx's device current for the duration of an entry point and restore the caller's device afterwards (one process may
+// hold contexts on several GPUs; torch keeps its own notion of the current device).
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+static int op_scratch(h3d_ctx* ctx, int64_t bytes, char** out) {
+    if (ctx->op_scratch_bytes < bytes) {
+        const int64_t want = std::max<int64_t>(align_up(bytes, 1 << 20), 2 * ctx->op_scratch_bytes);
+        char* p = nullptr;
+        H3D_CUDA(cudaMalloc(&p, (size_t)want));
+        if (ctx->op_scratch) ctx->retired.push_back(ctx->op_scratch);   // in-flight kernels may still use it
+        ctx->op_scratch = p; ctx->op_scratch_bytes = want;
+    }
+    *out = ctx->op_scratch;
+    return H3D_OK;
 }
 
 static int get_packed(h3d_ctx* ctx, const std::string& scope, const LayerSpec& l, int Cin_pad, const std::vector<int>& perm,
@@ -369,6 +399,7 @@ static int add_direct(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, con
     a.ys = ys; a.Cs_total = Cs_total; a.cs_off = cs_off; a.half = half_of(ctx->precision);
     a.B = B; a.H = H; a.W = W; a.Cin = l.cin; a.Cout = l.cout; a.k = l.k; a.stride = l.stride; a.leaky = l.leaky;
     a.splitk_scratch = splitk_scratch; a.splitk_scratch_floats = splitk_scratch ? kConvSplitKScratchFloats : 0;
+    a.err_flag = ctx->err_flag;
     pl->steps.push_back([a](const Ext& e, cudaStream_t s) {
         DirectConvArgs aa = a;
         if (!aa.x) aa.x = e.in;
@@ -394,6 +425,7 @@ static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const L
     d.half = half_of(ctx->precision);
     d.corr_scale = pw->corr_scale;
     d.pool = pool;
+    d.err_flag = ctx->err_flag;
     TcConvPlan* tp = tc_conv_plan_create(d);
     if (!tp) return H3D_ECUDA;
     pl->tc.push_back(tp);
@@ -424,7 +456,7 @@ static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, co
         const bool use_tc = tc && l.cin % 64 == 0 && l.cout % 64 == 0 && l.stride == 1;
         const int c_off = last_layer ? final_c_off : 0;
         const bool pool_after = !strcmp(l.name, "conv1_2") || !strcmp(l.name, "conv2_2") || !strcmp(l.name, "conv3_4");
-        const bool fuse_pool = use_tc && pool_after && (h % 2 == 0) && (w % 2 == 0) && !getenv("H3D_NO_POOL_FUSION");
+        const bool fuse_pool = use_tc && pool_after && (h % 2 == 0) && (w % 2 == 0) && !tc_tuning().no_pool_fusion;
         if (use_tc) {
             rc = add_tc(ctx, pl, scope, l, B, h, w, in.s, in.C, l.cin, {}, out.s, out.C, c_off, nullptr, 0, 0, fuse_pool ? 1 : 0);
         } else if (tc) {   // first layer (Cin = 3): CUDA-core conv writing the split planes directly
@@ -598,7 +630,7 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
     // modes, whose error budget (1e-2) is spent on the trunks; the fp8-correction mode keeps the fp32 CUDA-core kernels
     const int passes = 3;
     const Half16 half = half_of(ctx->precision);
-    const bool tc_lift = is_tc(ctx->precision) && passes_of(ctx->precision) != 4 && !getenv("H3D_LIFT_DIRECT");
+    const bool tc_lift = is_tc(ctx->precision) && passes_of(ctx->precision) != 4 && !tc_tuning().lift_direct;
     const int64_t slot_bytes = align_up((int64_t)B * 32 * 32 * 64 * 4, 1024);
     char* slot_in = a.alloc<char>(slot_bytes);
     struct Branch { char* slot[2]; float *xcat, *t1, *t2, *t3, *fcs, *cvs; } br[2];
@@ -776,7 +808,7 @@ static int run_plan(h3d_ctx* ctx, StagePlan* pl, const Ext& e, cudaStream_t s) {
         forked = false;
         return H3D_OK;
     };
-    const bool lanes = !getenv("H3D_NO_SIDE_STREAM");
+    const bool lanes = !tc_tuning().no_side_stream;
     for (size_t i = 0; i < pl->steps.size(); ++i) {
         int rc;
         const int ln = (lanes && i < pl->lane.size()) ? pl->lane[i] : 0;
@@ -854,12 +886,32 @@ int h3d_create(h3d_ctx** out, int device) {
         h3d_destroy(c);
         return H3D_ECUDA;
     }
+    if (cudaHostAlloc((void**)&c->err_flag, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        set_error("h3d_create: cannot allocate the error word (%s)", cudaGetErrorString(cudaGetLastError()));
+        h3d_destroy(c);
+        return H3D_ECUDA;
+    }
+    *c->err_flag = 0;
+    tc_tuning();   // read the H3D_* environment switches now, never on a launch path
     *out = c;
     return H3D_OK;
 }
 
+int h3d_check_errors(h3d_ctx* ctx, int* code) {
+    H3D_REQUIRE(ctx != nullptr, "h3d_check_errors: ctx is NULL");
+    const int c = ctx->err_flag ? *(volatile int*)ctx->err_flag : 0;
+    if (code) *code = c;
+    if (c == 0) return H3D_OK;
+    static const char* what[] = {"", "TMA producer waiting for a free shared-memory stage", "MMA issuer waiting for a drained TMEM accumulator",
+                                 "MMA issuer waiting for a TMA stage", "epilogue waiting for a finished accumulator", "MMA issuer waiting for the resident weights"};
+    if (c >= 100) set_error("device-side timeout: gather_records_p2p never saw the records of peer rank %d (code %d)", c - 100, c);
+    else set_error("device-side timeout in a tcgen05 convolution kernel: %s (code %d); the kernel trapped", c >= 1 && c <= 5 ? what[c] : "unknown wait", c);
+    return H3D_ECUDA;
+}
+
 int h3d_destroy(h3d_ctx* ctx) {
     if (!ctx) return H3D_OK;
+    DeviceGuard guard(ctx->device);
     ctx->drop_plans();
     for (auto& kv : ctx->dev_w) cudaFree(kv.second);
     for (auto& kv : ctx->packed) free_packed(kv.second);
@@ -869,6 +921,9 @@ int h3d_destroy(h3d_ctx* ctx) {
     if (ctx->side2) { cudaStreamSynchronize(ctx->side2); cudaStreamDestroy(ctx->side2); }   // the syncs only matter after a failed call
     for (cudaEvent_t e : {ctx->ev_fork, ctx->ev_join, ctx->ev_fork2, ctx->ev_join2})
         if (e) cudaEventDestroy(e);
+    if (ctx->op_scratch) cudaFree(ctx->op_scratch);
+    for (void* p : ctx->retired) cudaFree(p);
+    if (ctx->err_flag) cudaFreeHost(ctx->err_flag);
     delete ctx;
     return H3D_OK;
 }
@@ -879,6 +934,12 @@ int h3d_set_precision(h3d_ctx* ctx, int precision) {
     return H3D_OK;
 }
 int h3d_get_precision(const h3d_ctx* ctx) { return ctx ? ctx->precision : H3D_EINVAL; }
+int h3d_set_tuning(h3d_ctx* ctx, const char* key, int value) {
+    H3D_REQUIRE(key != nullptr, "h3d_set_tuning: key is NULL");
+    int rc = tc_set_tuning(key, value);
+    if (!rc && ctx) ctx->drop_plans();   // plans bake the kernel choice in
+    return rc;
+}
 int64_t h3d_launch_count(const h3d_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int h3d_profile_begin(h3d_ctx* ctx) {
@@ -974,6 +1035,7 @@ int h3d_set_workspace(h3d_ctx* ctx, void* dev_ptr, int64_t bytes) {
 }
 
 int h3d_handsegnet_forward(h3d_ctx* ctx, const float* image, int B, int H, int W, float* logits, void* stream) {
+    DeviceGuard guard_(ctx ? ctx->device : 0);
     H3D_REQUIRE(ctx && image && logits && B > 0, "h3d_handsegnet_forward: bad argument");
     int rc;
     if ((rc = ensure_layout_covers(ctx, B, H, W, 0, 0))) return rc;
@@ -984,6 +1046,7 @@ int h3d_handsegnet_forward(h3d_ctx* ctx, const float* image, int B, int H, int W
 }
 
 int h3d_posenet_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, int Wc, float* s0, float* s1, float* s2, void* stream) {
+    DeviceGuard guard_(ctx ? ctx->device : 0);
     H3D_REQUIRE(ctx && image_crop && B > 0, "h3d_posenet_forward: bad argument");
     int rc;
     if ((rc = ensure_layout_covers(ctx, B, 0, 0, Hc, Wc))) return rc;
@@ -998,8 +1061,26 @@ int h3d_posenet_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, in
     return H3D_OK;
 }
 
+int h3d_pose2d_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, int Wc, float* keypoints_scoremap, int32_t* keypoints_uv,
+                       void* stream) {
+    H3D_REQUIRE(ctx && image_crop && B > 0, "h3d_pose2d_forward: bad argument");
+    H3D_REQUIRE(keypoints_scoremap || (Hc <= 256 && Wc <= 256), "h3d_pose2d_forward: keypoints_scoremap is required for crops larger than 256x256");
+    DeviceGuard guard_(ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = h3d_posenet_forward(ctx, image_crop, B, Hc, Wc, nullptr, nullptr, nullptr, stream))) return rc;
+    h3d_ctx::Layout& L = ctx->lay;
+    float* kps = keypoints_scoremap ? keypoints_scoremap : L.kp_scoremap;
+    int nl = 0;
+    if (keypoints_uv) rc = launch_resize_argmax21(L.s[2], kps, B, Hc / 8, Wc / 8, Hc, Wc, L.argmax_scratch, keypoints_uv, s, &nl);
+    else { rc = launch_resize_bilinear_tf1(L.s[2], kps, B, Hc / 8, Wc / 8, 21, Hc, Wc, s); nl = 1; }
+    ctx->launches += nl;
+    return rc;
+}
+
 int h3d_lifting_forward(h3d_ctx* ctx, const float* scoremap32, const float* hand_side, int B, int variant,
                         float* coord_xyz_rel_normed, float* coord_can, float* rot_mat, void* stream) {
+    DeviceGuard guard_(ctx ? ctx->device : 0);
     H3D_REQUIRE(ctx && scoremap32 && hand_side && coord_xyz_rel_normed && B > 0, "h3d_lifting_forward: bad argument");
     H3D_REQUIRE(variant >= H3D_VARIANT_DIRECT && variant <= H3D_VARIANT_LOCAL, "h3d_lifting_forward: unknown variant");
     int rc;
@@ -1014,6 +1095,7 @@ int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_sid
                          const float* force_center, const float* force_scale, float* hand_scoremap, float* image_crop,
                          float* scale_crop, float* center, float* keypoints_scoremap, float* keypoint_coord3d,
                          int32_t* keypoints_uv, uint8_t* hand_mask, void* stream) {
+    DeviceGuard guard_(ctx ? ctx->device : 0);
     H3D_REQUIRE(ctx && image && B > 0, "h3d_pipeline_forward: bad argument");
     H3D_REQUIRE(!with_pose3d || (hand_side && keypoint_coord3d), "h3d_pipeline_forward: hand_side / keypoint_coord3d required with pose3d");
     cudaStream_t s = (cudaStream_t)stream;
@@ -1040,7 +1122,7 @@ int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_sid
     if ((rc = h3d_posenet_forward(ctx, crop, B, 256, 256, nullptr, nullptr, nullptr, stream))) return rc;
     // x8 up-sampling (nets/...:96-97) and detect_keypoints (utils/general.py:331-344), fused when both are requested; it only
     // reads the 32x32 score map, so it runs on a side stream concurrently with the lifting stage
-    const bool overlap = with_pose3d && !getenv("H3D_NO_SIDE_STREAM");
+    const bool overlap = with_pose3d && !tc_tuning().no_side_stream;
     cudaStream_t us = s;
     if (overlap) {
         H3D_CUDA(cudaEventRecord(ctx->ev_fork2, s));
@@ -1070,9 +1152,15 @@ int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_sid
 }
 
 // ---------------------------------------------------------------------------------------------- operators
+// Every operator entry ENQUEUES only: scratch comes from the context (op_scratch), never from a per-call cudaMalloc, and nothing
+// synchronises.  The one documented exception is h3d_conv2d_tc(_strided), which takes HOST weights and therefore packs, uploads and
+// frees them around the call (test / tuning entry); its enqueue-only form is h3d_pack_conv_weights + h3d_conv2d_tc_packed.
 #define H3D_OP_PROLOGUE(ctx)                              \
     H3D_REQUIRE((ctx) != nullptr, "ctx is NULL");         \
+    DeviceGuard guard_((ctx)->device);                    \
     cudaStream_t s = (cudaStream_t)stream;
+
+struct h3d_packed_conv { PackedW pw; int k = 0, Cin = 0, Cout = 0, precision = 0; };
 
 int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const float* bias, float* y, int B, int H, int W, int Cin,
                    int Cout, int ksize, int stride, int leaky, void* stream) {
@@ -1081,16 +1169,82 @@ int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const floa
     a.x = x; a.Cin_total = Cin; a.cin_off = 0; a.w = w_hwio; a.bias = bias; a.y = y; a.Cout_total = Cout; a.cout_off = 0;
     a.ys = Split(); a.Cs_total = 0; a.cs_off = 0; a.half = Half16::BF16;
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.k = ksize; a.stride = stride; a.leaky = leaky;
-    float* scratch = nullptr;   // lets tiny layers take the split-K path exactly as the lifting stage does
+    a.err_flag = ctx->err_flag;
+    // lets tiny layers take the split-K path exactly as the lifting stage does
     const bool tiny = (int64_t)B * ceil_div(H, stride) * ceil_div(W, stride) <= 64 * 295;
     if (tiny) {
-        H3D_CUDA(cudaMalloc(&scratch, (size_t)kConvSplitKScratchFloats * 4));
-        a.splitk_scratch = scratch; a.splitk_scratch_floats = kConvSplitKScratchFloats;
+        char* scratch = nullptr;
+        int rc0 = op_scratch(ctx, kConvSplitKScratchFloats * 4, &scratch);
+        if (rc0) return rc0;
+        a.splitk_scratch = (float*)scratch; a.splitk_scratch_floats = kConvSplitKScratchFloats;
     }
     int rc = launch_conv_direct(a, s);
-    if (!rc) ctx->launches += 1;
-    if (tiny) { cudaStreamSynchronize(s); cudaFree(scratch); }
+    if (!rc) ctx->launches += conv_direct_num_launches(a);
     return rc;
+}
+
+int h3d_pack_conv_weights(h3d_ctx* ctx, const float* host_w_hwio, const float* host_bias, int ksize, int Cin, int Cout, int precision,
+                          h3d_packed_conv** out) {
+    H3D_REQUIRE(ctx && host_w_hwio && host_bias && out, "h3d_pack_conv_weights: NULL argument");
+    H3D_REQUIRE(precision >= H3D_PREC_BF16X3 && precision <= H3D_PREC_FP16_F8C, "h3d_pack_conv_weights: precision must be a tensor-core mode");
+    H3D_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "h3d_pack_conv_weights: ksize must be 1, 3, 5 or 7");
+    DeviceGuard guard(ctx->device);
+    auto* h = new h3d_packed_conv();
+    h->k = ksize; h->Cin = Cin; h->Cout = Cout; h->precision = precision;
+    int rc = pack_conv_weights(host_w_hwio, host_bias, ksize, Cin, Cout, (int)align_up(Cin, 64), (int)align_up(Cout, 64), {}, half_of(precision),
+                               passes_of(precision), &h->pw);
+    if (rc) { free_packed(h->pw); delete h; return rc; }
+    *out = h;
+    return H3D_OK;
+}
+
+int h3d_free_packed_conv(h3d_ctx* ctx, h3d_packed_conv* packed) {
+    if (!packed) return H3D_OK;
+    H3D_REQUIRE(ctx != nullptr, "h3d_free_packed_conv: ctx is NULL");
+    DeviceGuard guard(ctx->device);
+    free_packed(packed->pw);     // cudaFree waits for kernels that still read the planes
+    delete packed;
+    return H3D_OK;
+}
+
+int h3d_conv2d_tc_packed(h3d_ctx* ctx, const float* x, const h3d_packed_conv* packed, float* y, int B, int H, int W, int stride,
+                         int leaky, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(x && packed && y && B > 0, "h3d_conv2d_tc_packed: bad argument");
+    const int ksize = packed->k, Cin = packed->Cin, Cout = packed->Cout, precision = packed->precision;
+    H3D_REQUIRE(stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0 && ksize >= 3),
+                "h3d_conv2d_tc: stride must be 1, or 2 with even H and W and ksize >= 3 (for ksize 1 TF's 'SAME' samples the even pixels)");
+    const Half16 half = half_of(precision);
+    const int passes = passes_of(precision);
+    const int Cin_pad = packed->pw.Cin_pad, Cout_pad = packed->pw.Cout_pad;
+    const int64_t rows = (int64_t)B * H * W, rows_out = rows / (stride * stride);
+    // operand planes carved from the context's operator scratch: [x hi | x lo / l8 h8 | y hi | y lo / l8 h8]
+    const int64_t xb = align_up(rows * Cin_pad * 2, 1024), yb = align_up(rows_out * Cout_pad * 2, 1024);
+    char* base = nullptr;
+    int rc = op_scratch(ctx, 2 * xb + 2 * yb, &base);
+    if (rc) return rc;
+    Split xs, ys;
+    xs.hi = (uint16_t*)base; ys.hi = (uint16_t*)(base + 2 * xb);
+    if (passes == 3) { xs.lo = (uint16_t*)(base + xb); ys.lo = (uint16_t*)(base + 2 * xb + yb); }
+    if (passes == 4) {
+        xs.l8 = (uint8_t*)(base + xb); xs.h8 = xs.l8 + align_up(rows * Cin_pad, 1024);
+        ys.l8 = (uint8_t*)(base + 2 * xb + yb); ys.h8 = ys.l8 + align_up(rows_out * Cout_pad, 1024);
+    }
+    if ((rc = launch_f32_to_split(x, xs, rows, Cin, Cin_pad, half, s))) return rc;
+    TcConvDesc d;
+    d.x = xs; d.Cin_total = Cin_pad; d.Cin_pad = Cin_pad; d.w = packed->pw.w; d.bias = packed->pw.bias; d.Cout = Cout; d.Cout_pad = Cout_pad;
+    d.y = ys; d.Cy_total = Cout_pad; d.cy_off = 0; d.yf = nullptr; d.Cyf_total = 0; d.cyf_off = 0;
+    d.B = B; d.H = H; d.W = W; d.k = ksize; d.leaky = leaky; d.passes = passes; d.half = half; d.corr_scale = packed->pw.corr_scale;
+    d.pool = stride == 2 ? 2 : 0;
+    d.err_flag = ctx->err_flag;
+    TcConvPlan* tp = tc_conv_plan_create(d);     // host-side only: tensor maps + launch geometry (passed to the kernel by value)
+    if (!tp) return H3D_ECUDA;
+    rc = tc_conv_launch(tp, s);
+    tc_conv_plan_destroy(tp);
+    if (rc) return rc;
+    if ((rc = launch_split_to_f32(ys, y, rows_out, Cout, Cout_pad, half, s))) return rc;
+    ctx->launches += 3;
+    return H3D_OK;
 }
 
 int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y, int B, int H, int W,
@@ -1100,47 +1254,13 @@ int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const 
 
 int h3d_conv2d_tc_strided(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y, int B, int H, int W,
                           int Cin, int Cout, int ksize, int stride, int leaky, int precision, void* stream) {
-    H3D_OP_PROLOGUE(ctx);
-    H3D_REQUIRE(precision >= H3D_PREC_BF16X3 && precision <= H3D_PREC_FP16_F8C, "h3d_conv2d_tc: precision must be a tensor-core mode");
-    H3D_REQUIRE(stride == 1 || (stride == 2 && H % 2 == 0 && W % 2 == 0 && ksize >= 3),
-                "h3d_conv2d_tc: stride must be 1, or 2 with even H and W and ksize >= 3 (for ksize 1 TF's 'SAME' samples the even pixels)");
-    const Half16 half = half_of(precision);
-    const int passes = passes_of(precision);
-    const int Cin_pad = (int)align_up(Cin, 64), Cout_pad = (int)align_up(Cout, 64);
-    PackedW pw;
-    int rc = pack_conv_weights(host_w_hwio, host_bias, ksize, Cin, Cout, Cin_pad, Cout_pad, {}, half, passes, &pw);
+    H3D_REQUIRE(ctx != nullptr, "ctx is NULL");
+    h3d_packed_conv* pk = nullptr;
+    int rc = h3d_pack_conv_weights(ctx, host_w_hwio, host_bias, ksize, Cin, Cout, precision, &pk);
     if (rc) return rc;
-    const int64_t rows = (int64_t)B * H * W, rows_out = rows / (stride * stride);
-    Split xs, ys;
-    TcConvPlan* tp = nullptr;
-    auto cleanup = [&]() {
-        if (xs.hi) cudaFree(xs.hi); if (xs.lo) cudaFree(xs.lo); if (ys.hi) cudaFree(ys.hi); if (ys.lo) cudaFree(ys.lo);
-        if (xs.l8) cudaFree(xs.l8); if (xs.h8) cudaFree(xs.h8); if (ys.l8) cudaFree(ys.l8); if (ys.h8) cudaFree(ys.h8);
-        if (tp) tc_conv_plan_destroy(tp);
-        free_packed(pw);
-    };
-    auto fail = [&](int code) { cleanup(); return code; };
-    if (cudaMalloc(&xs.hi, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.hi, rows_out * Cout_pad * 2) != cudaSuccess ||
-        (passes == 3 && (cudaMalloc(&xs.lo, rows * Cin_pad * 2) != cudaSuccess || cudaMalloc(&ys.lo, rows_out * Cout_pad * 2) != cudaSuccess)) ||
-        (passes == 4 && (cudaMalloc(&xs.l8, rows * Cin_pad) != cudaSuccess || cudaMalloc(&xs.h8, rows * Cin_pad) != cudaSuccess ||
-                         cudaMalloc(&ys.l8, rows_out * Cout_pad) != cudaSuccess || cudaMalloc(&ys.h8, rows_out * Cout_pad) != cudaSuccess))) {
-        set_error("h3d_conv2d_tc: out of device memory");
-        return fail(H3D_ECUDA);
-    }
-    if ((rc = launch_f32_to_split(x, xs, rows, Cin, Cin_pad, half, s))) return fail(rc);
-    TcConvDesc d;
-    d.x = xs; d.Cin_total = Cin_pad; d.Cin_pad = Cin_pad; d.w = pw.w; d.bias = pw.bias; d.Cout = Cout; d.Cout_pad = Cout_pad;
-    d.y = ys; d.Cy_total = Cout_pad; d.cy_off = 0; d.yf = nullptr; d.Cyf_total = 0; d.cyf_off = 0;
-    d.B = B; d.H = H; d.W = W; d.k = ksize; d.leaky = leaky; d.passes = passes; d.half = half; d.corr_scale = pw.corr_scale; d.pool = stride == 2 ? 2 : 0;
-    tp = tc_conv_plan_create(d);
-    if (!tp) return fail(H3D_ECUDA);
-    if ((rc = tc_conv_launch(tp, s))) return fail(rc);
-    if ((rc = launch_split_to_f32(ys, y, rows_out, Cout, Cout_pad, half, s))) return fail(rc);
-    ctx->launches += 3;
-    cudaError_t e = cudaStreamSynchronize(s);
-    cleanup();
-    if (e != cudaSuccess) return cuda_fail(e, "h3d_conv2d_tc sync", __FILE__, __LINE__);
-    return H3D_OK;
+    rc = h3d_conv2d_tc_packed(ctx, x, pk, y, B, H, W, stride, leaky, stream);
+    h3d_free_packed_conv(ctx, pk);               // host-weight convenience entry: the free waits for the kernel (documented exception)
+    return rc;
 }
 
 int h3d_maxpool2x2_f32(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, void* stream) {
@@ -1152,12 +1272,18 @@ int h3d_maxpool2x2_f32(h3d_ctx* ctx, const float* x, float* y, int B, int H, int
 int h3d_fully_connected_f32(h3d_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int in_features,
                             int out_features, int leaky, void* stream) {
     H3D_OP_PROLOGUE(ctx);
-    float* scratch = nullptr;
-    H3D_CUDA(cudaMalloc(&scratch, (size_t)fc_scratch_floats(B, in_features, out_features) * 4));
-    int rc = launch_fc(x, w, bias, y, scratch, B, in_features, out_features, leaky, in_features, s);
+    char* scratch = nullptr;
+    int rc = op_scratch(ctx, fc_scratch_floats(B, in_features, out_features) * 4, &scratch);
+    if (rc) return rc;
+    rc = launch_fc(x, w, bias, y, (float*)scratch, B, in_features, out_features, leaky, in_features, s);
     if (!rc) ctx->launches += 2;
-    cudaStreamSynchronize(s);
-    cudaFree(scratch);
+    return rc;
+}
+int h3d_leaky_relu_f32(h3d_ctx* ctx, const float* x, float* y, int64_t n, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(x && y && n > 0, "h3d_leaky_relu_f32: bad argument");
+    int rc = launch_leaky_relu(x, y, n, s);
+    if (!rc) ctx->launches += 1;
     return rc;
 }
 int h3d_resize_bilinear_tf1(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, int out_h, int out_w, void* stream) {
@@ -1176,13 +1302,19 @@ int h3d_seg_postprocess(h3d_ctx* ctx, const float* logits, int B, int H, int W, 
                         float* crop_size, float* scale_crop, void* stream) {
     H3D_OP_PROLOGUE(ctx);
     H3D_REQUIRE(logits && center && scale_crop, "h3d_seg_postprocess: logits, center and scale_crop are required");
-    void* scratch = nullptr;
-    H3D_CUDA(cudaMalloc(&scratch, seg_scratch_bytes(B, H, W)));
+    char* scratch = nullptr;
+    int rc = op_scratch(ctx, seg_scratch_bytes(B, H, W), &scratch);
+    if (rc) return rc;
     int nl = 0;
-    int rc = launch_seg_postprocess(logits, B, H, W, scratch, hand_mask, max_loc, center, crop_size, scale_crop, s, &nl);
+    rc = launch_seg_postprocess(logits, B, H, W, scratch, hand_mask, max_loc, center, crop_size, scale_crop, s, &nl);
     ctx->launches += nl;
-    cudaStreamSynchronize(s);
-    cudaFree(scratch);
+    return rc;
+}
+int h3d_calc_center_bb(h3d_ctx* ctx, const float* mask, int B, int H, int W, float* center, float* bb, float* crop_size, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(mask && center && B > 0 && H > 0 && W > 0, "h3d_calc_center_bb: bad argument");
+    int rc = launch_mask_bbox(mask, B, H, W, center, bb, crop_size, s);
+    if (!rc) ctx->launches += 1;
     return rc;
 }
 int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float* center, const float* scale, float* image_crop, int B,
@@ -1194,23 +1326,30 @@ int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float* center
 }
 int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int C, int32_t* keypoints_uv, void* stream) {
     H3D_OP_PROLOGUE(ctx);
-    void* scratch = nullptr;
-    H3D_CUDA(cudaMalloc(&scratch, argmax_scratch_bytes(B, C)));
+    char* scratch = nullptr;
+    int rc = op_scratch(ctx, argmax_scratch_bytes(B, C), &scratch);
+    if (rc) return rc;
     int nl = 0;
-    int rc = launch_detect_keypoints(scoremaps, B, H, W, C, scratch, keypoints_uv, s, &nl);
+    rc = launch_detect_keypoints(scoremaps, B, H, W, C, scratch, keypoints_uv, s, &nl);
     ctx->launches += nl;
-    cudaStreamSynchronize(s);
-    cudaFree(scratch);
+    return rc;
+}
+int h3d_pack_records(h3d_ctx* ctx, const float* coord3d, const int32_t* keypoints_uv, const float* center, const float* scale_crop, int B,
+                     float* records, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(coord3d && keypoints_uv && center && scale_crop && records && B > 0, "h3d_pack_records: bad argument");
+    int rc = launch_pack_records(coord3d, keypoints_uv, center, scale_crop, B, records, s);
+    if (!rc) ctx->launches += 1;
     return rc;
 }
 int h3d_gather_records_p2p(h3d_ctx* ctx, const float* coord3d, const int32_t* keypoints_uv, const float* center, const float* scale_crop,
-                           int B, const uint64_t* peer_buffers, const uint64_t* peer_signals, uint64_t multicast_ptr, int rank, int world,
-                           uint32_t epoch, int64_t parity_stride_floats, void* stream) {
+                           int B, int max_batch, const uint64_t* peer_buffers, const uint64_t* peer_signals, uint64_t multicast_ptr, int rank,
+                           int world, uint32_t epoch, int64_t parity_stride_floats, void* stream) {
     H3D_OP_PROLOGUE(ctx);
     H3D_REQUIRE(coord3d && keypoints_uv && center && scale_crop && peer_buffers && peer_signals, "h3d_gather_records_p2p: NULL argument");
-    H3D_REQUIRE(parity_stride_floats >= (int64_t)world * B * 108, "h3d_gather_records_p2p: parity stride too small");
+    H3D_REQUIRE(max_batch >= B && parity_stride_floats >= (int64_t)world * max_batch * 108, "h3d_gather_records_p2p: parity stride too small");
     int rc = launch_gather_records_p2p(coord3d, keypoints_uv, center, scale_crop, B, peer_buffers, peer_signals, multicast_ptr, rank,
-                                       world, epoch, parity_stride_floats, s);
+                                       world, epoch, parity_stride_floats, max_batch, ctx->err_flag, s);
     if (!rc) ctx->launches += 1;
     return rc;
 }
@@ -1250,6 +1389,13 @@ int h3d_rotate_canonical(h3d_ctx* ctx, const float* coord_can, const float* uxyz
                          float* coord_out, void* stream) {
     H3D_OP_PROLOGUE(ctx);
     int rc = launch_rotate_canonical(coord_can, uxyz, hand_side, B, rot_mat, coord_out, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_flip_right_hand(h3d_ctx* ctx, const float* coords_xyz, const uint8_t* cond_right, int B, float* out, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(coords_xyz && cond_right && out && B > 0, "h3d_flip_right_hand: bad argument");
+    int rc = launch_flip_right_hand(coords_xyz, cond_right, B, out, s);
     if (!rc) ctx->launches += 1;
     return rc;
 }

@@ -83,7 +83,11 @@ int launch_decode_records(const uint8_t* rec, int64_t record_bytes, int header_f
 int launch_eval_dist(const float* gt, const uint8_t* vis, const float* pred, int n, int D, float* dist, cudaStream_t s);
 int launch_gather_records_p2p(const float* coord3d, const int32_t* uv, const float* center, const float* scale, int B,
                               const uint64_t* peer_buffers, const uint64_t* peer_signals, uint64_t multicast_ptr, int rank, int world,
-                              uint32_t epoch, int64_t parity_stride_floats, cudaStream_t s);
+                              uint32_t epoch, int64_t parity_stride_floats, int max_batch, int* err_flag, cudaStream_t s);
+int launch_pack_records(const float* coord3d, const int32_t* uv, const float* center, const float* scale, int B, float* out, cudaStream_t s);
+int launch_mask_bbox(const float* mask, int B, int H, int W, float* center, float* bb, float* crop_size, cudaStream_t s);
+int launch_leaky_relu(const float* x, float* y, int64_t n, cudaStream_t s);
+int launch_flip_right_hand(const float* xyz, const uint8_t* cond_right, int B, float* out, cudaStream_t s);
 int launch_bone_rel_trafo_inv(const float* rel, float* xyz, int B, cudaStream_t s);
 int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot,
                             float* out, cudaStream_t s);
@@ -102,6 +106,7 @@ struct DirectConvArgs {
     int B, H, W, Cin, Cout, k, stride, leaky;
     float* splitk_scratch = nullptr;        // optional: enables deterministic split-K for layers with too few tiles
     int64_t splitk_scratch_floats = 0;
+    int* err_flag = nullptr;                // forwarded to the tensor-core first-layer kernel (bounded barrier waits)
 };
 constexpr int64_t kConvSplitKScratchFloats = 600ll * 64 * 64;   // upper bound used by launch_conv_direct's split-K policy
 int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s);
@@ -118,7 +123,7 @@ int launch_concat_handside_split(const float* feat, const float* hand_side, Spli
 // ---------------------------------------------------------------- kernels (conv_tc.cu)
 // first layer (Cin = 3, 3x3, 64 output channels) on the tensor cores, writing split planes (hi, lo optional)
 int launch_conv_c3_tc(const float* x, const float* w, const float* bias, Split y, int Cs_total, int cs_off, int B, int H, int W, int leaky,
-                      Half16 half, cudaStream_t s);
+                      Half16 half, cudaStream_t s, int* err_flag = nullptr);
 struct TcConvPlan;  // opaque: tensor maps + launch geometry of one tensor-core conv layer
 struct TcConvDesc {
     // input activations (split planes) [B,H,W,Cin_total]; channels [0,Cin_pad) are read (Cin_pad % 64 == 0)
@@ -138,7 +143,18 @@ struct TcConvDesc {
     float corr_scale = 0.f;   // passes == 4: 2^-(10 + b), un-does the scales of the fp8 operands (b: per-layer weight shift)
     Half16 half;
     int pool = 0;  // 1: fuse the following 2x2/2 max-pool; 2: stride-2 'SAME' convolution (even H, W); outputs are [B, H/2, W/2, C]
+    int* err_flag = nullptr;   // device int: a barrier wait that times out stores its code here before trapping (h3d_ctx owns it)
 };
+// Tuning switches: initialised from the environment once (H3D_TC_2CTA, H3D_TC_BN, ...), changed only through tc_set_tuning().
+struct TcTuning {
+    int two_cta = -1;      // -1 policy, 0 / 1 force the single-CTA / CTA-pair kernel family
+    int bn = 0;            // 0 policy, else forced N tile
+    int c64 = 1, c64x2 = 1, pair128 = 1, stack = 1;
+    int chunk_kb = 0;      // 0 policy
+    int no_side_stream = 0, no_pool_fusion = 0, lift_direct = 0, c3_ffma = 0;
+};
+TcTuning& tc_tuning();
+int tc_set_tuning(const char* key, int value);
 TcConvPlan* tc_conv_plan_create(const TcConvDesc& d);   // nullptr on failure (h3d_last_error set)
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t s);

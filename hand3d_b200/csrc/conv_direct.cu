@@ -350,8 +350,8 @@ int conv_direct_num_launches(const DirectConvArgs& a) {
 
 int launch_conv_direct(const DirectConvArgs& a, cudaStream_t s) {
     H3D_REQUIRE(a.k >= 1 && a.stride >= 1 && a.Cin >= 1 && a.Cout >= 1, "conv_direct: bad geometry");
-    if (is_c3_case(a) && !a.y && a.ys.hi && !a.ys.l8 && !getenv("H3D_C3_FFMA"))   // split planes only: tensor-core version
-        return launch_conv_c3_tc(a.x, a.w, a.bias, a.ys, a.Cs_total, a.cs_off, a.B, a.H, a.W, a.leaky, a.half, s);
+    if (is_c3_case(a) && !a.y && a.ys.hi && !a.ys.l8 && !tc_tuning().c3_ffma)   // split planes only: tensor-core version
+        return launch_conv_c3_tc(a.x, a.w, a.bias, a.ys, a.Cs_total, a.cs_off, a.B, a.H, a.W, a.leaky, a.half, s, a.err_flag);
     if (is_c3_case(a)) {
         const int tiles = ceil_div(ceil_div(a.W, C3_TW) * ceil_div(a.H, C3_TH) * a.B, C3_TILES_PER_CTA);
         if (a.half == Half16::FP16)

@@ -88,7 +88,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) {   // ~2 s
-            if (err_flag) atomicExch(err_flag, code);
+            if (err_flag) { atomicExch_system(err_flag, code); __threadfence_system(); }
             __trap();
         }
     }
@@ -909,12 +909,26 @@ conv_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 // TMA loads; empty[s] / tmem_full[a] are signalled in both CTAs by multicast commits; tmem_empty[a] lives in the leader
 // and collects one arrive per epilogue warp of both CTAs.
 constexpr int kThreads2 = 32 * 10;
-__host__ __device__ constexpr int stage_bytes2(int BN, int PASSES) { return (PASSES >= 3 ? 2 : 1) * (A_TILE_BYTES + (BN / 2) * BK * 2); }
+// N-stacked CTA-pair variant (3-pass, BN == 128): per K step  A_hi x [W_hi ; W_lo]  (one UMMA 256 x 256: TMEM columns [0,128) = hi*hi,
+// [128,256) = hi*lo) and  A_lo x W_hi  (UMMA 256 x 128 into columns [0,128)).  With cta_group::2 every CTA supplies half of the B
+// rows of an instruction, read at the SAME shared-memory offset in both CTAs, so each stage holds two weight regions:
+//   Y (128 rows): CTA 0 = W_hi[n0 .. n0+128), CTA 1 = W_lo[n0 .. n0+128)   -> B operand of the N = 256 instruction
+//   X ( 64 rows): CTA r = W_hi[n0 + 64 r .. + 64)                          -> B operand of the N = 128 instruction
+// Per K step each SM reads 14 KB of operands in 192 tensor cycles (73 B/clk; the single-CTA stacked kernel reads 20 KB = 107 B/clk,
+// which together with the TMA writes exceeds the 128 B/clk of shared memory) and pulls 56 KB per K block through L2 instead of 64.
+__host__ __device__ constexpr bool stack2(int BN, int PASSES) { return PASSES == 3 && BN == 128; }
+__host__ __device__ constexpr int stage_bytes2(int BN, int PASSES) {
+    return stack2(BN, PASSES) ? 2 * A_TILE_BYTES + 128 * BK * 2 + 64 * BK * 2 : (PASSES >= 3 ? 2 : 1) * (A_TILE_BYTES + (BN / 2) * BK * 2);
+}
 __host__ __device__ constexpr int num_stages2(int BN, int PASSES) {
     return kSmemBudget / stage_bytes2(BN, PASSES) > 8 ? 8 : kSmemBudget / stage_bytes2(BN, PASSES);
 }
 
 template <int BN, int PASSES, bool FP16>
+// Register budget: 10 warps land 3 / 3 / 2 / 2 on the four SM sub-partitions of 16384 registers each, so 16384 / (3 x 32) = 170 ->
+// 168 registers per thread is the hardware limit for this block shape (a __maxnreg__(200) build compiles spill-free at 197
+// registers but fails to launch: "too many resources requested").  With BN = 256 the 128 fp32 partial sums per epilogue thread
+// therefore spill 284 bytes to (L1-resident) local memory; the epilogue is off the tensor pipe's critical path.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -924,6 +938,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;
     constexpr int A8_TILE_BYTES = BM * BK, B8_TILE_BYTES = (BN / 2) * BK;   // e4m3 tiles (mode 4): 64-byte rows
     constexpr uint32_t IDESC = make_idesc(BN, FP16, 256);
+    constexpr bool STACK = stack2(BN, PASSES);
+    constexpr uint32_t IDESC_STACK = make_idesc(2 * BN, FP16, 256);
+    constexpr int ACC_COLS = STACK ? 2 * BN : BN;      // TMEM columns per accumulator stage
+    constexpr int TMEM_COLS = tmem_cols(ACC_COLS);
+    constexpr int Y_BYTES = 128 * BK * 2;              // stacked variant: weight region Y
     static_assert(PASSES != 4 || FP16, "fp8-correction mode uses an fp16 main plane");
     constexpr int COLS = BN / 2;                       // accumulator columns drained by one epilogue warp
     static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
@@ -950,7 +969,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -974,6 +993,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                             uint8_t* st = smem + stage * STAGE_BYTES;
                             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
                             tma_load_4d_2sm(&map_x_hi, st, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                            if (STACK) {   // [A_hi | A_lo | Y | X]; map_w_hi / map_w_lo have 128-row boxes, map_w_l8 = W_hi with 64-row boxes
+                                tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                tma_load_2d_2sm(rank == 0 ? &map_w_hi : &map_w_lo, st + 2 * A_TILE_BYTES, &full_bar[stage], kcol, nt * BN);
+                                tma_load_2d_2sm(&map_w_l8, st + 2 * A_TILE_BYTES + Y_BYTES, &full_bar[stage], kcol, n0);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             tma_load_2d_2sm(&map_w_hi, st + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
                             if (PASSES == 3) {
                                 tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
@@ -1001,7 +1027,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                     const int acc = acc_it & 1;
                     mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
                     const int kb1 = min(kblocks, kb0 + p.chunk_kb);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
@@ -1010,10 +1036,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                         const uint64_t a_hi = make_smem_desc(sa);
                         const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
                         const uint64_t b_hi = make_smem_desc(sa + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES);
-                        const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                        const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + (STACK ? Y_BYTES : B_TILE_BYTES));
 #pragma unroll
                         for (int j = 0; j < BK / UMMA_K; ++j) {
                             const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                            if (STACK) {   // b_hi = region Y ([W_hi ; W_lo] across the pair), b_lo = region X (W_hi halves)
+                                tc_mma_f16_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC_STACK, (uint32_t)((kb > kb0) | (j != 0)));
+                                tc_mma_f16_2cta(d_tmem, a_lo + koff, b_lo + koff, IDESC, 1u);
+                                continue;
+                            }
                             tc_mma_f16_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC, (uint32_t)((kb > kb0) | (j != 0)));
                             if (PASSES == 3) {
                                 tc_mma_f16_2cta(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
@@ -1060,7 +1091,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                 const int acc = acc_it & 1;
                 mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, p.err_flag, 4);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + ch * COLS);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS + ch * COLS);
 #pragma unroll
                 for (int c0 = 0; c0 < COLS; c0 += 32) {
                     uint32_t v[32];
@@ -1070,6 +1101,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
 #pragma unroll
                         for (int i = 0; i < 32; ++i) racc[c0 + i] = __uint_as_float(v[i]);
                     } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) racc[c0 + i] += __uint_as_float(v[i]);
+                    }
+                    if (STACK) {   // + the hi*lo products of the stacked half
+                        tc_ld_32x32b_x32(taddr + BN + c0, v);
+                        tc_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) racc[c0 + i] += __uint_as_float(v[i]);
                     }
@@ -1087,7 +1124,171 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     cluster_sync_all();          // nobody leaves (or frees TMEM) while the peer may still touch this CTA's smem / TMEM
     if (warp == 9) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(BN)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 64-channel kernel on a CTA pair
+// conv_c64_kernel is bound by shared-memory operand reads (N = 64: 14 KB per 96 tensor cycles = 146 B/clk against 128 B/clk;
+// ncu r01e: tensor pipe busy 76 %, computing 56 %) and by its two-deep patch ring (the 144 KB of resident weights leave room
+// for two 40 KB stages).  The cta_group::2 version halves the weight bytes per SM and the B rows each SM feeds per instruction:
+//   * CTA r keeps, per tap, [W_hi[32 r .. 32 r + 32) ; W_lo[32 r .. 32 r + 32)] (64 rows = 8 KB; 72 KB for the layer), which
+//     leaves three 40 KB patch stages;
+//   * UMMA 1: A_hi x stacked B, M = 256 (CTA r owns pixel tile 2 * item + r), N = 128: columns [0,32) hi*hi ch 0-31, [32,64) hi*lo
+//     ch 0-31 (CTA 0's rows), [64,96) hi*hi ch 32-63, [96,128) hi*lo ch 32-63 (CTA 1's rows);
+//   * UMMA 2: A_lo x W_hi, N = 64, B = the first 32 rows of the same weight region in both CTAs, into columns [128,192):
+//     lo*hi ch 0-31 | ch 32-63 (a separate accumulator region because the column order differs);
+//   * per pair of UMMAs each SM reads 11 KB instead of 14 KB; 8 epilogue warps (lane quadrant x 32-channel half) add the three
+//     column groups.
+// Barriers as in conv_tc2_kernel.  p.num_tiles counts pixel-tile PAIRS; Cout = 64 * n_tiles: cluster c serves channel group c % n_tiles.
+constexpr int C64X2_W_TAP_BYTES = 64 * BK * 2;
+constexpr int C64X2_W_BYTES = 9 * C64X2_W_TAP_BYTES;
+constexpr int C64X2_A_STAGE_BYTES = 2 * C64_PATCH_BYTES;
+constexpr int C64X2_STAGES = 3;
+constexpr int C64X2_ACC_COLS = 256;
+constexpr int C64X2_SMEM = C64X2_W_BYTES + C64X2_STAGES * C64X2_A_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(C64X2_SMEM <= 227 * 1024, "conv_c64x2_kernel: shared memory budget");
+
+template <bool FP16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+    constexpr uint32_t IDESC_MAIN = make_idesc(128, FP16, 256);
+    constexpr uint32_t IDESC_N64 = make_idesc(64, FP16, 256);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* wsm = smem;
+    uint8_t* asm_ = smem + C64X2_W_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(asm_ + C64X2_STAGES * C64X2_A_STAGE_BYTES);
+    uint64_t* a_empty = a_full + C64X2_STAGES;
+    uint64_t* tfull_bar = a_empty + C64X2_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* w_full = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int n0 = (cluster_id % p.n_tiles) * 64;
+    const int item0 = cluster_id / p.n_tiles, item_step = num_clusters / p.n_tiles;
+
+    if (warp == 8 && lane == 0) {
+        prefetch_tmap(&map_x_hi); prefetch_tmap(&map_w_hi); prefetch_tmap(&map_x_lo); prefetch_tmap(&map_w_lo);
+        for (int s = 0; s < C64X2_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * C64X2_ACC_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ================================ TMA producer (both CTAs) ================================
+        if (lane == 0) {
+            if (rank == 0) mbar_expect_tx(w_full, 2 * C64X2_W_BYTES);
+            for (int t = 0; t < 9; ++t) {
+                tma_load_2d_2sm(&map_w_hi, wsm + t * C64X2_W_TAP_BYTES, w_full, t * BK, n0 + (int)rank * 32);
+                tma_load_2d_2sm(&map_w_lo, wsm + t * C64X2_W_TAP_BYTES + 32 * BK * 2, w_full, t * BK, n0 + (int)rank * 32);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (int item = item0; item < p.num_tiles; item += item_step) {
+                const int mt = 2 * item + (int)rank;
+                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+                const int w0 = tw * C64_TW - 1, h0 = th * C64_TH - 1;
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 1);
+                    uint8_t* st = asm_ + stage * C64X2_A_STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&a_full[stage], 2 * C64X2_A_STAGE_BYTES);
+                    tma_load_4d_2sm(&map_x_hi, st, &a_full[stage], 0, w0 + kw, h0, tb);   // tb >= B (odd tile count): zero fill
+                    tma_load_4d_2sm(&map_x_lo, st + C64_PATCH_BYTES, &a_full[stage], 0, w0 + kw, h0, tb);
+                    if (++stage == C64X2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================================ MMA issuer (leader CTA) ================================
+        if (rank == 0 && lane == 0) {
+            mbar_wait(w_full, 0, p.err_flag, 5);
+            tc_fence_after();
+            const uint32_t wb = smem_u32(wsm);
+            int stage = 0; uint32_t phase = 0;
+            int acc_it = 0;
+            for (int item = item0; item < p.num_tiles; item += item_step, ++acc_it) {
+                const int acc = acc_it & 1;
+                mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C64X2_ACC_COLS);
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait(&a_full[stage], phase, p.err_flag, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(asm_ + stage * C64X2_A_STAGE_BYTES);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint64_t a_hi = make_smem_desc(sa + kh * C64_ROW_BYTES);
+                        const uint64_t a_lo = make_smem_desc(sa + C64_PATCH_BYTES + kh * C64_ROW_BYTES);
+                        const uint64_t b = make_smem_desc(wb + (kh * 3 + kw) * C64X2_W_TAP_BYTES);
+#pragma unroll
+                        for (int j = 0; j < BK / UMMA_K; ++j) {
+                            const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                            const uint32_t accum = (uint32_t)((kw | kh | j) != 0);
+                            tc_mma_f16_2cta(d_tmem, a_hi + koff, b + koff, IDESC_MAIN, accum);
+                            tc_mma_f16_2cta(d_tmem + 128, a_lo + koff, b + koff, IDESC_N64, accum);
+                        }
+                    }
+                    tc_commit_2cta(&a_empty[stage]);
+                    if (++stage == C64X2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2cta(&tfull_bar[acc]);
+            }
+        }
+    } else {
+        // ================================ epilogue (8 warps: lane quadrant q, 32-channel half ch) ================================
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        const int w_l = row % C64_TW, h_l = row / C64_TW;
+        int acc_it = 0;
+        for (int item = item0; item < p.num_tiles; item += item_step, ++acc_it) {
+            const int mt = 2 * item + (int)rank;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
+            const int w = tw * C64_TW + w_l, h = th * C64_TH + h_l;
+            bool valid = (w < p.W) && (h < p.H) && (b < p.B);
+            int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
+            if (p.pool) {
+                const int par = p.pool == 2 ? 1 : 0;
+                valid = valid && ((w & 1) == par) && ((h & 1) == par);
+                pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+            }
+            const int acc = acc_it & 1;
+            mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, p.err_flag, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C64X2_ACC_COLS);
+            uint32_t v0[32], v1[32], v2[32];
+            tc_ld_32x32b_x32(taddr + 64 * ch, v0);          // hi*hi
+            tc_ld_32x32b_x32(taddr + 64 * ch + 32, v1);     // hi*lo
+            tc_ld_32x32b_x32(taddr + 128 + 32 * ch, v2);    // lo*hi
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+            float racc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) racc[i] = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + __uint_as_float(v2[i]);
+            epilogue_store32<3, FP16>(p, racc, pix, n0 + 32 * ch, valid);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * C64X2_ACC_COLS) : "memory");
     }
 }
 
@@ -1158,6 +1359,8 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s);
 struct TcConvPlan {
     bool two_cta = false;
     bool c64 = false;      // 64 -> 64 channel 3x3 specialisation (conv_c64_kernel)
+    bool c64x2 = false;    // ... on a CTA pair (conv_c64x2_kernel)
+    int device = 0;
 
     TcConvDesc d;
     CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo, map_x_h8, map_w_l8;
@@ -1166,24 +1369,75 @@ struct TcConvPlan {
     int* err_flag;
 };
 
+// SM count and the shared-memory opt-in are per DEVICE (one process may hold contexts on several GPUs)
+constexpr int kMaxDevices = 64;
+static int current_device() { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; } return dev; }
 int tc_num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static int n[kMaxDevices] = {};
+    const int dev = current_device() % kMaxDevices;
+    if (!n[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 148; }
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
+}
+// once per (kernel instance, device): raise the dynamic shared-memory limit
+template <typename K>
+static int smem_opt_in(K kernel, int bytes, bool* done /*[kMaxDevices]*/) {
+    const int dev = current_device() % kMaxDevices;
+    if (!done[dev]) {
+        H3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done[dev] = true;
+    }
+    return H3D_OK;
+}
+
+// Tuning switches (A/B experiments, forced kernel variants in the tests).  Read from the environment ONCE, when the library
+// is first used, and changeable afterwards only through tc_set_tuning() (h3d_set_tuning): nothing on a launch path calls getenv.
+TcTuning& tc_tuning() {
+    static TcTuning t = [] {
+        TcTuning v;
+        auto geti = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+        v.two_cta = geti("H3D_TC_2CTA", -1);
+        v.bn = geti("H3D_TC_BN", 0);
+        v.c64 = geti("H3D_TC_C64", 1);
+        v.c64x2 = geti("H3D_TC_C64X2", 1);
+        v.pair128 = geti("H3D_TC_PAIR128", 1);
+        v.stack = geti("H3D_TC_STACK", 1);
+        v.chunk_kb = geti("H3D_TC_CHUNK_KB", 0);
+        v.no_side_stream = geti("H3D_NO_SIDE_STREAM", 0);
+        v.no_pool_fusion = geti("H3D_NO_POOL_FUSION", 0);
+        v.lift_direct = geti("H3D_LIFT_DIRECT", 0);
+        v.c3_ffma = geti("H3D_C3_FFMA", 0);
+        return v;
+    }();
+    return t;
+}
+int tc_set_tuning(const char* key, int value) {
+    TcTuning& t = tc_tuning();
+    const std::string k(key ? key : "");
+    if (k == "tc_2cta") t.two_cta = value;
+    else if (k == "tc_bn") t.bn = value;
+    else if (k == "tc_c64") t.c64 = value;
+    else if (k == "tc_c64x2") t.c64x2 = value;
+    else if (k == "tc_pair128") t.pair128 = value;
+    else if (k == "tc_stack") t.stack = value;
+    else if (k == "tc_chunk_kb") t.chunk_kb = value;
+    else if (k == "no_side_stream") t.no_side_stream = value;
+    else if (k == "no_pool_fusion") t.no_pool_fusion = value;
+    else if (k == "lift_direct") t.lift_direct = value;
+    else if (k == "c3_ffma") t.c3_ffma = value;
+    else { set_error("h3d_set_tuning: unknown key '%s'", k.c_str()); return H3D_EINVAL; }
+    return H3D_OK;
 }
 
 namespace {
 template <int BN, int PASSES, bool FP16>
 int launch_inst(const TcConvPlan* pl, cudaStream_t s) {
     constexpr int smem = num_stages(BN, PASSES) * stage_bytes(BN, PASSES) + 1024 /*align slack*/ + 256 /*barriers*/;
-    static bool attr = false;
-    if (!attr) {
-        H3D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, PASSES, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    static bool attr[kMaxDevices] = {};
+    if (int rc = smem_opt_in(conv_tc_kernel<BN, PASSES, FP16>, smem, attr)) return rc;
     conv_tc_kernel<BN, PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->map_x_h8,
                                                                       pl->map_w_l8, pl->p);
     H3D_CHECK_LAUNCH();
@@ -1195,12 +1449,17 @@ namespace {
 template <int PASSES, bool FP16>
 int launch_c64(const TcConvPlan* pl, cudaStream_t s) {
     constexpr int smem = c64_smem_bytes(PASSES);
-    static bool attr = false;
-    if (!attr) {
-        H3D_CUDA(cudaFuncSetAttribute(conv_c64_kernel<PASSES, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    static bool attr[kMaxDevices] = {};
+    if (int rc = smem_opt_in(conv_c64_kernel<PASSES, FP16>, smem, attr)) return rc;
     conv_c64_kernel<PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+template <bool FP16>
+int launch_c64x2(const TcConvPlan* pl, cudaStream_t s) {
+    static bool attr[kMaxDevices] = {};
+    if (int rc = smem_opt_in(conv_c64x2_kernel<FP16>, C64X2_SMEM, attr)) return rc;
+    conv_c64x2_kernel<FP16><<<pl->grid, kThreads2, C64X2_SMEM, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }
@@ -1210,11 +1469,9 @@ namespace {
 template <int BN, int PASSES, bool FP16>
 int launch_inst2(const TcConvPlan* pl, cudaStream_t s) {
     constexpr int smem = num_stages2(BN, PASSES) * stage_bytes2(BN, PASSES) + 1024 /*align slack*/ + 256 /*barriers*/;
-    static bool attr = false;
-    if (!attr) {
-        H3D_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<BN, PASSES, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
-    }
+    static_assert(smem <= 227 * 1024, "conv_tc2_kernel: shared memory budget");
+    static bool attr[kMaxDevices] = {};
+    if (int rc = smem_opt_in(conv_tc2_kernel<BN, PASSES, FP16>, smem, attr)) return rc;
     conv_tc2_kernel<BN, PASSES, FP16><<<pl->grid, kThreads2, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->map_x_h8,
                                                                         pl->map_w_l8, pl->p);
     H3D_CHECK_LAUNCH();
@@ -1242,28 +1499,31 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if (d.passes == 4 && d.y.hi && ((d.Cy_total % 16) || (d.cy_off % 16))) { set_error("tc_conv: fp8 planes need 16-channel aligned offsets"); return nullptr; }
     TcConvPlan* pl = new TcConvPlan();
     pl->d = d;
+    const TcTuning& tune = tc_tuning();
     int BN = d.Cout_pad % 128 == 0 ? 128 : 64;
-    // CTA-pair kernel when N can be 256 (measured: 7-10 % faster there; for Cout = 64 / 128 the A operand dominates the
-    // shared-memory traffic either way and the single-CTA kernel is as fast or faster).  H3D_TC_2CTA=0/1 forces one kernel.
-    bool two = d.Cout_pad % 256 == 0;
-    if (const char* e = getenv("H3D_TC_2CTA")) two = atoi(e) != 0;
+    // CTA-pair kernel (cta_group::2, UMMA 256 x BN) when N can be 256, and - in the 3-pass modes - its N-stacked variant for
+    // Cout = 128 (conv2_2, the 7x7 refinement layers, conv4_7 / conv5_2): half the weight rows and a quarter fewer operand bytes
+    // per SM and K step than the single-CTA stacked kernel, which is bound by shared-memory bandwidth there.  tune.two_cta = 0 / 1
+    // forces one kernel family.
+    bool two = d.Cout_pad % 256 == 0 || (tune.pair128 && d.passes == 3 && d.Cout_pad % 128 == 0);
+    if (tune.two_cta >= 0) two = tune.two_cta != 0;
     if (two) BN = d.Cout_pad % 256 == 0 ? 256 : (d.Cout_pad % 128 == 0 ? 128 : 64);   // CTA pair: UMMA 256 x BN
     // Small maps (lifting pyramids from 16x16 down, the FC stacks = 1x1 convolutions over batch rows): too few pixel tiles to fill
     // the machine with wide tiles, so N = 64 tiles on single CTAs spread the work (and the weight stream) over 4-8x more SMs.  The
     // rule depends on the layer geometry only, never on the batch size: the arithmetic of an image must not depend on how a batch
     // is cut (tests/test_gpu_properties.py: bit-identical results under sharding).
-    if (!getenv("H3D_TC_2CTA") && (int64_t)d.H * d.W <= 256) { two = false; BN = 64; }
-    if (const char* e = getenv("H3D_TC_BN")) {
-        const int v = atoi(e);
-        if ((v == 64 || v == 128 || v == 256) && d.Cout_pad % v == 0) BN = v;
-    }
-    // 64 -> 64 channels, 3x3 (conv1_2 of both networks, small lifting layers): weights-resident / patch-reuse kernel
-    bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad <= 128 && (d.passes == 1 || d.passes == 3);
-    if (const char* e = getenv("H3D_TC_C64")) c64 = c64 && atoi(e) != 0;
+    if (tune.two_cta < 0 && (int64_t)d.H * d.W <= 256) { two = false; BN = 64; }
+    if ((tune.bn == 64 || tune.bn == 128 || tune.bn == 256) && d.Cout_pad % tune.bn == 0) BN = tune.bn;
+    // 64 -> 64 / 64 -> 128 channels, 3x3 (conv1_2, conv2_1, small lifting layers): weights-resident / patch-reuse kernels; on a CTA
+    // pair in the 3-pass modes when the map is large enough to fill the machine with tile pairs
+    bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad <= 128 && (d.passes == 1 || d.passes == 3) && tune.c64 != 0;
+    const bool c64x2 = c64 && d.passes == 3 && tune.c64x2 != 0 && (int64_t)d.H * d.W > 256;
     if (c64) { two = false; BN = 64; }
     pl->BN = BN;
     pl->two_cta = two;
     pl->c64 = c64;
+    pl->c64x2 = c64x2;
+    pl->device = current_device();
 
     int TW, TH, TB;
     if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool / stride 2 needs even H and W"); delete pl; return nullptr; }
@@ -1284,20 +1544,24 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     p.leaky = d.leaky;
     p.n_valid = d.Cout;
     p.pool = d.pool;
-    p.stack = 1;
-    if (const char* e = getenv("H3D_TC_STACK")) p.stack = atoi(e) != 0;
-    p.err_flag = nullptr;
+    p.stack = tune.stack != 0;
+    p.err_flag = d.err_flag;
     // <= ~108 accumulating MMAs per TMEM partial sum (9 K blocks x 4 K steps x 3 passes); BN = 256 keeps everything in
     // TMEM (its 256 fp32 partial sums per thread would not fit the register file)
     p.chunk_kb = d.passes >= 3 ? 9 : 27;
-    if (const char* e = getenv("H3D_TC_CHUNK_KB")) { const int v = atoi(e); if (v > 0) p.chunk_kb = v; }
+    if (tune.chunk_kb > 0) p.chunk_kb = tune.chunk_kb;
     if (BN > 128 && !two) p.chunk_kb = 1 << 30;
     pl->grid = two ? 2 * std::min(p.num_tiles, tc_num_sms() / 2) : std::min(p.num_tiles, tc_num_sms());
     if (c64) {   // work items = pixel tiles; CTAs are split evenly over the 64-channel groups
         p.num_tiles = p.tiles_w * p.tiles_h * tiles_b;
         pl->grid = p.n_tiles * std::max(1, std::min(p.num_tiles, tc_num_sms() / p.n_tiles));
     }
-    const int w_box_rows = two ? BN / 2 : BN;
+    if (c64x2) {   // work items = pixel-tile pairs; clusters are split evenly over the 64-channel groups
+        p.num_tiles = ceil_div(p.tiles_w * p.tiles_h * tiles_b, 2);
+        pl->grid = 2 * p.n_tiles * std::max(1, std::min(p.num_tiles, (tc_num_sms() / 2) / p.n_tiles));
+    }
+    const bool stacked_pair = two && stack2(BN, d.passes);
+    const int w_box_rows = c64x2 ? 32 : stacked_pair ? BN : two ? BN / 2 : BN;
     const int Ktot = d.k * d.k * d.Cin_pad;
     const int box_h = c64 ? C64_PH : TH;   // the 64 -> 64 kernel fetches the tile rows plus the halo rows in one box
     bool ok = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, box_h, TB) &&
@@ -1312,6 +1576,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
              encode_w_map(&pl->map_w_l8, d.w.l8, Ktot, d.Cout_pad, w_box_rows, 1);
     if (ok && d.passes == 1) { pl->map_x_lo = pl->map_x_hi; pl->map_w_lo = pl->map_w_hi; }
     if (ok && d.passes != 4) { pl->map_x_h8 = pl->map_x_hi; pl->map_w_l8 = pl->map_w_hi; }
+    if (ok && stacked_pair) ok = encode_w_map(&pl->map_w_l8, d.w.hi, Ktot, d.Cout_pad, BN / 2);   // region X: W_hi in 64-row boxes
     if (!ok) { delete pl; return nullptr; }
     return pl;
 }
@@ -1325,6 +1590,7 @@ int64_t tc_conv_flops(const TcConvPlan* p) {
 int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
     const bool fp16 = pl->d.half == Half16::FP16;
     const int key = pl->BN * 10 + pl->d.passes;
+    if (pl->c64x2) return fp16 ? launch_c64x2<true>(pl, s) : launch_c64x2<false>(pl, s);
     if (pl->c64) {
         if (pl->d.passes == 3) return fp16 ? launch_c64<3, true>(pl, s) : launch_c64<3, false>(pl, s);
         return fp16 ? launch_c64<1, true>(pl, s) : launch_c64<1, false>(pl, s);
@@ -1358,7 +1624,7 @@ int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
 // conv1_1 (3 -> 64 channels, 3x3, stride 1) on the tensor cores: x fp32 [B,H,W,3], w fp32 HWIO [3,3,3,64] and bias [64] on the
 // device, output split planes y (hi, and lo when present) [B,H,W,Cs_total] at channel offset cs_off.
 int launch_conv_c3_tc(const float* x, const float* w, const float* bias, Split y, int Cs_total, int cs_off, int B, int H, int W, int leaky,
-                      Half16 half, cudaStream_t s) {
+                      Half16 half, cudaStream_t s, int* err_flag) {
     H3D_REQUIRE(x && w && bias && y.hi && !y.l8 && (Cs_total % 8) == 0 && (cs_off % 8) == 0, "conv_c3_tc: bad argument");
     TcParams p{};
     p.bias = bias;
@@ -1368,14 +1634,11 @@ int launch_conv_c3_tc(const float* x, const float* w, const float* bias, Split y
     p.TW = C64_TW; p.TH = C64_TH; p.TB = 1;
     p.tiles_w = ceil_div(W, C64_TW); p.tiles_h = ceil_div(H, C64_TH); p.n_tiles = 1;
     p.num_tiles = p.tiles_w * p.tiles_h * B;
-    p.n_valid = 64; p.pool = 0; p.chunk_kb = 1; p.leaky = leaky; p.err_flag = nullptr;
+    p.n_valid = 64; p.pool = 0; p.chunk_kb = 1; p.leaky = leaky; p.err_flag = err_flag;
     const int grid = std::min(p.num_tiles, 2 * tc_num_sms());   // two co-resident CTAs per SM (86 KB, 72 registers, 256 TMEM columns each)
-    static bool attr = false;
-    if (!attr) {
-        H3D_CUDA(cudaFuncSetAttribute(conv_c3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3T_SMEM));
-        H3D_CUDA(cudaFuncSetAttribute(conv_c3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3T_SMEM));
-        attr = true;
-    }
+    static bool attr_h[kMaxDevices] = {}, attr_b[kMaxDevices] = {};
+    if (int rc = smem_opt_in(conv_c3_tc_kernel<true>, C3T_SMEM, attr_h)) return rc;
+    if (int rc = smem_opt_in(conv_c3_tc_kernel<false>, C3T_SMEM, attr_b)) return rc;
     if (half == Half16::FP16) conv_c3_tc_kernel<true><<<grid, C3T_THREADS, C3T_SMEM, s>>>(x, w, p);
     else conv_c3_tc_kernel<false><<<grid, C3T_THREADS, C3T_SMEM, s>>>(x, w, p);
     H3D_CHECK_LAUNCH();

@@ -494,10 +494,12 @@ int launch_seg_postprocess(const float* logits, int B, int H, int W, void* scrat
     seg_prob_kernel<<<grid, 256, 0, s>>>((const float2*)logits, H, W, Ww, key, det);
     H3D_CHECK_LAUNCH();
     const size_t smem = (size_t)3 * words * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per device (one process may drive several GPUs)
+    int dev = 0;
+    H3D_CUDA(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
         H3D_CUDA(cudaFuncSetAttribute(mask_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kMaxMaskWords * 4));
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     const int num_passes = std::max(H, W) / (21 / 2);   // utils/general.py:256
     mask_grow_kernel<<<B, kGrowThreads, smem, s>>>(key, det, H, W, Ww, num_passes, hand_mask, max_loc, center, crop_size,
@@ -814,9 +816,10 @@ __global__ void __launch_bounds__(1024, 1)
 gather_records_p2p_kernel(const float* __restrict__ coord3d, const int32_t* __restrict__ uv, const float* __restrict__ center,
                           const float* __restrict__ scale, int B, const uint64_t* __restrict__ peer_buffers,
                           const uint64_t* __restrict__ peer_signals, uint64_t multicast_ptr, int rank, int world, uint32_t epoch,
-                          int64_t parity_stride_floats, int* __restrict__ err_flag) {
+                          int64_t parity_stride_floats, int64_t slot_floats, int* __restrict__ err_flag) {
     const int n = B * 108;
-    const int64_t base = (int64_t)(epoch & 1u) * parity_stride_floats + (int64_t)rank * n;
+    // rank r's records live at slot r * slot_floats (slot_floats = max_batch * 108): ranks with different B never overlap
+    const int64_t base = (int64_t)(epoch & 1u) * parity_stride_floats + (int64_t)rank * slot_floats;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int b = i / 108, j = i - b * 108;
         float v;
@@ -838,7 +841,7 @@ gather_records_p2p_kernel(const float* __restrict__ coord3d, const int32_t* __re
         const uint32_t* mine = reinterpret_cast<const uint32_t*>(peer_signals[rank]) + r;
         const long long t0 = clock64();
         while ((int32_t)(ld_acquire_sys_u32(mine) - epoch) < 0) {                                 // wait for peer r's records
-            if (clock64() - t0 > 20000000000ll) { if (err_flag) atomicExch(err_flag, 100 + r); break; }
+            if (clock64() - t0 > 20000000000ll) { if (err_flag) atomicExch_system(err_flag, 100 + r); break; }   // ~10 s: peer r never signalled
         }
     }
     __syncthreads();
@@ -846,10 +849,10 @@ gather_records_p2p_kernel(const float* __restrict__ coord3d, const int32_t* __re
 
 int launch_gather_records_p2p(const float* coord3d, const int32_t* uv, const float* center, const float* scale, int B,
                               const uint64_t* peer_buffers, const uint64_t* peer_signals, uint64_t multicast_ptr, int rank, int world,
-                              uint32_t epoch, int64_t parity_stride_floats, cudaStream_t s) {
-    H3D_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && B > 0, "gather_records_p2p: bad geometry");
+                              uint32_t epoch, int64_t parity_stride_floats, int max_batch, int* err_flag, cudaStream_t s) {
+    H3D_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && B > 0 && B <= max_batch, "gather_records_p2p: bad geometry");
     gather_records_p2p_kernel<<<1, 1024, 0, s>>>(coord3d, uv, center, scale, B, peer_buffers, peer_signals, multicast_ptr, rank, world,
-                                                 epoch, parity_stride_floats, nullptr);
+                                                 epoch, parity_stride_floats, (int64_t)max_batch * 108, err_flag);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }
@@ -899,6 +902,111 @@ int launch_bone_rel_trafo_inv(const float* rel, float* xyz, int B, cudaStream_t 
 int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot, float* out,
                             cudaStream_t s) {
     rotate_canonical_kernel<<<B, 64, 0, s>>>(coord_can, uxyz, hand_side, B, rot, out);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
+// Record pack alone (single-GPU serving path; the multi-GPU path packs inside gather_records_p2p_kernel):
+// [B,108] = coord3d 63 f32 | key-points 42 i32 (bit-cast) | center 2 | scale 1.
+// =============================================================================================
+__global__ void pack_records_kernel(const float* __restrict__ coord3d, const int32_t* __restrict__ uv, const float* __restrict__ center,
+                                    const float* __restrict__ scale, int B, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 108) return;
+    const int b = i / 108, j = i - b * 108;
+    float v;
+    if (j < 63) v = coord3d[b * 63 + j];
+    else if (j < 105) v = __int_as_float(uv[b * 42 + (j - 63)]);
+    else if (j < 107) v = center[b * 2 + (j - 105)];
+    else v = scale[b];
+    out[i] = v;
+}
+int launch_pack_records(const float* coord3d, const int32_t* uv, const float* center, const float* scale, int B, float* out, cudaStream_t s) {
+    pack_records_kernel<<<ceil_div(B * 108, 256), 256, 0, s>>>(coord3d, uv, center, scale, B, out);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// =============================================================================================
+// calc_center_bb (utils/general.py:271-328) on an arbitrary mask: one CTA per image reduces the bounding box of the pixels
+// with int(mask) == 1 (X = row index, Y = column index as in the reference), then centre = 0.5 (max + min), crop size =
+// max extent; an empty mask gives the reference's written fall-backs (centre 160, size 100) and bb = (+inf, -inf).
+// =============================================================================================
+__global__ void mask_bbox_kernel(const float* __restrict__ mask, int H, int W, float* __restrict__ center, float* __restrict__ bb,
+                                 float* __restrict__ crop_size) {
+    __shared__ int s_rmin, s_rmax, s_cmin, s_cmax;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) { s_rmin = 1 << 30; s_rmax = -1; s_cmin = 1 << 30; s_cmax = -1; }
+    __syncthreads();
+    int rmin = 1 << 30, rmax = -1, cmin = 1 << 30, cmax = -1;
+    const float* m = mask + (int64_t)b * H * W;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+        if ((int)__ldg(m + i) == 1) {     // tf.cast(mask, tf.int32) == 1 (:274-275)
+            const int y = i / W, x = i - y * W;
+            rmin = min(rmin, y); rmax = max(rmax, y); cmin = min(cmin, x); cmax = max(cmax, x);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rmin = min(rmin, __shfl_xor_sync(0xFFFFFFFFu, rmin, o)); rmax = max(rmax, __shfl_xor_sync(0xFFFFFFFFu, rmax, o));
+        cmin = min(cmin, __shfl_xor_sync(0xFFFFFFFFu, cmin, o)); cmax = max(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && rmax >= 0) {
+        atomicMin(&s_rmin, rmin); atomicMax(&s_rmax, rmax); atomicMin(&s_cmin, cmin); atomicMax(&s_cmax, cmax);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float inf = __int_as_float(0x7f800000);
+        float c0 = 160.0f, c1 = 160.0f, sz = 100.0f, xmin = inf, xmax = -inf, ymin = inf, ymax = -inf;
+        if (s_rmax >= 0) {
+            xmin = (float)s_rmin; xmax = (float)s_rmax; ymin = (float)s_cmin; ymax = (float)s_cmax;
+            c0 = __fmul_rn(0.5f, __fadd_rn(xmax, xmin));
+            c1 = __fmul_rn(0.5f, __fadd_rn(ymax, ymin));
+            sz = fmaxf(__fsub_rn(xmax, xmin), __fsub_rn(ymax, ymin));
+        }
+        center[2 * b] = c0; center[2 * b + 1] = c1;
+        if (bb) { bb[4 * b] = xmin; bb[4 * b + 1] = xmax; bb[4 * b + 2] = ymin; bb[4 * b + 3] = ymax; }   // [[x_min, x_max], [y_min, y_max]] (:303)
+        if (crop_size) crop_size[b] = sz;
+    }
+}
+int launch_mask_bbox(const float* mask, int B, int H, int W, float* center, float* bb, float* crop_size, cudaStream_t s) {
+    mask_bbox_kernel<<<B, 512, 0, s>>>(mask, H, W, center, bb, crop_size);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// NetworkOps.leaky_relu (utils/general.py:31-33): tf.maximum(x, 0.01 x)
+__global__ void leaky_relu_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        v.x = fmaxf(v.x, __fmul_rn(kNegSlope, v.x)); v.y = fmaxf(v.y, __fmul_rn(kNegSlope, v.y));
+        v.z = fmaxf(v.z, __fmul_rn(kNegSlope, v.z)); v.w = fmaxf(v.w, __fmul_rn(kNegSlope, v.w));
+        reinterpret_cast<float4*>(y)[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (n4 << 2) + threadIdx.x;
+        y[i] = fmaxf(x[i], __fmul_rn(kNegSlope, x[i]));
+    }
+}
+int launch_leaky_relu(const float* x, float* y, int64_t n, cudaStream_t s) {
+    H3D_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "leaky_relu: pointers must be 16-byte aligned");
+    leaky_relu_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(n / 4 + 1, 256), 148 * 16)), 256, 0, s>>>(x, y, n);
+    H3D_CHECK_LAUNCH();
+    return H3D_OK;
+}
+
+// _flip_right_hand (nets/ColorHandPose3DNetwork.py:336-361): z -> -z where cond_right[b] != 0
+__global__ void flip_right_hand_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ cond_right, int B, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 63) return;
+    const int b = i / 63, j = (i - b * 63) % 3;
+    const float v = xyz[i];
+    out[i] = (j == 2 && cond_right[b]) ? -v : v;
+}
+int launch_flip_right_hand(const float* xyz, const uint8_t* cond_right, int B, float* out, cudaStream_t s) {
+    flip_right_hand_kernel<<<ceil_div(B * 63, 256), 256, 0, s>>>(xyz, cond_right, B, out);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }

@@ -20,7 +20,11 @@ def shard_range(total: int, rank: int, world: int):
 
 
 def pack_records(coord3d, keypoints_uv, center, scale_crop):
+    """[B,108] records.  CUDA tensors: ONE kernel (h3d_pack_records); CPU tensors (gloo tests, host-side tools): torch.cat."""
     B = coord3d.shape[0]
+    if coord3d.is_cuda:
+        from . import runtime
+        return runtime.default_context(coord3d.device).pack_records(coord3d, keypoints_uv, center, scale_crop)
     uv_bits = keypoints_uv.reshape(B, 42).contiguous().view(torch.float32)    # bit-cast, gathered bitwise
     return torch.cat([coord3d.reshape(B, 63), uv_bits, center.reshape(B, 2), scale_crop.reshape(B, 1)], dim=1).contiguous()
 
@@ -71,12 +75,18 @@ class P2PGather:
         self.buf = symm_mem.empty(2 * self.stride, dtype=torch.float32, device=ctx.device)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        # dedicated signal words (one uint32 per peer): NOT the handle's signal pad, which hdl.barrier() uses
+        self.sig = symm_mem.empty(max(64, self.world), dtype=torch.int32, device=ctx.device)
+        self.sig.zero_()
+        self.sig_hdl = symm_mem.rendezvous(self.sig, self.group)
         self.mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if use_multicast else 0
         self.epoch = 0
+        torch.cuda.synchronize(ctx.device)
         self.hdl.barrier()
 
     def gather(self, coord3d, keypoints_uv, center, scale_crop):
-        """-> [world * B, 108] view of the local gather buffer holding all ranks' records (rank-major)."""
+        """-> [world * B, 108] records of all ranks (rank-major): a view of the local gather buffer when B == max_batch, else
+        the per-rank slots' first B rows (every rank must then pass the same B; ragged shards read `slots()` instead)."""
         from . import _lib
         B = coord3d.shape[0]
         if B > self.max_batch:
@@ -86,8 +96,15 @@ class P2PGather:
         cs = torch.cuda.current_stream().cuda_stream
         _lib.check(self.ctx.lib.h3d_gather_records_p2p(
             self.ctx.h, C.c_void_p(coord3d.data_ptr()), C.c_void_p(keypoints_uv.data_ptr()), C.c_void_p(center.data_ptr()),
-            C.c_void_p(scale_crop.data_ptr()), B, C.c_void_p(int(self.hdl.buffer_ptrs_dev)), C.c_void_p(int(self.hdl.signal_pad_ptrs_dev)),
-            C.c_uint64(self.mc), self.rank, self.world, C.c_uint32(self.epoch), C.c_int64(self.stride), C.c_void_p(cs)),
-            "h3d_gather_records_p2p")
+            C.c_void_p(scale_crop.data_ptr()), B, self.max_batch, C.c_void_p(int(self.hdl.buffer_ptrs_dev)),
+            C.c_void_p(int(self.sig_hdl.buffer_ptrs_dev)), C.c_uint64(self.mc), self.rank, self.world, C.c_uint32(self.epoch),
+            C.c_int64(self.stride), C.c_void_p(cs)), "h3d_gather_records_p2p")
+        s = self.slots()
+        if B == self.max_batch:
+            return s.view(self.world * B, RECORD_FLOATS)
+        return s[:, :B].reshape(self.world * B, RECORD_FLOATS)
+
+    def slots(self):
+        """[world, max_batch, 108] view of the current parity of the local gather buffer (rank r's records in slot r)."""
         off = (self.epoch & 1) * self.stride
-        return self.buf[off: off + self.world * B * RECORD_FLOATS].view(self.world * B, RECORD_FLOATS)
+        return self.buf[off: off + self.stride].view(self.world, self.max_batch, RECORD_FLOATS)

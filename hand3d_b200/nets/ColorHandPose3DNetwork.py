@@ -108,5 +108,6 @@ class ColorHandPose3DNetwork(object):
     @staticmethod
     def _flip_right_hand(coords_xyz_canonical, cond_right):
         """ Mirrors z where cond_right is true (reference :336-361). """
-        mirrored = torch.stack([coords_xyz_canonical[..., 0], coords_xyz_canonical[..., 1], -coords_xyz_canonical[..., 2]], -1)
-        return torch.where(cond_right, mirrored, coords_xyz_canonical)
+        B = coords_xyz_canonical.shape[0]
+        cond = cond_right.reshape(B, -1)[:, 0] if torch.is_tensor(cond_right) else torch.as_tensor(cond_right).reshape(B, -1)[:, 0]
+        return runtime.default_context().flip_right_hand(coords_xyz_canonical, cond.to(coords_xyz_canonical.device))

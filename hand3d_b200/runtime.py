@@ -63,9 +63,18 @@ class Context:
         _lib.check(self.lib.h3d_set_precision(self.h, p), "h3d_set_precision")
         self.precision = p
 
+    def set_tuning(self, key, value):
+        """Kernel-selection switch (process-wide, see include/hand3d_b200.h: h3d_set_tuning); drops this context's plans."""
+        _lib.check(self.lib.h3d_set_tuning(self.h, key.encode(), int(value)), "h3d_set_tuning(%s)" % key)
+
     @property
     def launch_count(self):
         return int(self.lib.h3d_launch_count(self.h))
+
+    def check_errors(self):
+        """Raises if a kernel reported a device-side timeout (bounded barrier wait, missing gather peer); see h3d_check_errors."""
+        code = C.c_int(0)
+        _lib.check(self.lib.h3d_check_errors(self.h, C.byref(code)), "device-side error word = %d" % code.value)
 
     def profile_begin(self):
         _lib.check(self.lib.h3d_profile_begin(self.h), "h3d_profile_begin")
@@ -85,6 +94,7 @@ class Context:
                 raise ValueError(_lib.last_error())
             _lib.check(rc, "h3d_load_weight(%s)" % name)
             self.weights[name] = a
+            self.__dict__.get("_dev_w", {}).pop(name, None)    # the operator-level device copy follows the reload
 
     def scope_ready(self, scope):
         return bool(self.lib.h3d_scope_ready(self.h, scope.encode()))
@@ -102,6 +112,9 @@ class Context:
         kB, kH, kW = max(B, self._ws_key[0]), max(H, self._ws_key[1]), max(W, self._ws_key[2])
         if (kB, kH, kW) == self._ws_key and self._ws is not None:
             return
+        if getattr(self, "_graphs_captured", 0):
+            raise RuntimeError("the workspace cannot grow (to B=%d, %dx%d) after capture_pipeline(): captured CUDA graphs hold its "
+                               "pointers; call release_graphs() first or size it up front with ensure_workspace()" % (kB, kH, kW))
         need = int(self.lib.h3d_workspace_bytes(self.h, kB, kH, kW))
         if need < 0:
             _lib.check(need, "h3d_workspace_bytes")
@@ -129,6 +142,18 @@ class Context:
         _lib.check(self.lib.h3d_posenet_forward(self.h, _ptr(image_crop), B, H, W, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
                                                 _stream()), "h3d_posenet_forward")
         return outs
+
+    def pose2d(self, image_crop, outputs="all"):
+        """inference_pose2d + x8 up-sampling + detect_keypoints (eval2d_gt_cropped.py:45-50,78).  Returns dict with
+        keypoints_scoremap [B,H,W,21] (None with outputs="keypoints" and crops <= 256x256) and keypoints_uv [B,21,2] int32."""
+        image_crop = _chk_f32(image_crop, "image_crop", 4)
+        B, H, W, _ = image_crop.shape
+        self.ensure_workspace(B, H if H > 256 else 8, W if W > 256 else 8)
+        big = outputs == "all" or H > 256 or W > 256
+        sm = torch.empty((B, H, W, 21), dtype=torch.float32, device=image_crop.device) if big else None
+        uv = torch.empty((B, 21, 2), dtype=torch.int32, device=image_crop.device)
+        _lib.check(self.lib.h3d_pose2d_forward(self.h, _ptr(image_crop), B, H, W, _ptr(sm), _ptr(uv), _stream()), "h3d_pose2d_forward")
+        return {"keypoints_scoremap": sm, "keypoints_uv": uv}
 
     def lifting(self, scoremap32, hand_side, variant="proposed"):
         scoremap32 = _chk_f32(scoremap32, "scoremap", 4)
@@ -192,7 +217,12 @@ class Context:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             results = self.pipeline(image, hand_side, with_pose3d, outputs=outputs)
+        self._graphs_captured = getattr(self, "_graphs_captured", 0) + 1    # the graph bakes in workspace pointers: no growth from now on
         return graph.replay, results
+
+    def release_graphs(self):
+        """Declares every graph returned by capture_pipeline() dead (the caller must drop them); the workspace may grow again."""
+        self._graphs_captured = 0
 
     # ---- operators ---------------------------------------------------------------------------
     def conv2d(self, x, w, b, stride=1, leaky=False):
@@ -205,6 +235,7 @@ class Context:
         return y
 
     def conv2d_tc(self, x, w_host, b_host, leaky=False, precision="bf16x3", stride=1):
+        """Host-weight convenience form (packs, uploads and frees the weights around the call)."""
         x = _chk_f32(x, "x", 4)
         w = np.ascontiguousarray(w_host, np.float32); b = np.ascontiguousarray(b_host, np.float32)
         B, H, W, Cin = x.shape
@@ -216,6 +247,58 @@ class Context:
                                                   B, H, W, Cin, Cout, k, stride, int(leaky), PRECISIONS[precision], _stream()),
                    "h3d_conv2d_tc_strided")
         return y
+
+    def pack_conv(self, w_host, b_host, precision="bf16x3"):
+        """Packs HWIO weights once for conv2d_tc_packed (the enqueue-only tensor-core operator)."""
+        w = np.ascontiguousarray(w_host, np.float32); b = np.ascontiguousarray(b_host, np.float32)
+        k, _, Cin, Cout = w.shape
+        h = C.c_void_p()
+        _lib.check(self.lib.h3d_pack_conv_weights(self.h, w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), k, Cin, Cout,
+                                                  PRECISIONS[precision], C.byref(h)), "h3d_pack_conv_weights")
+        return PackedConv(self, h, k, Cin, Cout)
+
+    def conv2d_tc_packed(self, x, packed, leaky=False, stride=1):
+        x = _chk_f32(x, "x", 4)
+        B, H, W, Cin = x.shape
+        if Cin != packed.Cin:
+            raise ValueError("conv2d_tc_packed: input has %d channels, weights expect %d" % (Cin, packed.Cin))
+        y = torch.empty((B, H // stride, W // stride, packed.Cout), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.h3d_conv2d_tc_packed(self.h, _ptr(x), packed.h, _ptr(y), B, H, W, stride, int(leaky), _stream()),
+                   "h3d_conv2d_tc_packed")
+        return y
+
+    def leaky_relu(self, x):
+        x = _chk_f32(x, "x")
+        y = torch.empty_like(x)
+        _lib.check(self.lib.h3d_leaky_relu_f32(self.h, _ptr(x), _ptr(y), x.numel(), _stream()), "h3d_leaky_relu_f32")
+        return y
+
+    def calc_center_bb(self, mask):
+        """mask [B,H,W] float32 -> (center [B,2], bb [B,2,2], crop_size [B,1]) (utils/general.py:271-328)."""
+        mask = _chk_f32(mask, "binary_class_mask", 3)
+        B, H, W = mask.shape
+        dev = mask.device
+        center = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        bb = torch.empty((B, 2, 2), dtype=torch.float32, device=dev)
+        size = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.h3d_calc_center_bb(self.h, _ptr(mask), B, H, W, _ptr(center), _ptr(bb), _ptr(size), _stream()), "h3d_calc_center_bb")
+        return center, bb, size
+
+    def flip_right_hand(self, coords_xyz, cond_right):
+        coords_xyz = _chk_f32(coords_xyz, "coords_xyz_canonical", 3)
+        B = coords_xyz.shape[0]
+        cond = cond_right.reshape(B).to(torch.uint8).contiguous()
+        out = torch.empty_like(coords_xyz)
+        _lib.check(self.lib.h3d_flip_right_hand(self.h, _ptr(coords_xyz), _ptr(cond), B, _ptr(out), _stream()), "h3d_flip_right_hand")
+        return out
+
+    def pack_records(self, coord3d, keypoints_uv, center, scale_crop):
+        """[B,108] float32 records (coord3d | key-points bit-cast | center | scale_crop), one kernel."""
+        B = coord3d.shape[0]
+        out = torch.empty((B, 108), dtype=torch.float32, device=coord3d.device)
+        _lib.check(self.lib.h3d_pack_records(self.h, _ptr(coord3d.contiguous()), _ptr(keypoints_uv.contiguous()), _ptr(center.contiguous()),
+                                             _ptr(scale_crop.contiguous()), B, _ptr(out), _stream()), "h3d_pack_records")
+        return out
 
     def max_pool(self, x):
         x = _chk_f32(x, "x", 4)
@@ -324,6 +407,20 @@ class Context:
         _lib.check(self.lib.h3d_rotate_canonical(self.h, _ptr(coord_can), _ptr(uxyz), _ptr(hand_side), B, _ptr(rot), _ptr(out),
                                                  _stream()), "h3d_rotate_canonical")
         return rot, out
+
+
+class PackedConv:
+    """Handle of h3d_pack_conv_weights (freed with the object; the free waits for kernels still reading the planes)."""
+    def __init__(self, ctx, h, k, Cin, Cout):
+        self.ctx, self.h, self.k, self.Cin, self.Cout = ctx, h, k, Cin, Cout
+
+    def __del__(self):
+        try:
+            if self.h and getattr(self.ctx, "h", None):
+                self.ctx.lib.h3d_free_packed_conv(self.ctx.h, self.h)
+            self.h = None
+        except Exception:
+            pass
 
 
 _default = {}

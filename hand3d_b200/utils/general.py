@@ -42,7 +42,7 @@ class NetworkOps(object):
 
     @classmethod
     def leaky_relu(cls, tensor, name='relu'):
-        return torch.maximum(tensor, cls.neg_slope_of_relu * tensor)
+        return runtime.default_context().leaky_relu(tensor)
 
     @classmethod
     def conv(cls, in_tensor, layer_name, kernel_size, stride, out_chan, trainable=True):
@@ -119,32 +119,13 @@ def single_obj_scoremap(scoremap):
 
 
 def calc_center_bb(binary_class_mask):
-    """utils/general.py:271-328: mask [B,H,W,1] -> (center [B,2], bb [B,2,2], crop_size [B,1]).
-
-    Runs the bbox tail of the seg kernel on the given mask by feeding it as logits (0, +/-1) with the
-    growth seed inside the mask being irrelevant: the mask is first reduced on device with torch ops."""
+    """utils/general.py:271-328: mask [B,H,W,1] / [B,H,W] -> (center [B,2], bb [B,2,2], crop_size [B,1]); one kernel
+    (h3d_calc_center_bb): bounding box of the pixels with int(mask) == 1, the reference's fall-backs for an empty mask."""
     m = binary_class_mask
     if m.dim() == 4:
         m = m.squeeze(3)
     assert m.dim() == 3, "binary_class_mask must be 3D."
-    m = m.to(torch.int32) == 1
-    B, H, W = m.shape
-    rows = m.any(dim=2)
-    cols = m.any(dim=1)
-    ar_h = torch.arange(H, device=m.device).expand(B, H)
-    ar_w = torch.arange(W, device=m.device).expand(B, W)
-    big = 1 << 30
-    x_min = torch.where(rows, ar_h, big).amin(1).float(); x_max = torch.where(rows, ar_h, -1).amax(1).float()
-    y_min = torch.where(cols, ar_w, big).amin(1).float(); y_max = torch.where(cols, ar_w, -1).amax(1).float()
-    empty = ~rows.any(dim=1)
-    center = torch.stack([0.5 * (x_max + x_min), 0.5 * (y_max + y_min)], 1)
-    center[empty] = 160.0
-    size = torch.maximum(x_max - x_min, y_max - y_min).unsqueeze(1)
-    size[empty] = 100.0
-    inf = float("inf")
-    bb = torch.stack([torch.stack([x_min, x_max], 1), torch.stack([y_min, y_max], 1)], 1)
-    bb[empty] = torch.tensor([[inf, -inf], [inf, -inf]], device=m.device)
-    return center, bb, size
+    return runtime.default_context().calc_center_bb(m.to(torch.float32).contiguous())
 
 
 def detect_keypoints(scoremaps):

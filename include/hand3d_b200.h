@@ -9,10 +9,15 @@
  * Conventions:
  *   - plain C, raw DEVICE pointers unless a parameter is named host_*, explicit sizes, NHWC fp32
  *     tensors exactly as the reference lays them out;
- *   - every call ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns at once;
+ *   - every compute call ENQUEUES work on `stream` (a cudaStream_t passed as void*) and returns at once: no device
+ *     synchronisation, no per-call cudaMalloc / cudaFree (capturable into a CUDA graph).  The caller owns all tensors and the
+ *     workspace arena of the stage entry points; operator entry points borrow scratch from a context-owned buffer that only
+ *     ever grows (old blocks are retired until h3d_destroy), so consecutive operator calls on one context must be ordered by
+ *     the caller when they run on different streams.  Documented exceptions: h3d_load_weight, h3d_pack_conv_weights and the
+ *     host-weight convenience entry h3d_conv2d_tc(_strided) upload weights (allocate + copy);
  *   - return 0 on success, negative H3D_E* on failure; h3d_last_error() gives a thread-local message;
- *   - no allocation inside hot calls: the caller owns all tensors and the workspace arena;
- *   - one h3d_ctx per device, used from one host thread at a time (one rank <-> one GPU);
+ *   - one h3d_ctx per device, used from one host thread at a time (one rank <-> one GPU); every entry makes the context's device
+ *     current for the duration of the call and restores the caller's device;
  *   - there is NO CPU fallback: without a usable sm_100a device every compute call fails with
  *     H3D_ENODEVICE.
  */
@@ -65,6 +70,16 @@ H3D_API int h3d_create(h3d_ctx** out, int device);
 H3D_API int h3d_destroy(h3d_ctx* ctx);
 H3D_API int h3d_set_precision(h3d_ctx* ctx, int precision);
 H3D_API int h3d_get_precision(const h3d_ctx* ctx);
+/* Kernel-selection switches for A/B measurements and forced-variant tests (process-wide; initialised ONCE from the H3D_*
+ * environment variables when the library is first used, never read on a launch path).  Keys: "tc_2cta" (-1 policy / 0 / 1),
+ * "tc_bn" (0 policy / 64 / 128 / 256), "tc_c64", "tc_c64x2", "tc_pair128", "tc_stack", "tc_chunk_kb", "no_side_stream",
+ * "no_pool_fusion", "lift_direct", "c3_ffma".  ctx may be NULL; when given, its cached layer plans are dropped. */
+H3D_API int h3d_set_tuning(h3d_ctx* ctx, const char* key, int value);
+/* Device-side error word (pinned host memory, survives a trapped kernel): 0 = none; 1-5 = a bounded mbarrier wait of a tcgen05
+ * convolution kernel timed out (1 TMA producer / free stage, 2 MMA issuer / drained accumulator, 3 MMA issuer / TMA stage,
+ * 4 epilogue / finished accumulator, 5 MMA issuer / resident weights) and the kernel trapped; 100 + r = h3d_gather_records_p2p
+ * never saw peer rank r's records.  Returns H3D_OK or H3D_ECUDA (message in h3d_last_error); *code (optional) = the word. */
+H3D_API int h3d_check_errors(h3d_ctx* ctx, int* code);
 /* Number of kernels this library launched through `ctx` since creation (bench "gpu_launches"). */
 H3D_API int64_t h3d_launch_count(const h3d_ctx* ctx);
 
@@ -117,13 +132,20 @@ H3D_API int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* 
                          float* keypoints_scoremap, float* keypoint_coord3d, int32_t* keypoints_uv,
                          uint8_t* hand_mask, void* stream);
 
+/* ColorHandPose3DNetwork.inference_pose2d + the x8 up-sampling and key-point detection of eval2d_gt_cropped.py:45-50,78:
+ * image_crop [B,Hc,Wc,3] -> keypoints_scoremap [B,Hc,Wc,21] (tf.image.resize_images of the last stage; may be NULL when
+ * Hc, Wc <= 256: kept in the workspace) and keypoints_uv [B,21,2] int32 (row, col) (may be NULL). */
+H3D_API int h3d_pose2d_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, int Wc, float* keypoints_scoremap,
+                               int32_t* keypoints_uv, void* stream);
+
 /* ---- operator entry points (utils/general.py) ------------------------------------------------- */
 /* NetworkOps.conv / conv_relu (utils/general.py:36-59): tf.nn.conv2d SAME + bias (+ leaky 0.01).
  * fp32 CUDA-core kernel; x [B,H,W,Cin], w HWIO [k,k,Cin,Cout] (device), y [B,ceil(H/s),ceil(W/s),Cout]. */
 H3D_API int h3d_conv2d_f32(h3d_ctx* ctx, const float* x, const float* w_hwio, const float* bias, float* y,
                    int B, int H, int W, int Cin, int Cout, int ksize, int stride, int leaky, void* stream);
 /* Same op on the tcgen05 tensor-core path (stride 1, Cin and Cout multiples of 64 after internal padding;
- * ksize in {1,3,7}); host_w_hwio / host_bias are HOST pointers (packed per call: test / tuning entry). */
+ * ksize in {1,3,5,7}); host_w_hwio / host_bias are HOST pointers: this convenience entry packs, uploads and frees the weights
+ * around the call (allocates, and the free waits for the kernel) -- use h3d_pack_conv_weights + h3d_conv2d_tc_packed on a hot path. */
 H3D_API int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y,
                   int B, int H, int W, int Cin, int Cout, int ksize, int leaky, int precision, void* stream);
 /* Same with the `stride` argument of NetworkOps.conv (utils/general.py:36-53): 1, or 2 with even H and W and ksize >= 3 (the lifting
@@ -131,6 +153,17 @@ H3D_API int h3d_conv2d_tc(h3d_ctx* ctx, const float* x, const float* host_w_hwio
  * for stride 2 on an even size, i.e. the result is the stride-1 output at the odd pixels. */
 H3D_API int h3d_conv2d_tc_strided(h3d_ctx* ctx, const float* x, const float* host_w_hwio, const float* host_bias, float* y,
                           int B, int H, int W, int Cin, int Cout, int ksize, int stride, int leaky, int precision, void* stream);
+/* Enqueue-only form of the tensor-core convolution: weights packed once (HOST pointers, HWIO / [Cout]) into a handle ... */
+typedef struct h3d_packed_conv h3d_packed_conv;
+H3D_API int h3d_pack_conv_weights(h3d_ctx* ctx, const float* host_w_hwio, const float* host_bias, int ksize, int Cin, int Cout,
+                                  int precision, h3d_packed_conv** out);
+H3D_API int h3d_free_packed_conv(h3d_ctx* ctx, h3d_packed_conv* packed);
+/* ... and applied any number of times: x [B,H,W,Cin] -> y [B,H/stride,W/stride,Cout]; operand planes live in the context's
+ * operator scratch (no allocation, no synchronisation). */
+H3D_API int h3d_conv2d_tc_packed(h3d_ctx* ctx, const float* x, const h3d_packed_conv* packed, float* y, int B, int H, int W,
+                                 int stride, int leaky, void* stream);
+/* NetworkOps.leaky_relu (utils/general.py:31-33): y = max(x, 0.01 x), n elements, 16-byte aligned pointers. */
+H3D_API int h3d_leaky_relu_f32(h3d_ctx* ctx, const float* x, float* y, int64_t n, void* stream);
 /* NetworkOps.max_pool (utils/general.py:62-65): 2x2 / 2 VALID. */
 H3D_API int h3d_maxpool2x2_f32(h3d_ctx* ctx, const float* x, float* y, int B, int H, int W, int C, void* stream);
 /* NetworkOps.fully_connected(_relu) (utils/general.py:113-136): y = x[B,in] @ w[in,out] + b. */
@@ -147,6 +180,11 @@ H3D_API int h3d_avgpool8(h3d_ctx* ctx, const float* x, float* y, int B, int H, i
  * scale_crop [B,1].  H,W <= 512, W % 32 == 0 not required. */
 H3D_API int h3d_seg_postprocess(h3d_ctx* ctx, const float* logits, int B, int H, int W, uint8_t* hand_mask,
                         int32_t* max_loc, float* center, float* crop_size, float* scale_crop, void* stream);
+/* calc_center_bb (utils/general.py:271-328) on an arbitrary mask [B,H,W] fp32 (pixels with int(mask) == 1 count):
+ * center [B,2] (row, col), bb [B,2,2] = [[x_min, x_max], [y_min, y_max]] (optional), crop_size [B,1] (optional); an empty mask
+ * gives center (160, 160), crop_size 100, bb (+inf, -inf) as the reference's tf.cond fall-backs do. */
+H3D_API int h3d_calc_center_bb(h3d_ctx* ctx, const float* mask, int B, int H, int W, float* center, float* bb, float* crop_size,
+                               void* stream);
 /* crop_image_from_xy (utils/general.py:163-196) incl. tf.image.crop_and_resize bilinear/extrapolation 0. */
 H3D_API int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float* center, const float* scale,
                            float* image_crop, int B, int H, int W, int C, int crop_size, void* stream);
@@ -154,17 +192,22 @@ H3D_API int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float
  * first occurrence of the maximum in row-major order. */
 H3D_API int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int C,
                          int32_t* keypoints_uv, void* stream);
-/* Multi-GPU result exchange (the reference has no multi-GPU code): packs this rank's per-image records
- * (coord3d [B,21,3] | keypoints_uv [B,21,2] i32 | center [B,2] | scale_crop [B,1] = 108 words) and all-gathers them over
- * NVLink peer memory in ONE kernel.  peer_buffers / peer_signals are DEVICE arrays of `world` device pointers: the
- * symmetric gather buffers ([2][world*B][108] floats each, parity_stride_floats = world*B*108 or more) and uint32 signal pads
- * (>= world entries, zero-initialised) of all ranks, e.g. from torch.distributed._symmetric_memory.  multicast_ptr: NVSwitch
- * multicast address of the gather buffer or 0.  epoch must increase by 1 per call (start at 1).  On completion (stream order)
- * the local buffer's parity (epoch & 1) holds all ranks' records in rank-major order. */
+/* Per-image result record: coord3d [21,3] | keypoints_uv [21,2] i32 (bit-cast) | center [2] | scale_crop [1]
+ * = 108 words = 432 B.  records [B,108]. */
+H3D_API int h3d_pack_records(h3d_ctx* ctx, const float* coord3d, const int32_t* keypoints_uv, const float* center,
+                             const float* scale_crop, int B, float* records, void* stream);
+/* Multi-GPU result exchange (the reference has no multi-GPU code): packs this rank's records and all-gathers
+ * them over NVLink peer memory in ONE kernel.  peer_buffers / peer_signals are DEVICE arrays of `world` device pointers: the
+ * symmetric gather buffers ([2 parities][world][max_batch][108] floats each, parity_stride_floats >= world*max_batch*108) and
+ * DEDICATED uint32 signal words (>= world entries, zero-initialised, used by nothing else) of all ranks, e.g. two
+ * torch.distributed._symmetric_memory allocations.  Rank r's B <= max_batch records land in slot r (offset r*max_batch*108) of
+ * every rank's buffer, so ranks may hold different B.  multicast_ptr: NVSwitch multicast address of the gather buffer or 0.
+ * epoch must increase by 1 per call (start at 1).  On completion (stream order) the local buffer's parity (epoch & 1) holds all
+ * ranks' slots.  A peer that never signals (~10 s) sets the context's error word (h3d_check_errors) instead of hanging. */
 H3D_API int h3d_gather_records_p2p(h3d_ctx* ctx, const float* coord3d, const int32_t* keypoints_uv, const float* center,
-                                   const float* scale_crop, int B, const uint64_t* peer_buffers, const uint64_t* peer_signals,
-                                   uint64_t multicast_ptr, int rank, int world, uint32_t epoch, int64_t parity_stride_floats,
-                                   void* stream);
+                                   const float* scale_crop, int B, int max_batch, const uint64_t* peer_buffers,
+                                   const uint64_t* peer_signals, uint64_t multicast_ptr, int rank, int world, uint32_t epoch,
+                                   int64_t parity_stride_floats, void* stream);
 /* On-device decode of the dataset readers' fixed-length records.  dataset 0 = RHD
  * (data/BinaryDbReader.py:103-208; 410520-byte records: header [B,219] = 42x3 xyz | 42x2 uv | 3x3 K, image [B,320,320,3],
  * mask [B,320,320] u8, visibility [B,42] u8), dataset 1 = STB (data/BinaryDbReaderSTB.py:99-185; 922104-byte records:
@@ -183,6 +226,8 @@ H3D_API int h3d_bone_rel_trafo_inv(h3d_ctx* ctx, const float* coords_rel, float*
 /* _get_rot_mat + _flip_right_hand + matmul (nets/ColorHandPose3DNetwork.py:239-247,311-384). */
 H3D_API int h3d_rotate_canonical(h3d_ctx* ctx, const float* coord_can, const float* uxyz, const float* hand_side,
                          int B, float* rot_mat, float* coord_out, void* stream);
+/* _flip_right_hand (nets/ColorHandPose3DNetwork.py:336-361): out = coords with z negated where cond_right[b] != 0 (u8 [B]). */
+H3D_API int h3d_flip_right_hand(h3d_ctx* ctx, const float* coords_xyz, const uint8_t* cond_right, int B, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,8 +3,9 @@ reference (lmb-freiburg/hand3d) relies on.
 
 PARITY UNPINNED: the reference has no tests / golden tensors and TensorFlow 1.3 cannot be
 installed in this image, so this file restates the *published* TF 1.3
-kernel behaviour and is pinned only by the hand-derivable known-answer
-vectors in tests/test_oracle_kat.py.
+kernel behaviour and is pinned by the hand-derivable known-answer
+vectors in tests/test_oracle_kat.py, by the vectors of TensorFlow's own op tests and by independent
+implementations (scipy, scalar transcriptions of the published kernels) in tests/test_tf_published_vectors.py.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this package.  The product (hand3d_b200/) never does.
@@ -134,9 +135,43 @@ def dilation2d_21(obj):
     return d + obj.dtype.type(1.0 / 441.0)
 
 
-def crop_and_resize(image, boxes, crop_h: int, crop_w: int):
+def dilation2d(x, filt, strides=(1, 1), rates=(1, 1), padding="SAME"):
+    """tf.nn.dilation2d, general form (TF 1.3 core/kernels/dilation_ops.cc, DilationOp / ParseSizes): grey-scale max-sum
+    correlation  out[b,y,x,c] = max_{dy,dx in bounds} in[b, y*sy - pad_top + ry*dy, x*sx - pad_left + rx*dx, c] + filter[dy,dx,c],
+    out-of-bounds taps skipped, SAME padding computed on the dilated ("effective") filter size, before = total // 2.
+    Brute-force loops: used to pin dilation2d_21 (the 21x21 / 441 case of utils/general.py:249,259) and for TF's op-test vectors."""
+    x = np.asarray(x); filt = np.asarray(filt)
+    B, H, W, C = x.shape
+    fh, fw, fc = filt.shape
+    assert fc == C
+    sy, sx = strides; ry, rx = rates
+    eh, ew = (fh - 1) * ry + 1, (fw - 1) * rx + 1
+    if padding == "SAME":
+        Ho, Wo = -(-H // sy), -(-W // sx)
+        pt = max((Ho - 1) * sy + eh - H, 0) // 2
+        pl = max((Wo - 1) * sx + ew - W, 0) // 2
+    else:
+        Ho, Wo = (H - eh) // sy + 1, (W - ew) // sx + 1
+        pt = pl = 0
+    out = np.full((B, Ho, Wo, C), -np.inf, dtype=x.dtype)
+    for dy in range(fh):
+        for dx in range(fw):
+            for y in range(Ho):
+                iy = y * sy - pt + ry * dy
+                if iy < 0 or iy >= H:
+                    continue
+                for xo in range(Wo):
+                    ix = xo * sx - pl + rx * dx
+                    if ix < 0 or ix >= W:
+                        continue
+                    out[:, y, xo, :] = np.maximum(out[:, y, xo, :], x[:, iy, ix, :] + filt[dy, dx, :])
+    return out
+
+
+def crop_and_resize(image, boxes, crop_h: int, crop_w: int, extrapolation_value=0.0):
     """tf.image.crop_and_resize(image, boxes, box_ind=range(B), [crop_h,crop_w]) -- bilinear,
-    extrapolation_value 0 (TF 1.3 crop_and_resize_op.cc).  boxes [B,4]=(y1,x1,y2,x2) normalised."""
+    extrapolation_value 0 at the reference's call site (TF 1.3 crop_and_resize_op.cc).
+    boxes [B,4]=(y1,x1,y2,x2) normalised."""
     B, H, W, C = image.shape
     f = np.float32
     out = np.zeros((B, crop_h, crop_w, C), dtype=np.float32)
@@ -167,5 +202,5 @@ def crop_and_resize(image, boxes, crop_h: int, crop_w: int):
         bo = bl + (br - bl) * lx
         val = (t + (bo - t) * ly).astype(f)
         mask = (vy.reshape(crop_h, 1, 1) & vx.reshape(1, crop_w, 1))
-        out[b] = np.where(mask, val, f(0))
+        out[b] = np.where(mask, val, f(extrapolation_value))
     return out

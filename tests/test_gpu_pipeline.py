@@ -253,22 +253,6 @@ def test_unknown_variable_and_bad_numerics(ctx):
         ctx.load_weights({"PosePrior/fc_xyz/weights": bad})
 
 
-def test_fp16_fast_mode_tolerance(wd):
-    """BASELINE config 5: single-pass fp16 tensor-core path within 1e-2."""
-    from hand3d_b200 import runtime
-    img = Wt.synthetic_images(2, 320, 320, seed=1)
-    hs = Wt.synthetic_hand_side(2, seed=2)
-    ctx = runtime.default_context()
-    ctx.load_weights(wd)
-    ctx.set_precision("bf16x3")
-    base = ctx.pipeline(_dev(img), _dev(hs), True)
-    ctx.set_precision("fp16")
-    fast = ctx.pipeline(_dev(img), _dev(hs), True, force_center=base["center"], force_scale=base["scale_crop"])
-    assert (fast["keypoints_scoremap"] - base["keypoints_scoremap"]).abs().max().item() < 1e-2
-    assert (fast["keypoint_coord3d"] - base["keypoint_coord3d"]).abs().max().item() < 1e-2
-    ctx.set_precision("bf16x3")
-
-
 def test_example_drivers_run():
     """The run.py / eval2d.py shaped drivers (examples/) execute end to end on synthetic data."""
     import os

@@ -23,7 +23,18 @@ CASES = [  # B,H,W,Cin,Cout,k
     (3, 64, 64, 64, 64, 3),     # 64 -> 64: more tiles than fit one wave of the A ring
     (2, 24, 48, 64, 128, 3),    # 64 -> 128 (conv2_1): two 64-channel groups, CTAs split between them
     (4, 80, 80, 128, 256, 3),   # enough tiles (200) for the CTA-pair kernel to be chosen by the policy itself
+    (1, 24, 16, 64, 64, 3),     # 64 -> 64 on a CTA pair: odd number of pixel tiles (the last pair's second tile is out of range)
+    (2, 48, 32, 128, 128, 3),   # Cout = 128: N-stacked CTA-pair kernel chosen by the policy, 4 K blocks per tap
 ]
+
+
+@pytest.fixture
+def tuning(ctx):
+    """Sets kernel-selection switches for one test and restores the policy defaults afterwards."""
+    defaults = {"tc_2cta": -1, "tc_bn": 0, "tc_c64": 1, "tc_c64x2": 1, "tc_pair128": 1, "tc_stack": 1}
+    yield ctx.set_tuning
+    for k, v in defaults.items():
+        ctx.set_tuning(k, v)
 
 
 @pytest.fixture(scope="module")
@@ -48,10 +59,10 @@ def test_conv2d_tc_vs_oracle(ctx, case, prec):
 
 @pytest.mark.parametrize("prec", ["bf16x3", "fp16", "fp16_f8c"])
 @pytest.mark.parametrize("case", [CASES[3], CASES[4], CASES[6]])
-def test_conv2d_tc_forced_cta_pair(ctx, case, prec, monkeypatch):
-    """Small problems normally fall back to single-CTA tiles; H3D_TC_2CTA=1 forces the cta_group::2 kernel onto them
-    (ragged pairs, odd tile counts, N = 128 / 256 pair tiles)."""
-    monkeypatch.setenv("H3D_TC_2CTA", "1")
+def test_conv2d_tc_forced_cta_pair(ctx, case, prec, tuning):
+    """Small problems normally fall back to single-CTA tiles; tc_2cta = 1 forces the cta_group::2 kernel onto them
+    (ragged pairs, odd tile counts, N = 128 (N-stacked in the 3-pass mode) / 256 pair tiles)."""
+    tuning("tc_2cta", 1)
     B, H, W, Cin, Cout, k = case
     rng = np.random.default_rng(15)
     x = rng.normal(size=(B, H, W, Cin)).astype(f32)
@@ -63,12 +74,31 @@ def test_conv2d_tc_forced_cta_pair(ctx, case, prec, monkeypatch):
     assert err < TOL[prec], "max abs err %.3e (tolerance %.1e)" % (err, TOL[prec])
 
 
+@pytest.mark.parametrize("switch", ["tc_pair128", "tc_c64x2", "tc_c64", "tc_stack"])
+@pytest.mark.parametrize("case", [CASES[2], CASES[4], CASES[7], CASES[9], CASES[11]])
+def test_conv2d_tc_single_cta_variants(ctx, case, switch, tuning):
+    """The kernels the policy no longer picks for these shapes (single-CTA stacked N = 128, single-CTA 64-channel kernel, the
+    generic kernel for 64 -> 64, un-stacked passes) stay correct: they serve the small maps and the single-pass modes."""
+    tuning(switch, 0)
+    B, H, W, Cin, Cout, k = case
+    rng = np.random.default_rng(16)
+    x = rng.normal(size=(B, H, W, Cin)).astype(f32)
+    w = (rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(f32)
+    b = rng.normal(size=Cout).astype(f32)
+    y = ctx.conv2d_tc(torch.from_numpy(x).cuda(), w, b, leaky=True, precision="bf16x3").cpu().numpy()
+    ref = T.leaky_relu(T.conv2d_same(x, w, b, 1, np.float64))
+    err = np.abs(y - ref).max()
+    assert err < TOL["bf16x3"], "max abs err %.3e (tolerance %.1e)" % (err, TOL["bf16x3"])
+
+
 STRIDED = [  # B,H,W,Cin,Cout: the stride-2 layers of the lifting pyramids (nets/ColorHandPose3DNetwork.py:255-258,291-294)
     (2, 32, 32, 32, 32),      # conv_pose_0_2: Cin / Cout padded 32 -> 64
     (3, 16, 16, 64, 64),      # conv_pose_1_2 / conv_vp_0_2 geometry
     (5, 8, 8, 128, 128),      # conv_pose_2_2: (8,8,2) tiles, ragged batch
     (2, 8, 8, 256, 256),      # conv_vp_2_2: CTA-pair kernel
     (1, 12, 20, 21, 40),      # odd channel counts, partial tiles
+    (2, 32, 32, 64, 64),      # 64 -> 64 on a CTA pair with the stride-2 epilogue
+    (2, 32, 32, 128, 128),    # N-stacked CTA-pair kernel with the stride-2 epilogue
 ]
 
 
