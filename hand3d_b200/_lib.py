@@ -59,6 +59,10 @@ SIGNATURES = {
     "h3d_pack_records": (_i, [_p, _p, _p, _p, _p, _i, _p, _p]),
     "h3d_gather_records_p2p": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, C.c_uint64, _i, _i, C.c_uint32, _i64, _p]),
     "h3d_decode_records": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "h3d_rhd_reader_items": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "h3d_stb_reader_items": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "h3d_gaussian_scoremap": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p, _p]),
+    "h3d_canonical_trafo": (_i, [_p, _p, _p, _i, _p, _p, _p, _p]),
     "h3d_eval_keypoint_dist": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
     "h3d_bone_rel_trafo_inv": (_i, [_p, _p, _p, _i, _p]),
     "h3d_rotate_canonical": (_i, [_p, _p, _p, _p, _i, _p, _p, _p]),

@@ -1371,6 +1371,40 @@ int h3d_decode_records(h3d_ctx* ctx, int dataset, const uint8_t* records, int B,
     if (!rc) ctx->launches += 1;
     return rc;
 }
+int h3d_rhd_reader_items(h3d_ctx* ctx, const float* header, const uint8_t* hand_parts, const uint8_t* visibility, int B, int use_wrist_coord,
+                         int hand_crop, int crop_size, float* keypoint_xyz21, float* keypoint_uv21, uint8_t* keypoint_vis21, float* hand_side,
+                         float* keypoint_scale, float* keypoint_xyz21_normed, float* crop_center, float* crop_scale, float* cam_mat, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(header && hand_parts && visibility && hand_side && B > 0 && crop_size > 1, "h3d_rhd_reader_items: bad argument");
+    int rc = launch_rhd_items(header, hand_parts, visibility, B, use_wrist_coord, hand_crop, crop_size, keypoint_xyz21, keypoint_uv21, keypoint_vis21,
+                              hand_side, keypoint_scale, keypoint_xyz21_normed, crop_center, crop_scale, cam_mat, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_stb_reader_items(h3d_ctx* ctx, const float* header, int B, int use_wrist_coord, float* keypoint_xyz21, float* keypoint_uv21,
+                         uint8_t* keypoint_vis21, float* keypoint_scale, float* keypoint_xyz21_normed, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(header && B > 0, "h3d_stb_reader_items: bad argument");
+    int rc = launch_stb_items(header, B, use_wrist_coord, keypoint_xyz21, keypoint_uv21, keypoint_vis21, keypoint_scale, keypoint_xyz21_normed, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_gaussian_scoremap(h3d_ctx* ctx, const float* coords_hw, const uint8_t* valid, int B, int N, int H, int W, float sigma, float* scoremap,
+                          void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(coords_hw && scoremap && B > 0 && H > 0 && W > 0 && sigma > 0.f, "h3d_gaussian_scoremap: bad argument");
+    int rc = launch_gaussian_map(coords_hw, valid, B, N, H, W, sigma, scoremap, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
+int h3d_canonical_trafo(h3d_ctx* ctx, const float* coords_xyz, const uint8_t* cond_right, int B, float* coords_can, float* rot_mat,
+                        float* rot_mat_inv, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(coords_xyz && B > 0, "h3d_canonical_trafo: bad argument");
+    int rc = launch_canonical_trafo(coords_xyz, cond_right, B, coords_can, rot_mat, rot_mat_inv, s);
+    if (!rc) ctx->launches += 1;
+    return rc;
+}
 int h3d_eval_keypoint_dist(h3d_ctx* ctx, const float* gt, const uint8_t* vis, const float* pred, int n, int D, float* dist, void* stream) {
     H3D_OP_PROLOGUE(ctx);
     H3D_REQUIRE(gt && vis && pred && dist && n > 0 && D >= 1 && D <= 4, "h3d_eval_keypoint_dist: bad argument");

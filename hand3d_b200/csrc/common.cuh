@@ -92,6 +92,15 @@ int launch_bone_rel_trafo_inv(const float* rel, float* xyz, int B, cudaStream_t 
 int launch_rotate_canonical(const float* coord_can, const float* uxyz, const float* hand_side, int B, float* rot,
                             float* out, cudaStream_t s);
 
+// ---------------------------------------------------------------- kernels (reader.cu): the dataset readers' forward generators
+int launch_rhd_items(const float* header, const uint8_t* parts, const uint8_t* vis, int B, int use_wrist, int hand_crop, int crop_size,
+                     float* xyz21, float* uv21, uint8_t* vis21, float* hand_side, float* kp_scale, float* xyz21_normed, float* crop_center,
+                     float* crop_scale, float* cam_mat, cudaStream_t s);
+int launch_stb_items(const float* header, int B, int use_wrist, float* xyz21, float* uv21, uint8_t* vis21, float* kp_scale, float* xyz21_normed,
+                     cudaStream_t s);
+int launch_gaussian_map(const float* coords_hw, const uint8_t* valid, int B, int N, int H, int W, float sigma, float* out, cudaStream_t s);
+int launch_canonical_trafo(const float* xyz, const uint8_t* cond_right, int B, float* can, float* rot, float* rot_inv, cudaStream_t s);
+
 // ---------------------------------------------------------------- kernels (conv_direct.cu)
 struct DirectConvArgs {
     const float* x;       // [B,H,W,Cin_total] fp32, channels [cin_off, cin_off+Cin) are read
@@ -151,7 +160,9 @@ struct TcTuning {
     int bn = 0;            // 0 policy, else forced N tile
     int c64 = 1, c64x2 = 1, pair128 = 1, stack = 1;
     int chunk_kb = 0;      // 0 policy
+    int exp = 0;           // timing experiments (wrong results allowed), see TcParams::exp
     int no_side_stream = 0, no_pool_fusion = 0, lift_direct = 0, c3_ffma = 0;
+    int c3_tma = 1;        // first layer: shared-memory staged epilogue + bulk tensor stores (0 = direct 16-byte global stores)
 };
 TcTuning& tc_tuning();
 int tc_set_tuning(const char* key, int value);

@@ -58,6 +58,8 @@ struct TcParams {
     int chunk_kb;   // K blocks accumulated inside the tensor core before the epilogue folds the partial sum into fp32 registers
     int leaky;
     int stack;      // N-stacked passes (generic single-CTA kernel, 3-pass, BN <= 128); 0 = three separate UMMAs per K step
+    int exp;        // timing experiments only (tc_set_tuning("tc_exp")): bit 0 drops the lo*hi UMMA (WRONG results), bit 1 issues the
+                    // UMMAs of a stage grouped by shape instead of interleaved (conv_c64x2_kernel)
     int* err_flag;
 };
 
@@ -136,6 +138,14 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -899,6 +909,214 @@ conv_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------ first layer, TMA-store epilogue
+// conv_c3_tc_kernel spends most of its time in the load / store unit: every epilogue thread owns one pixel and writes its 64-byte
+// channel slices with 16-byte st.global, so each warp-level store touches 32 different 128-byte lines (half a sector each):
+// 2048 LSU cycles per 128-pixel tile (ncu r02b: 2.2 TB/s = 33 % of the HBM roofline, tensor pipe 5 %).  This version stages the
+// output tile in shared memory in the SWIZZLE_128B layout (conflict-free 16-byte st.shared) and writes it with ONE bulk tensor
+// store per plane (cp.async.bulk.tensor, SASS UTMASTG): full 128-byte lines, 8x fewer LSU cycles, partial tiles clipped by TMA.
+// To stay at two CTAs per SM the A operand shrinks: K = 32 needs 64 bytes per row, so A_hi lives in bytes [0,64) and A_lo in
+// bytes [64,128) of ONE 128-byte-row tile (start address + 64 B selects the plane, exactly like a K step).
+constexpr int C3S_A_STAGE_BYTES = A_TILE_BYTES;          // [A_hi | A_lo] interleaved per row
+constexpr int C3S_OUT_BYTES = 2 * A_TILE_BYTES;          // hi plane tile + lo plane tile, 128 rows x 128 B each
+constexpr int C3S_SMEM = C3T_B_BYTES + C3T_STAGES * C3S_A_STAGE_BYTES + C3S_OUT_BYTES + 2 * C3T_PATCH_FLOATS * 4 + 1024 + 256;
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <bool FP16>
+__global__ void __launch_bounds__(C3T_THREADS, 2)
+conv_c3_tma_kernel(const float* __restrict__ x, const float* __restrict__ w, const __grid_constant__ CUtensorMap map_y_hi,
+                   const __grid_constant__ CUtensorMap map_y_lo, const TcParams p) {
+    constexpr uint32_t IDESC_N128 = make_idesc(128, FP16);
+    constexpr uint32_t IDESC_N64 = make_idesc(64, FP16);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bsm = smem;                                   // weights [W_hi ; W_lo], 128 rows x 128 B (first 64 B used)
+    uint8_t* asm_ = smem + C3T_B_BYTES;                    // [STAGES] tiles of 128 rows: bytes [0,64) A_hi, [64,128) A_lo
+    uint8_t* osm = asm_ + C3T_STAGES * C3S_A_STAGE_BYTES;  // output staging: [hi tile | lo tile]
+    float* patch = reinterpret_cast<float*>(osm + C3S_OUT_BYTES);
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(patch + 2 * C3T_PATCH_FLOATS);
+    uint64_t* a_empty = a_full + C3T_STAGES;
+    uint64_t* tfull_bar = a_empty + C3T_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool want_lo = p.y_lo != nullptr;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&map_y_hi);
+        if (want_lo) prefetch_tmap(&map_y_lo);
+        for (int s = 0; s < C3T_STAGES; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 12) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 8 && warp < 12) {
+        // ================================ producers: build B once, then one A tile per iteration ================================
+        const int t = threadIdx.x - 256;
+        {
+            const int co = t & 63;
+            uint32_t pk[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                float v0 = 0.f, v1 = 0.f;
+                if (2 * k2 < 27) v0 = __ldg(w + (2 * k2) * 64 + co);
+                if (2 * k2 + 1 < 27) v1 = __ldg(w + (2 * k2 + 1) * 64 + co);
+                const uint32_t h = pack_hi2<FP16>(v0, v1);
+                if (t < 64) pk[k2] = h;
+                else { const float2 r = unpack2<FP16>(h); pk[k2] = pack_hi2<FP16>(v0 - r.x, v1 - r.y); }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(bsm + sw128_chunk(t, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        const int w_l = t % C64_TW, h_l = t / C64_TW;
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        constexpr int PRE = (C3T_PATCH_FLOATS + 127) / 128;
+        float pre[PRE];
+        auto load_patch = [&](int tile) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+            const int x0 = tw * C64_TW - 1, y0 = th * C64_TH - 1;
+            const float* xb = x + (int64_t)b * p.H * p.W * 3;
+#pragma unroll
+            for (int j = 0; j < PRE; ++j) {
+                const int i = t + j * 128;
+                const int r = i / (C3T_PW * 3), rem = i - r * (C3T_PW * 3);
+                const int gy = y0 + r, gx = x0 + rem / 3;
+                float v = 0.f;
+                if (i < C3T_PATCH_FLOATS && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(xb + ((int64_t)gy * p.W + x0) * 3 + rem);
+                pre[j] = v;
+            }
+        };
+        if ((int)blockIdx.x < p.num_tiles) load_patch(blockIdx.x);
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            float* pb = patch + (it & 1) * C3T_PATCH_FLOATS;
+#pragma unroll
+            for (int j = 0; j < PRE; ++j)
+                if (t + j * 128 < C3T_PATCH_FLOATS) pb[t + j * 128] = pre[j];
+            named_bar_sync(1, 128);
+            if (tile + (int)gridDim.x < p.num_tiles) load_patch(tile + gridDim.x);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                float v0 = 0.f, v1 = 0.f;
+                if (2 * k2 < 27) { const int k = 2 * k2; v0 = pb[(h_l + k / 9) * (C3T_PW * 3) + w_l * 3 + (k % 9)]; }
+                if (2 * k2 + 1 < 27) { const int k = 2 * k2 + 1; v1 = pb[(h_l + k / 9) * (C3T_PW * 3) + w_l * 3 + (k % 9)]; }
+                hi[k2] = pack_hi2<FP16>(v0, v1);
+                const float2 r = unpack2<FP16>(hi[k2]);
+                lo[k2] = pack_hi2<FP16>(v0 - r.x, v1 - r.y);
+            }
+            mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 1);
+            uint8_t* st = asm_ + stage * C3S_A_STAGE_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4*>(st + sw128_chunk(t, c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                *reinterpret_cast<uint4*>(st + sw128_chunk(t, 4 + c)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&a_full[stage]);
+            if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 12) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint64_t bdesc = make_smem_desc(smem_u32(bsm));
+            int stage = 0; uint32_t phase = 0; int acc_it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+                const int acc = acc_it & 1;
+                mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+                mbar_wait(&a_full[stage], phase, p.err_flag, 3);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
+                const uint64_t a_hi = make_smem_desc(smem_u32(asm_ + stage * C3S_A_STAGE_BYTES));
+                const uint64_t a_lo = a_hi + (uint64_t)(64 >> 4);          // bytes [64,128) of every row
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                    tc_mma_f16(d_tmem, a_hi + koff, bdesc + koff, IDESC_N128, (uint32_t)(j != 0));
+                    tc_mma_f16(d_tmem, a_lo + koff, bdesc + koff, IDESC_N64, 1u);
+                }
+                tc_commit(&a_empty[stage]);
+                tc_commit(&tfull_bar[acc]);
+                if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ================================ epilogue: warps 0-7 (lane quadrant q, channel half ch) -> smem staging -> TMA store ================================
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        int acc_it = 0;
+        const float2* bias2 = reinterpret_cast<const float2*>(p.bias + ch * 32);
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+            const int acc = acc_it & 1;
+            mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, p.err_flag, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + ch * 32);
+            // the previous tile's bulk stores must have finished READING the staging buffer before it is overwritten
+            if (threadIdx.x == 0) tma_store_wait_read();
+            named_bar_sync(2, 256);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {           // 16 channels at a time (72-register budget at two CTAs per SM)
+                uint32_t v[16], v2[16];
+                tc_ld_32x32b_x16(taddr + 16 * half, v);          // hi*hi + lo*hi
+                tc_ld_32x32b_x16(taddr + 64 + 16 * half, v2);    // hi*lo
+                tc_wait_ld();
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 bv = __ldg(bias2 + 8 * half + i);
+                    float f0 = (__uint_as_float(v[2 * i]) + __uint_as_float(v2[2 * i])) + bv.x;
+                    float f1 = (__uint_as_float(v[2 * i + 1]) + __uint_as_float(v2[2 * i + 1])) + bv.y;
+                    if (p.leaky) { f0 = fmaxf(f0, kNegSlope * f0); f1 = fmaxf(f1, kNegSlope * f1); }
+                    hi[i] = pack_hi2<FP16>(f0, f1);
+                    const float2 r = unpack2<FP16>(hi[i]);
+                    lo[i] = pack_hi2<FP16>(f0 - r.x, f1 - r.y);
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int chunk = 4 * ch + 2 * half + c;
+                    *reinterpret_cast<uint4*>(osm + sw128_chunk(row, chunk)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                    if (want_lo)
+                        *reinterpret_cast<uint4*>(osm + A_TILE_BYTES + sw128_chunk(row, chunk)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            fence_proxy_async_smem();
+            named_bar_sync(2, 256);
+            if (threadIdx.x == 0) {
+                tma_store_4d(&map_y_hi, osm, 0, tw * C64_TW, th * C64_TH, b);
+                if (want_lo) tma_store_4d(&map_y_lo, osm + A_TILE_BYTES, 0, tw * C64_TW, th * C64_TH, b);
+                tma_store_commit();
+            }
+        }
+        if (threadIdx.x == 0) tma_store_wait_all();        // global writes complete before the CTA exits
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 12) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ CTA-pair kernel
 // Same algorithm on a cluster of two CTAs (two SMs of one TPC) with tcgen05 cta_group::2: one UMMA covers M = 256 pixels
 // (CTA r owns pixel tile 2*pair + r and TMEM rows of it) x N = BN channels; each CTA stages its own A tile and HALF of the
@@ -1229,6 +1447,22 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                     mbar_wait(&a_full[stage], phase, p.err_flag, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(asm_ + stage * C64X2_A_STAGE_BYTES);
+                    if (p.exp & 2) {   // experiment: grouped by instruction shape
+#pragma unroll
+                        for (int pass = 0; pass < 2; ++pass)
+#pragma unroll
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const uint64_t a = make_smem_desc(sa + pass * C64_PATCH_BYTES + kh * C64_ROW_BYTES);
+                                const uint64_t b = make_smem_desc(wb + (kh * 3 + kw) * C64X2_W_TAP_BYTES);
+#pragma unroll
+                                for (int j = 0; j < BK / UMMA_K; ++j) {
+                                    const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                                    const uint32_t accum = (uint32_t)((kw | kh | j) != 0);
+                                    if (pass == 0) tc_mma_f16_2cta(d_tmem, a + koff, b + koff, IDESC_MAIN, accum);
+                                    else if (!(p.exp & 1)) tc_mma_f16_2cta(d_tmem + 128, a + koff, b + koff, IDESC_N64, accum);
+                                }
+                            }
+                    } else {
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
                         const uint64_t a_hi = make_smem_desc(sa + kh * C64_ROW_BYTES);
@@ -1239,8 +1473,9 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                             const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
                             const uint32_t accum = (uint32_t)((kw | kh | j) != 0);
                             tc_mma_f16_2cta(d_tmem, a_hi + koff, b + koff, IDESC_MAIN, accum);
-                            tc_mma_f16_2cta(d_tmem + 128, a_lo + koff, b + koff, IDESC_N64, accum);
+                            if (!(p.exp & 1)) tc_mma_f16_2cta(d_tmem + 128, a_lo + koff, b + koff, IDESC_N64, accum);
                         }
+                    }
                     }
                     tc_commit_2cta(&a_empty[stage]);
                     if (++stage == C64X2_STAGES) { stage = 0; phase ^= 1; }
@@ -1406,10 +1641,12 @@ TcTuning& tc_tuning() {
         v.pair128 = geti("H3D_TC_PAIR128", 1);
         v.stack = geti("H3D_TC_STACK", 1);
         v.chunk_kb = geti("H3D_TC_CHUNK_KB", 0);
+        v.exp = geti("H3D_TC_EXP", 0);
         v.no_side_stream = geti("H3D_NO_SIDE_STREAM", 0);
         v.no_pool_fusion = geti("H3D_NO_POOL_FUSION", 0);
         v.lift_direct = geti("H3D_LIFT_DIRECT", 0);
         v.c3_ffma = geti("H3D_C3_FFMA", 0);
+        v.c3_tma = geti("H3D_C3_TMA", 1);
         return v;
     }();
     return t;
@@ -1424,10 +1661,12 @@ int tc_set_tuning(const char* key, int value) {
     else if (k == "tc_pair128") t.pair128 = value;
     else if (k == "tc_stack") t.stack = value;
     else if (k == "tc_chunk_kb") t.chunk_kb = value;
+    else if (k == "tc_exp") t.exp = value;
     else if (k == "no_side_stream") t.no_side_stream = value;
     else if (k == "no_pool_fusion") t.no_pool_fusion = value;
     else if (k == "lift_direct") t.lift_direct = value;
     else if (k == "c3_ffma") t.c3_ffma = value;
+    else if (k == "c3_tma") t.c3_tma = value;
     else { set_error("h3d_set_tuning: unknown key '%s'", k.c_str()); return H3D_EINVAL; }
     return H3D_OK;
 }
@@ -1545,6 +1784,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     p.n_valid = d.Cout;
     p.pool = d.pool;
     p.stack = tune.stack != 0;
+    p.exp = tune.exp;
     p.err_flag = d.err_flag;
     // <= ~108 accumulating MMAs per TMEM partial sum (9 K blocks x 4 K steps x 3 passes); BN = 256 keeps everything in
     // TMEM (its 256 fp32 partial sums per thread would not fit the register file)
@@ -1636,6 +1876,19 @@ int launch_conv_c3_tc(const float* x, const float* w, const float* bias, Split y
     p.num_tiles = p.tiles_w * p.tiles_h * B;
     p.n_valid = 64; p.pool = 0; p.chunk_kb = 1; p.leaky = leaky; p.err_flag = err_flag;
     const int grid = std::min(p.num_tiles, 2 * tc_num_sms());   // two co-resident CTAs per SM (86 KB, 72 registers, 256 TMEM columns each)
+    if (tc_tuning().c3_tma) {   // smem-staged epilogue with bulk tensor stores (output tensor maps over the 64-channel slice of the planes)
+        CUtensorMap my_hi, my_lo;
+        if (!encode_act_map(&my_hi, y.hi + cs_off, Cs_total, 64, W, H, B, C64_TW, C64_TH, 1)) return H3D_ECUDA;
+        my_lo = my_hi;
+        if (y.lo && !encode_act_map(&my_lo, y.lo + cs_off, Cs_total, 64, W, H, B, C64_TW, C64_TH, 1)) return H3D_ECUDA;
+        static bool at_h[kMaxDevices] = {}, at_b[kMaxDevices] = {};
+        if (int rc = smem_opt_in(conv_c3_tma_kernel<true>, C3S_SMEM, at_h)) return rc;
+        if (int rc = smem_opt_in(conv_c3_tma_kernel<false>, C3S_SMEM, at_b)) return rc;
+        if (half == Half16::FP16) conv_c3_tma_kernel<true><<<grid, C3T_THREADS, C3S_SMEM, s>>>(x, w, my_hi, my_lo, p);
+        else conv_c3_tma_kernel<false><<<grid, C3T_THREADS, C3S_SMEM, s>>>(x, w, my_hi, my_lo, p);
+        H3D_CHECK_LAUNCH();
+        return H3D_OK;
+    }
     static bool attr_h[kMaxDevices] = {}, attr_b[kMaxDevices] = {};
     if (int rc = smem_opt_in(conv_c3_tc_kernel<true>, C3T_SMEM, attr_h)) return rc;
     if (int rc = smem_opt_in(conv_c3_tc_kernel<false>, C3T_SMEM, attr_b)) return rc;

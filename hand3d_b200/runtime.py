@@ -380,6 +380,55 @@ class Context:
                                                _stream()), "h3d_decode_records")
         return {"image": image, "header": header, "mask": mask, "visibility": vis}
 
+    def rhd_reader_items(self, header, hand_parts, visibility, use_wrist_coord=True, hand_crop=False, crop_size=256):
+        """Derived items of BinaryDbReader.get() (evaluation mode) from the outputs of decode_records(..., "rhd")."""
+        B = header.shape[0]
+        dev = header.device
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)      # noqa: E731
+        r = {"keypoint_xyz21": f(B, 21, 3), "keypoint_uv21": f(B, 21, 2), "keypoint_vis21": torch.empty((B, 21), dtype=torch.uint8, device=dev),
+             "hand_side": f(B, 2), "keypoint_scale": f(B), "keypoint_xyz21_normed": f(B, 21, 3), "cam_mat": f(B, 3, 3),
+             "crop_center": f(B, 2) if hand_crop else None, "crop_scale": f(B) if hand_crop else None}
+        _lib.check(self.lib.h3d_rhd_reader_items(
+            self.h, _ptr(header.contiguous()), _ptr(hand_parts.contiguous()), _ptr(visibility.contiguous()), B, int(bool(use_wrist_coord)),
+            int(bool(hand_crop)), int(crop_size), _ptr(r["keypoint_xyz21"]), _ptr(r["keypoint_uv21"]), _ptr(r["keypoint_vis21"]),
+            _ptr(r["hand_side"]), _ptr(r["keypoint_scale"]), _ptr(r["keypoint_xyz21_normed"]), _ptr(r["crop_center"]), _ptr(r["crop_scale"]),
+            _ptr(r["cam_mat"]), _stream()), "h3d_rhd_reader_items")
+        return r
+
+    def stb_reader_items(self, header, use_wrist_coord=True):
+        B = header.shape[0]
+        dev = header.device
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)      # noqa: E731
+        r = {"keypoint_xyz21": f(B, 21, 3), "keypoint_uv21": f(B, 21, 2), "keypoint_vis21": torch.empty((B, 21), dtype=torch.uint8, device=dev),
+             "keypoint_scale": f(B), "keypoint_xyz21_normed": f(B, 21, 3)}
+        _lib.check(self.lib.h3d_stb_reader_items(self.h, _ptr(header.contiguous()), B, int(bool(use_wrist_coord)), _ptr(r["keypoint_xyz21"]),
+                                                 _ptr(r["keypoint_uv21"]), _ptr(r["keypoint_vis21"]), _ptr(r["keypoint_scale"]),
+                                                 _ptr(r["keypoint_xyz21_normed"]), _stream()), "h3d_stb_reader_items")
+        return r
+
+    def gaussian_scoremap(self, coords_hw, output_size, sigma, valid=None):
+        """create_multiple_gaussian_map, batched: coords_hw [B,N,2] (row, col), valid [B,N] -> [B,H,W,N]."""
+        coords_hw = _chk_f32(coords_hw, "coords_hw", 3)
+        B, N, _ = coords_hw.shape
+        H, W = int(output_size[0]), int(output_size[1])
+        v = valid.to(torch.uint8).contiguous() if valid is not None else None
+        out = torch.empty((B, H, W, N), dtype=torch.float32, device=coords_hw.device)
+        _lib.check(self.lib.h3d_gaussian_scoremap(self.h, _ptr(coords_hw), _ptr(v), B, N, H, W, C.c_float(float(sigma)), _ptr(out), _stream()),
+                   "h3d_gaussian_scoremap")
+        return out
+
+    def canonical_trafo(self, coords_xyz, cond_right=None):
+        """-> (coords_can [B,21,3], rot_mat [B,3,3], rot_mat_inv [B,3,3]) (utils/canonical_trafo.py:97-162)."""
+        coords_xyz = _chk_f32(coords_xyz.reshape(-1, 21, 3), "coords_xyz", 3)
+        B = coords_xyz.shape[0]
+        dev = coords_xyz.device
+        cr = cond_right.reshape(B).to(torch.uint8).contiguous() if cond_right is not None else None
+        can = torch.empty((B, 21, 3), dtype=torch.float32, device=dev)
+        rot = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+        inv = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.h3d_canonical_trafo(self.h, _ptr(coords_xyz), _ptr(cr), B, _ptr(can), _ptr(rot), _ptr(inv), _stream()), "h3d_canonical_trafo")
+        return can, rot, inv
+
     def eval_keypoint_dist(self, gt, vis, pred):
         gt = _chk_f32(gt, "keypoint_gt"); pred = _chk_f32(pred, "keypoint_pred")
         D = gt.shape[-1]

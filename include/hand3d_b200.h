@@ -217,6 +217,30 @@ H3D_API int h3d_gather_records_p2p(h3d_ctx* ctx, const float* coord3d, const int
 #define H3D_DATASET_STB 1
 H3D_API int h3d_decode_records(h3d_ctx* ctx, int dataset, const uint8_t* records, int B, int step, float* header, float* image,
                                uint8_t* mask, uint8_t* visibility, void* stream);
+/* The readers' DERIVED items, evaluation mode (no augmentation noise).  RHD (data/BinaryDbReader.py:139-162
+ * palm substitution when use_wrist_coord == 0, :210-250 dominant hand by part-mask pixel counts / 21-key-point subsets /
+ * root-relative normalisation, :269-346 ground-truth hand crop when hand_crop != 0): inputs are the outputs of h3d_decode_records
+ * (header [B,219], mask = hand_parts [B,320,320] u8, visibility [B,42] u8).  Outputs (any may be NULL except hand_side):
+ * keypoint_xyz21 [B,21,3], keypoint_uv21 [B,21,2] (crop space when hand_crop), keypoint_vis21 [B,21] u8, hand_side [B,2] one-hot,
+ * keypoint_scale [B], keypoint_xyz21_normed [B,21,3], crop_center [B,2] (row, col) and crop_scale [B] (feed h3d_crop_image_from_xy
+ * to obtain image_crop), cam_mat [B,3,3] (updated for the crop when hand_crop). */
+H3D_API int h3d_rhd_reader_items(h3d_ctx* ctx, const float* header, const uint8_t* hand_parts, const uint8_t* visibility, int B,
+                                 int use_wrist_coord, int hand_crop, int crop_size, float* keypoint_xyz21, float* keypoint_uv21,
+                                 uint8_t* keypoint_vis21, float* hand_side, float* keypoint_scale, float* keypoint_xyz21_normed,
+                                 float* crop_center, float* crop_scale, float* cam_mat, void* stream);
+/* STB (data/BinaryDbReaderSTB.py:123-196): header [B,126] -> metres, convert_kp order (:397-410), wrist extrapolation when
+ * use_wrist_coord != 0, root-relative normalisation.  hand_side is the constant (1, 0) for this dataset. */
+H3D_API int h3d_stb_reader_items(h3d_ctx* ctx, const float* header, int B, int use_wrist_coord, float* keypoint_xyz21, float* keypoint_uv21,
+                                 uint8_t* keypoint_vis21, float* keypoint_scale, float* keypoint_xyz21_normed, void* stream);
+/* create_multiple_gaussian_map (data/BinaryDbReader.py:413-459): coords_hw [B,N,2] (row, col; truncated to int32), valid [B,N] u8
+ * (NULL = all valid) -> scoremap [B,H,W,N] = exp(-d^2 / sigma^2) for key-points strictly inside the map, 0 otherwise.  N <= 64. */
+H3D_API int h3d_gaussian_scoremap(h3d_ctx* ctx, const float* coords_hw, const uint8_t* valid, int B, int N, int H, int W, float sigma,
+                                  float* scoremap, void* stream);
+/* canonical_trafo (+ flip_right_hand, + the tf.matrix_inverse the readers apply) (utils/canonical_trafo.py:97-162,
+ * data/BinaryDbReader.py:247-252): coords_xyz [B,21,3] -> coords_can [B,21,3] (z mirrored where cond_right[b] != 0; cond_right may be
+ * NULL), rot_mat [B,3,3] (total rotation), rot_mat_inv [B,3,3]; each output may be NULL. */
+H3D_API int h3d_canonical_trafo(h3d_ctx* ctx, const float* coords_xyz, const uint8_t* cond_right, int B, float* coords_can, float* rot_mat,
+                                float* rot_mat_inv, void* stream);
 /* EvalUtil.feed (utils/general.py:531-549), batched on device: gt / pred [n, D] (D = 2 or 3), vis [n] u8 ->
  * dist [n] = ||gt - pred||_2, or -1 where the key-point is not visible. */
 H3D_API int h3d_eval_keypoint_dist(h3d_ctx* ctx, const float* gt, const uint8_t* vis, const float* pred, int n, int D, float* dist,

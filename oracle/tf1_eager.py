@@ -9,7 +9,11 @@ resize, soft-max, dilation2d, crop_and_resize) delegate to oracle/tf1_ops.py -- 
 kernels the oracle uses -- so the outputs pin the oracle's GRAPH restatement (oracle/hand3d_oracle.py) to the reference source,
 not the op semantics (those stay pinned by the known-answer tests only: "parity unpinned" still applies to them).
 
-Used only by tests/golden/make_golden_reference_graph.py.  Variables: `tf.get_variable` looks the full scoped name up in
+Since round 2 it also carries the queue-reader stubs (FixedLengthRecordReader, string_input_producer, decode_raw, batch_join) and
+the extra element-wise ops the reference's dataset readers need (data/BinaryDbReader.py, data/BinaryDbReaderSTB.py,
+utils/canonical_trafo.py), so that their derived items can be generated from the reference source as well.
+
+Used only by tests/golden/make_golden_reference_graph.py and tests/golden/make_golden_reference_reader.py.  Variables: `tf.get_variable` looks the full scoped name up in
 `set_weights({name: ndarray})` and checks the shape the reference asks for.
 """
 from __future__ import annotations
@@ -155,12 +159,90 @@ def range(*a, **k):      # noqa: A001
     return _w(np.arange(*a, dtype=np.int32))
 
 
+def _pair(a, b):
+    """TF converts python numbers / tuples to the dtype of the tensor operand (numpy would promote a tuple of ints to int64)."""
+    if isinstance(a, np.ndarray) and not isinstance(b, np.ndarray):
+        return a, np.asarray(b, a.dtype)
+    if isinstance(b, np.ndarray) and not isinstance(a, np.ndarray):
+        return np.asarray(a, b.dtype), b
+    return a, b
+
+
 def maximum(a, b, **k):
-    return _w(np.maximum(a, b))
+    return _w(np.maximum(*_pair(a, b)))
 
 
 def minimum(a, b, **k):
-    return _w(np.minimum(a, b))
+    return _w(np.minimum(*_pair(a, b)))
+
+
+def exp(x, **k):
+    return _w(np.exp(x))
+
+
+def logical_or(a, b, **k):
+    return _w(np.logical_or(a, b))
+
+
+def logical_not(a, **k):
+    return _w(np.logical_not(a))
+
+
+def slice(x, begin, size, **k):      # noqa: A001
+    x = np.asarray(x)
+    idx = tuple(np.s_[int(b):int(b) + int(n)] for b, n in zip(begin, size))
+    return _w(x[idx])
+
+
+def one_hot(indices, depth, on_value=1.0, off_value=0.0, dtype=np.float32, **k):
+    idx = np.asarray(indices)
+    out = np.full(idx.shape + (depth,), off_value, dtype)
+    np.put_along_axis(out, idx[..., None].astype(np.int64), np.asarray(on_value, dtype), -1)
+    return _w(out)
+
+
+uint8 = np.uint8
+
+
+def decode_raw(value, out_type, **k):
+    return _w(np.frombuffer(bytes(value), dtype=out_type).copy())
+
+
+# ---- queue-reader stubs: the records of the file named by string_input_producer are handed out one per read()
+_record_files: dict = {}
+
+
+class _Queue:
+    def __init__(self, names):
+        self.names = list(names)
+
+
+class FixedLengthRecordReader:
+    def __init__(self, header_bytes=0, record_bytes=0, **k):
+        assert header_bytes == 0
+        self.record_bytes = int(record_bytes)
+
+    def read(self, queue):
+        name = queue.names[0]
+        st = _record_files.setdefault(name, {"pos": 0})
+        with open(name, "rb") as f:
+            f.seek(st["pos"] * self.record_bytes)
+            value = f.read(self.record_bytes)
+        assert len(value) == self.record_bytes, "ran out of records in %s" % name
+        st["pos"] += 1
+        return "%s:%d" % (name, st["pos"] - 1), value
+
+
+def reset_readers():
+    _record_files.clear()
+
+
+def _batch_join(tensors_list, batch_size, capacity=None, enqueue_many=False, **k):
+    assert batch_size == 1 and len(tensors_list) == 1 and not enqueue_many
+    return [_w(np.expand_dims(np.asarray(t), 0)) for t in tensors_list[0]]
+
+
+train = types.SimpleNamespace(string_input_producer=lambda names, **k: _Queue(names), batch_join=_batch_join)
 
 
 def multiply(a, b, **k):
@@ -259,7 +341,7 @@ def sparse_to_dense(sparse_indices, output_shape, sparse_values, default_value=0
 def dynamic_stitch(indices, data, **k):   # only the use of the reference: indices [[0],[1],...], data[i] of shape [1, B]
     n = len(indices)
     assert [list(i) for i in indices] == [[i] for i in np.arange(n)]
-    return _w(np.concatenate([np.asarray(d) for d in data], 0))
+    return _w(np.concatenate([np.asarray(_f(d)) for d in data], 0))
 
 
 def cond(pred, fn1, fn2, **k):
@@ -324,7 +406,10 @@ nn = types.SimpleNamespace(conv2d=_conv2d, bias_add=_bias_add, max_pool=_max_poo
 
 
 def _resize_images(x, size, **k):
-    return _w(T.resize_bilinear_tf1(np.asarray(x), int(size[0]), int(size[1])))
+    x = np.asarray(x)
+    if x.ndim == 3:      # tf.image.resize_images also takes a single [H,W,C] image (data/BinaryDbReader.py:372)
+        return _w(T.resize_bilinear_tf1(x[None], int(size[0]), int(size[1]))[0])
+    return _w(T.resize_bilinear_tf1(x, int(size[0]), int(size[1])))
 
 
 def _crop_and_resize(image, boxes, box_ind, crop_size, **k):

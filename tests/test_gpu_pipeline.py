@@ -55,6 +55,20 @@ def test_handsegnet_stage(net, ctx, seg_ref, prec):
     assert err < TOL[prec], "HandSegNet %s: max abs err %.3e" % (prec, err)
 
 
+@pytest.mark.parametrize("switch", ["c3_tma", "c3_ffma"])
+def test_first_layer_kernel_variants(net, ctx, seg_ref, switch):
+    """conv1_1 has three kernels: tensor cores with bulk-tensor-store epilogue (default), tensor cores with direct global stores
+    (c3_tma = 0) and the register-tiled FFMA kernel (c3_ffma = 1); all must give the HandSegNet parity."""
+    img, ref = seg_ref
+    ctx.set_precision("bf16x3")
+    ctx.set_tuning(switch, 0 if switch == "c3_tma" else 1)
+    try:
+        out = net.inference_detection(_dev(img))[0].cpu().numpy()
+    finally:
+        ctx.set_tuning(switch, 1 if switch == "c3_tma" else 0)
+    assert np.abs(out - ref).max() < 1e-3
+
+
 def test_handsegnet_240x320(net, ctx, wd):
     img = Wt.synthetic_images(1, 240, 320, seed=7)
     ctx.set_precision("bf16x3")
@@ -259,7 +273,10 @@ def test_example_drivers_run():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for script, args in (("run_demo.py", []), ("eval2d_demo.py", ["--samples", "8", "--batch", "4"])):
+    for script, args in (("run_demo.py", []), ("eval2d_demo.py", ["--samples", "8", "--batch", "4"]),
+                         ("eval2d_gt_cropped_demo.py", ["--samples", "8", "--batch", "4"]), ("eval3d_demo.py", ["--samples", "8", "--batch", "4"]),
+                         ("eval3d_demo.py", ["--samples", "4", "--batch", "4", "--variant", "proposed"]),
+                         ("eval_full_demo.py", ["--samples", "4", "--batch", "2"])):
         r = subprocess.run([sys.executable, os.path.join(root, "examples", script)] + args, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
+        assert r.returncode == 0, (script, r.stderr[-2000:])
         assert ("3D wrist" in r.stdout) or ("Area under curve" in r.stdout), r.stdout
