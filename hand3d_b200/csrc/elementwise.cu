@@ -377,6 +377,7 @@ __global__ void seg_prob_kernel(const float2* __restrict__ logits, int H, int W,
 
 constexpr int kGrowThreads = 1024;
 constexpr int kMaxMaskWords = 512 * 16;  // H, W <= 512
+constexpr int kMaxRowWords = 16;         // W <= 512
 
 __global__ void __launch_bounds__(kGrowThreads, 1)
 mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ det_g, int H, int W, int Ww,
@@ -407,34 +408,56 @@ mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __r
     if (tid == 0) obj[sy * Ww + (sx >> 5)] = 1u << (sx & 31);   // one-hot seed (utils/general.py:252-253)
     __syncthreads();
 
+    // One pass = obj <- det AND dilate21x21(obj).  The 21 x 21 box dilation is separable:
+    //  * horizontal (bits): one thread per image row keeps the row's words in registers and widens the set by -+1, -+2, -+4, -+3 pixels
+    //    (windows 3 -> 7 -> 15 -> 21 pixels: 4 multi-word shift-OR steps instead of 20);
+    //  * vertical (rows): van Herk / Gil-Werman with blocks of 21 rows: pre[y] = OR of the block's rows up to y, suf[y] = OR from y
+    //    to the block's end, window [y-10, y+10] = suf[y-10] | pre[y+10] (3 word operations per row instead of 21).
+    uint32_t* pre = sm + 3 * H * Ww;        // [H][Ww]
+    uint32_t* suf = sm + 4 * H * Ww;        // [H][Ww]
+    const int nblk = (H + 20) / 21;
     for (int pass = 0; pass < num_passes; ++pass) {
         if (tid == 0) s_changed = 0;
-        // horizontal OR over [-10, +10] pixels
-        for (int i = tid; i < words; i += kGrowThreads) {
-            const int xw = i % Ww;
-            const uint32_t cur = obj[i];
-            const uint32_t prev = xw > 0 ? obj[i - 1] : 0u;
-            const uint32_t next = xw + 1 < Ww ? obj[i + 1] : 0u;
-            uint32_t r = cur;
+        if (tid < H) {
+            uint32_t w[kMaxRowWords];
 #pragma unroll
-            for (int sft = 1; sft <= 10; ++sft) {
-                r |= __funnelshift_l(prev, cur, sft);   // pixel x - sft -> x
-                r |= __funnelshift_r(cur, next, sft);   // pixel x + sft -> x
+            for (int i = 0; i < kMaxRowWords; ++i) w[i] = i < Ww ? obj[tid * Ww + i] : 0u;
+#pragma unroll
+            for (int step = 0; step < 4; ++step) {
+                const int sft = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 3;
+                uint32_t r[kMaxRowWords];
+#pragma unroll
+                for (int i = 0; i < kMaxRowWords; ++i) {
+                    const uint32_t prev = i > 0 ? w[i - 1] : 0u, next = i + 1 < kMaxRowWords ? w[i + 1] : 0u;
+                    r[i] = w[i] | __funnelshift_l(prev, w[i], sft) | __funnelshift_r(w[i], next, sft);
+                }
+#pragma unroll
+                for (int i = 0; i < kMaxRowWords; ++i) w[i] = r[i];
             }
-            hor[i] = r;
+#pragma unroll
+            for (int i = 0; i < kMaxRowWords; ++i)
+                if (i < Ww) hor[tid * Ww + i] = w[i];      // bits beyond W in the last word are masked by det below
         }
         __syncthreads();
-        // vertical OR over [-10, +10] rows, AND with det
+        for (int t = tid; t < nblk * Ww; t += kGrowThreads) {
+            const int k = t / Ww, xw = t - k * Ww;
+            const int y0 = 21 * k, y1 = min(y0 + 20, H - 1);
+            uint32_t a = 0u;
+            for (int y = y0; y <= y1; ++y) { a |= hor[y * Ww + xw]; pre[y * Ww + xw] = a; }
+            a = 0u;
+            for (int y = y1; y >= y0; --y) { a |= hor[y * Ww + xw]; suf[y * Ww + xw] = a; }
+        }
+        __syncthreads();
         int changed = 0;
         for (int i = tid; i < words; i += kGrowThreads) {
-            const int y = i / Ww;
-            const int y0 = max(y - 10, 0), y1 = min(y + 10, H - 1);
-            uint32_t r = 0u;
-            for (int yy = y0; yy <= y1; ++yy) r |= hor[i + (yy - y) * Ww];
+            const int y = i / Ww, xw = i - y * Ww;
+            const int a = max(y - 10, 0), b2 = min(y + 10, H - 1);
+            uint32_t r;
+            if (a / 21 == b2 / 21) r = (a % 21 == 0) ? pre[b2 * Ww + xw] : suf[a * Ww + xw];   // window inside one block: it starts at the block's first row or ends at its last
+            else r = suf[a * Ww + xw] | pre[b2 * Ww + xw];
             r &= det[i];
             changed |= (r != obj[i]);
-            // obj is only read through `hor` in this phase, so the in-place update is race-free
-            obj[i] = r;
+            obj[i] = r;                      // obj is not read by anybody else in this phase
         }
         if (changed) s_changed = 1;
         __syncthreads();
@@ -493,12 +516,12 @@ int launch_seg_postprocess(const float* logits, int B, int H, int W, void* scrat
     dim3 grid(std::min(ceil_div(words, 8), 64), B);
     seg_prob_kernel<<<grid, 256, 0, s>>>((const float2*)logits, H, W, Ww, key, det);
     H3D_CHECK_LAUNCH();
-    const size_t smem = (size_t)3 * words * sizeof(uint32_t);
+    const size_t smem = (size_t)5 * words * sizeof(uint32_t);    // det, obj, hor, pre, suf
     static bool attr_set[64] = {};   // per device (one process may drive several GPUs)
     int dev = 0;
     H3D_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        H3D_CUDA(cudaFuncSetAttribute(mask_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kMaxMaskWords * 4));
+        H3D_CUDA(cudaFuncSetAttribute(mask_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kMaxMaskWords * 4));
         attr_set[dev & 63] = true;
     }
     const int num_passes = std::max(H, W) / (21 / 2);   // utils/general.py:256
@@ -703,11 +726,103 @@ __global__ void resize_argmax_kernel(const float* __restrict__ x, float* __restr
     }
 }
 
+// Power-of-two integer up-sampling (the x8 of nets/ColorHandPose3DNetwork.py:96-97) restructured for instruction count: with scale
+// 1/s exact in fp32, the s output rows oy = s y0 .. s y0 + s - 1 share the input rows (y0, y1) and therefore the horizontal
+// interpolants top(ox) / bot(ox): one CTA per (image, y0) stages the two input rows in shared memory, every thread owns ONE 16-byte
+// output column group (4 consecutive floats of the flattened (ox, c) row; the channel pattern of a group repeats every 4 pixels =
+// 84 floats, so a thread's four channels are fixed), computes top / bot once and emits s rows with one vertical lerp + one arg-max
+// update per value and 16-byte stores.  Values are computed by exactly the operations of resize_bilinear_tf1_kernel.
+template <int C>
+__global__ void resize_argmax_pow2_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W, int s_log2, float hscale,
+                                          float wscale, unsigned long long* __restrict__ key) {
+    static_assert((4 * C) % 4 == 0, "");
+    constexpr int G4 = C;                        // float4 groups per 4 output pixels (4 C floats)
+    extern __shared__ unsigned long long sdyn[];
+    float* rows = reinterpret_cast<float*>(sdyn);                         // [2][W * C]
+    unsigned long long* skey = sdyn + (2 * W * C + 1) / 2;                // [C][slots]
+    const int sfac = 1 << s_log2;
+    const int ow = W << s_log2;
+    const int b = blockIdx.y, y0 = blockIdx.x;
+    const int y1 = min(y0 + 1, H - 1);
+    const int t = threadIdx.x;
+    const int j = t % G4, gsub = t / G4, gstep = blockDim.x / G4;          // float4 index inside the 4-pixel group, pixel-group lane
+    const float* xb = x + (int64_t)b * H * W * C;
+    for (int i = t; i < W * C; i += blockDim.x) { rows[i] = __ldg(xb + (int64_t)y0 * W * C + i); rows[W * C + i] = __ldg(xb + (int64_t)y1 * W * C + i); }
+    __syncthreads();
+    int pofs[4], cc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pofs[i] = (4 * j + i) / C; cc[i] = (4 * j + i) % C; }
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    int bp[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    bool have[4] = {false, false, false, false};
+    const int groups = ow >> 2;                   // 4-pixel groups per output row
+    float* yb = y + (int64_t)b * (int64_t)(H << s_log2) * ow * C;
+    if (gsub < gstep) {
+        for (int g = gsub; g < groups; g += gstep) {
+            float top[4], bot[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ox = 4 * g + pofs[i];
+                const float in_x = __fmul_rn((float)ox, wscale);
+                const int x0 = (int)floorf(in_x), x1 = min(x0 + 1, W - 1);
+                const float lx = __fsub_rn(in_x, (float)x0);
+                top[i] = lerp_tf(rows[x0 * C + cc[i]], rows[x1 * C + cc[i]], lx);
+                bot[i] = lerp_tf(rows[W * C + x0 * C + cc[i]], rows[W * C + x1 * C + cc[i]], lx);
+            }
+            for (int r = 0; r < sfac; ++r) {
+                const int oy = (y0 << s_log2) + r;
+                const float in_y = __fmul_rn((float)oy, hscale);
+                const float ly = __fsub_rn(in_y, (float)y0);            // floor(in_y) == y0 exactly for a power-of-two scale
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    o[i] = lerp_tf(top[i], bot[i], ly);
+                    const int pidx = oy * ow + 4 * g + pofs[i];
+                    if (!have[i] || o[i] > bv[i] || (o[i] == bv[i] && pidx < bp[i])) { bv[i] = o[i]; bp[i] = pidx; have[i] = true; }
+                }
+                *reinterpret_cast<float4*>(yb + ((int64_t)oy * ow + 4 * g) * C + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    // per-channel reduction: slot (gsub, j-slot) -> skey[c][...]; every channel occurs in exactly 4 (j, i) pairs
+    const int slots = 4 * gstep;
+    for (int i = t; i < C * slots; i += blockDim.x) skey[i] = 0ull;
+    __syncthreads();
+    if (gsub < gstep) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (have[i]) {
+                const unsigned long long k = ((unsigned long long)float_orderable(bv[i]) << 32) | (uint32_t)(0xFFFFFFFFu - (uint32_t)bp[i]);
+                skey[cc[i] * slots + gsub * 4 + pofs[i]] = k;            // (gsub, pixel offset) is unique per channel
+            }
+    }
+    __syncthreads();
+    if (t < C) {
+        unsigned long long m = 0ull;
+        for (int q = 0; q < slots; ++q) { const unsigned long long k = skey[t * slots + q]; m = k > m ? k : m; }
+        atomicMax(key + (int64_t)b * C + t, m);
+    }
+}
+
 int launch_resize_argmax21(const float* x, float* y, int B, int H, int W, int oh, int ow, void* scratch, int32_t* uv, cudaStream_t s,
                            int* n_launch) {
     constexpr int C = 21;
     unsigned long long* key = (unsigned long long*)scratch;
     H3D_CUDA(cudaMemsetAsync(key, 0, (size_t)B * C * 8, s));
+    // integer power-of-two up-sampling in both directions (x8 on the hot path): row-group kernel
+    if (oh % H == 0 && ow % W == 0 && oh / H == ow / W && ((oh / H) & (oh / H - 1)) == 0 && oh / H >= 2 && (ow % 4) == 0 &&
+        (((uintptr_t)y) & 15) == 0 && (int64_t)W * C * 8 + 4 * 16 * C * 8 <= 48 * 1024) {
+        int sl = 0;
+        while ((1 << sl) < oh / H) ++sl;
+        const int gstep = 16, threads = C * gstep;                        // 336 threads: 21 float4 columns x 16 pixel-group lanes
+        const size_t smem = (size_t)((2 * W * C + 1) / 2) * 8 + (size_t)C * 4 * gstep * 8;
+        resize_argmax_pow2_kernel<C><<<dim3(H, B), threads, smem, s>>>(x, y, H, W, sl, (float)H / (float)oh, (float)W / (float)ow, key);
+        H3D_CHECK_LAUNCH();
+        argmax_decode_kernel<<<ceil_div(B * C, 256), 256, 0, s>>>(key, B * C, ow, uv);
+        H3D_CHECK_LAUNCH();
+        if (n_launch) *n_launch += 2;
+        return H3D_OK;
+    }
     const int P = 256 / C;
     dim3 grid(std::max(1, std::min(ceil_div(oh * ow, P * 8), 4 * 148 / std::max(1, std::min(B, 4)))), B);
     resize_argmax_kernel<C><<<grid, P * C, (size_t)P * C * 8, s>>>(x, y, H, W, oh, ow, (float)H / (float)oh, (float)W / (float)ow, P, key);
