@@ -56,6 +56,7 @@ SIGNATURES = {
     "h3d_calc_center_bb": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "h3d_crop_image_from_xy": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "h3d_detect_keypoints": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "h3d_upsample_detect_keypoints": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "h3d_pack_records": (_i, [_p, _p, _p, _p, _p, _i, _p, _p]),
     "h3d_gather_records_p2p": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, C.c_uint64, _i, _i, C.c_uint32, _i64, _p]),
     "h3d_decode_records": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p]),

@@ -115,12 +115,13 @@ struct StagePlan {
     std::vector<int> kinds;             // StepKind per step (profiling)
     std::vector<int64_t> step_flops;    // algorithmic FLOPs per step
     std::vector<TcConvPlan*> tc;
+    std::vector<FcChainPlan*> fc;
     std::vector<int> lane;              // per step: 0 = caller's stream, 1 = the context's side stream (independent branch)
     std::vector<char> join_before;      // per step: wait for the side stream before this step
     int cur_lane = 0;                   // lane given to steps as they are appended (see seal())
     int B = 0, H = 0, W = 0, variant = -1;
     int64_t flops = 0;
-    ~StagePlan() { for (auto* p : tc) tc_conv_plan_destroy(p); }
+    ~StagePlan() { for (auto* p : tc) tc_conv_plan_destroy(p); for (auto* p : fc) fc_chain_plan_destroy(p); }
     // label every step appended since the last call with the current lane
     void seal(bool join = false) {
         const size_t first = lane.size();
@@ -161,6 +162,7 @@ struct h3d_ctx {
     // atomic) before trapping, and the gather kernel stores 100 + peer when a peer never signals.  Readable by the host even
     // after the trap has poisoned the CUDA context (h3d_check_errors).
     int* err_flag = nullptr;
+    unsigned int* fc_counter = nullptr;      // ticket of the FC-chain kernel ("last cluster applies the rotation epilogue"), zero between launches
     // Operator entry points borrow scratch from here instead of allocating per call: grown geometrically on demand, old blocks
     // are retired (not freed) until h3d_destroy, so no call ever synchronises or frees.
     char* op_scratch = nullptr; int64_t op_scratch_bytes = 0;
@@ -600,6 +602,10 @@ static int ensure_vp_heads(h3d_ctx* ctx) {
         for (int i = 0; i < 128; ++i) w[i * 3 + j] = wi->second.data[i];
         b[j] = bi->second.data[0];
     }
+    HostTensor hw; hw.data = w; hw.shape = {128, 3};
+    HostTensor hb; hb.data = b; hb.shape = {3};
+    ctx->host_w["ViewpointNet/fc_vp_heads/weights"] = hw;      // fused ux | uy | uz heads: one 128 -> 3 layer of the FC chain
+    ctx->host_w["ViewpointNet/fc_vp_heads/biases"] = hb;
     H3D_CUDA(cudaMalloc(&ctx->vp_head_w, w.size() * 4)); H3D_CUDA(cudaMalloc(&ctx->vp_head_b, b.size() * 4));
     H3D_CUDA(cudaMemcpy(ctx->vp_head_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     H3D_CUDA(cudaMemcpy(ctx->vp_head_b, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
@@ -705,6 +711,84 @@ static int build_lifting(h3d_ctx* ctx, int B, int variant) {
         return add_tc(ctx, pl.get(), scope, l, B, 1, 1, x.s, x.stride, (int)align_up(in_f, 64), {}, y ? y->s : Split(), y ? y->stride : 0, 0, yf,
                       out_f, 0, 0, passes);
     };
+    // ---- FC stacks + Rodrigues / flip / rotate as ONE kernel (fc_chain_kernel): both pyramids first (ViewpointNet on the side
+    //      stream), their concat kernels, one join, one launch.  tune.fc_chain = 0 keeps the layer-by-layer path below.
+    const bool use_chain = tc_lift && tc_tuning().fc_chain != 0;
+    if (use_chain) {
+        if (bott) H3D_REQUIRE(xyz_in == 30, "bottleneck variant needs PosePrior/fc_xyz/weights of shape [30,63]");
+        else H3D_REQUIRE(xyz_in == 512, "PosePrior/fc_xyz/weights must have shape [512,63] for this variant");
+        FcChainDesc chains[2];
+        int64_t fl = 0;
+        auto fc_layer = [&](FcChainDesc& cd, const std::string& scope, const char* name, int in_f, int out_f, int leaky, const Planes& x, const Planes* y,
+                            float* yf, int yf_stride) -> int {
+            LayerSpec l{name, 1, 1, in_f, out_f, leaky};
+            const PackedW* pw;
+            int rc2 = get_packed(ctx, scope, l, (int)align_up(in_f, 64), {}, &pw, passes);
+            if (rc2) return rc2;
+            FcLayerDesc& d = cd.layer[cd.num_layers++];
+            d.x = x.s; d.x_stride = x.stride; d.in_features = in_f;
+            d.w = pw->w; d.bias = pw->bias; d.out_features = out_f; d.out_pad = pw->Cout_pad;
+            d.y = y ? y->s : Split(); d.y_stride = y ? y->stride : 0; d.yf = yf; d.yf_stride = yf_stride; d.leaky = leaky;
+            fl += 2ll * B * in_f * out_f;
+            return H3D_OK;
+        };
+        const bool proposed = variant == H3D_VARIANT_PROPOSED;
+        if (proposed) {
+            if ((rc = ensure_vp_heads(ctx))) return rc;
+            const Branch& b = br[1];
+            float* feat = nullptr;
+            pl->cur_lane = 1;
+            if ((rc = pyramid("ViewpointNet", kViewpoint, b, &feat))) return rc;
+            char* cur = b.slot[0];
+            const Planes xp = carve_planes(cur, 4098), p1 = carve_planes(cur, 256), p2 = carve_planes(cur, 128);
+            pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside_split(feat, e.hand_side, xp.s, B, 4096, xp.stride, half, s); });
+            pl->launches.push_back(1);
+            pl->seal();
+            pl->cur_lane = 0;
+            if ((rc = fc_layer(chains[1], "ViewpointNet", "fc_vp0", 4098, 256, 1, xp, &p1, nullptr, 0))) return rc;
+            if ((rc = fc_layer(chains[1], "ViewpointNet", "fc_vp1", 256, 128, 1, p1, &p2, nullptr, 0))) return rc;
+            if ((rc = fc_layer(chains[1], "ViewpointNet", "fc_vp_heads", 128, 3, 0, p2, nullptr, uxyz, 3))) return rc;    // ux | uy | uz (:303-308)
+        }
+        {
+            const Branch& b = br[0];
+            float* feat = nullptr;
+            if ((rc = pyramid("PosePrior", kPosePrior, b, &feat))) return rc;
+            char* cur = b.slot[0];
+            const Planes xp = carve_planes(cur, 2050), p1 = carve_planes(cur, 512), p2 = carve_planes(cur, 512), p3 = carve_planes(cur, 64);
+            pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_concat_handside_split(feat, e.hand_side, xp.s, B, 2048, xp.stride, half, s); });
+            pl->launches.push_back(1);
+            if ((rc = fc_layer(chains[0], "PosePrior", "fc_rel0", 2050, 512, 1, xp, &p1, nullptr, 0))) return rc;
+            if ((rc = fc_layer(chains[0], "PosePrior", "fc_rel1", 512, 512, 1, p1, &p2, nullptr, 0))) return rc;
+            if (bott) {
+                if ((rc = fc_layer(chains[0], "PosePrior", "fc_bottleneck", 512, 30, 0, p2, &p3, nullptr, 0))) return rc;
+                if ((rc = fc_layer(chains[0], "PosePrior", "fc_xyz", 30, 63, 0, p3, nullptr, can, 63))) return rc;
+            } else {
+                if ((rc = fc_layer(chains[0], "PosePrior", "fc_xyz", 512, 63, 0, p2, nullptr, can, 63))) return rc;
+            }
+            pl->seal();
+        }
+        FcChainPlan* fp = fc_chain_plan_create(chains, proposed ? 2 : 1, B, half, can, uxyz, ctx->fc_counter, ctx->err_flag);
+        if (!fp) return H3D_ECUDA;
+        pl->fc.push_back(fp);
+        const int var = variant;
+        pl->steps.push_back([=](const Ext& e, cudaStream_t s) {
+            int rc2 = fc_chain_launch(fp, e.hand_side, var == H3D_VARIANT_PROPOSED ? e.out3 : nullptr, var == H3D_VARIANT_PROPOSED ? e.out : nullptr, s);
+            if (rc2) return rc2;
+            if (var == H3D_VARIANT_LOCAL) {
+                if (e.out2) H3D_CUDA(cudaMemcpyAsync(e.out2, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
+                return launch_bone_rel_trafo_inv(can, e.out, B, s);     // nets/PosePriorNetwork.py:70-75
+            }
+            if (var != H3D_VARIANT_PROPOSED) H3D_CUDA(cudaMemcpyAsync(e.out, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
+            if (e.out2) H3D_CUDA(cudaMemcpyAsync(e.out2, can, (size_t)B * 63 * 4, cudaMemcpyDeviceToDevice, s));
+            return H3D_OK;
+        });
+        pl->launches.push_back(variant == H3D_VARIANT_LOCAL ? 2 : 1);
+        pl->flops += fl;
+        tag(pl.get(), KIND_TC, fl);
+        pl->seal(true);                                       // joins the ViewpointNet branch before the launch
+        ctx->lift = std::move(pl);
+        return H3D_OK;
+    }
     auto pose_prior = [&]() -> int {
         const Branch& b = br[0];
         float* feat = nullptr;
@@ -892,6 +976,11 @@ int h3d_create(h3d_ctx** out, int device) {
         return H3D_ECUDA;
     }
     *c->err_flag = 0;
+    if (cudaMalloc(&c->fc_counter, sizeof(unsigned int)) != cudaSuccess || cudaMemset(c->fc_counter, 0, sizeof(unsigned int)) != cudaSuccess) {
+        set_error("h3d_create: cannot allocate the FC-chain ticket (%s)", cudaGetErrorString(cudaGetLastError()));
+        h3d_destroy(c);
+        return H3D_ECUDA;
+    }
     tc_tuning();   // read the H3D_* environment switches now, never on a launch path
     *out = c;
     return H3D_OK;
@@ -924,6 +1013,7 @@ int h3d_destroy(h3d_ctx* ctx) {
     if (ctx->op_scratch) cudaFree(ctx->op_scratch);
     for (void* p : ctx->retired) cudaFree(p);
     if (ctx->err_flag) cudaFreeHost(ctx->err_flag);
+    if (ctx->fc_counter) cudaFree(ctx->fc_counter);
     delete ctx;
     return H3D_OK;
 }
@@ -1000,6 +1090,11 @@ int h3d_load_weight(h3d_ctx* ctx, const char* name, const float* host_data, cons
     }
     if (nm.find("fc_vp_u") != std::string::npos && ctx->vp_head_w) {
         cudaFree(ctx->vp_head_w); cudaFree(ctx->vp_head_b); ctx->vp_head_w = ctx->vp_head_b = nullptr;
+        ctx->host_w.erase("ViewpointNet/fc_vp_heads/weights"); ctx->host_w.erase("ViewpointNet/fc_vp_heads/biases");
+        for (auto pit = ctx->packed.begin(); pit != ctx->packed.end();) {
+            if (pit->first.compare(0, 25, "ViewpointNet/fc_vp_heads|") == 0) { free_packed(pit->second); pit = ctx->packed.erase(pit); }
+            else ++pit;
+        }
     }
     ctx->drop_plans();
     return H3D_OK;
@@ -1331,6 +1426,18 @@ int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int
     if (rc) return rc;
     int nl = 0;
     rc = launch_detect_keypoints(scoremaps, B, H, W, C, scratch, keypoints_uv, s, &nl);
+    ctx->launches += nl;
+    return rc;
+}
+int h3d_upsample_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int out_h, int out_w, float* scoremaps_up,
+                                  int32_t* keypoints_uv, void* stream) {
+    H3D_OP_PROLOGUE(ctx);
+    H3D_REQUIRE(scoremaps && scoremaps_up && keypoints_uv && B > 0, "h3d_upsample_detect_keypoints: bad argument");
+    char* scratch = nullptr;
+    int rc = op_scratch(ctx, argmax_scratch_bytes(B, 21), &scratch);
+    if (rc) return rc;
+    int nl = 0;
+    rc = launch_resize_argmax21(scoremaps, scoremaps_up, B, H, W, out_h, out_w, scratch, keypoints_uv, s, &nl);
     ctx->launches += nl;
     return rc;
 }

@@ -50,6 +50,37 @@ struct Split {
 
 enum class Half16 : int { BF16 = 0, FP16 = 1 };
 
+// ---------------------------------------------------------------- Rodrigues rotation (nets/ColorHandPose3DNetwork.py:311-334)
+// R[9] from the axis-angle vector (ux, uy, uz); separate multiply / add as the TF graph evaluates it.
+__device__ __forceinline__ void rodrigues_rot_mat(float ux_b, float uy_b, float uz_b, float* R) {
+    const float n2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux_b, ux_b), __fmul_rn(uy_b, uy_b)), __fmul_rn(uz_b, uz_b)), 1e-8f);
+    const float theta = sqrtf(n2);
+    const float st = sinf(theta), ct = cosf(theta);
+    const float one_ct = __fsub_rn(1.0f, ct);
+    const float nf = __fdiv_rn(1.0f, theta);
+    const float ux = __fmul_rn(ux_b, nf), uy = __fmul_rn(uy_b, nf), uz = __fmul_rn(uz_b, nf);
+#define H3D_M3(a, b_, c) __fmul_rn(__fmul_rn(a, b_), c)
+    R[0] = __fadd_rn(ct, H3D_M3(ux, ux, one_ct));
+    R[1] = __fsub_rn(H3D_M3(ux, uy, one_ct), __fmul_rn(uz, st));
+    R[2] = __fadd_rn(H3D_M3(ux, uz, one_ct), __fmul_rn(uy, st));
+    R[3] = __fadd_rn(H3D_M3(uy, ux, one_ct), __fmul_rn(uz, st));
+    R[4] = __fadd_rn(ct, H3D_M3(uy, uy, one_ct));
+    R[5] = __fsub_rn(H3D_M3(uy, uz, one_ct), __fmul_rn(ux, st));
+    R[6] = __fsub_rn(H3D_M3(uz, ux, one_ct), __fmul_rn(uy, st));
+    R[7] = __fadd_rn(H3D_M3(uz, uy, one_ct), __fmul_rn(ux, st));
+    R[8] = __fadd_rn(ct, H3D_M3(uz, uz, one_ct));
+#undef H3D_M3
+}
+
+// out[kp, j] = sum_i can[kp, i] R[i, j] with the right-hand mirror of z (nets/ColorHandPose3DNetwork.py:239-247,336-361)
+__device__ __forceinline__ float rotate_canonical_point(const float* can_b, const float* R, int i, bool right) {
+    const int kp = i / 3, j = i - kp * 3;
+    const float cx = can_b[3 * kp], cy = can_b[3 * kp + 1];
+    float cz = can_b[3 * kp + 2];
+    if (right) cz = -cz;
+    return cx * R[j] + cy * R[3 + j] + cz * R[6 + j];
+}
+
 // ---------------------------------------------------------------- launch counter
 struct LaunchCounter {
     int64_t n = 0;
@@ -162,10 +193,29 @@ struct TcTuning {
     int chunk_kb = 0;      // 0 policy
     int exp = 0;           // timing experiments (wrong results allowed), see TcParams::exp
     int no_side_stream = 0, no_pool_fusion = 0, lift_direct = 0, c3_ffma = 0;
+    int fc_chain = 1;      // FC stacks + rotation epilogue of the lifting stage as one kernel (0 = one launch per layer)
+    int pdl = 1;           // programmatic dependent launch between the tensor-core kernels (prologue overlaps the previous kernel's tail)
     int c3_tma = 1;        // first layer: shared-memory staged epilogue + bulk tensor stores (0 = direct 16-byte global stores)
 };
 TcTuning& tc_tuning();
 int tc_set_tuning(const char* key, int value);
+// FC stack of a lifting network as ONE kernel (conv_tc.cu: fc_chain_kernel): up to 4 fully connected layers per chain, the
+// activations of every layer as split planes [B, width_pad] (row stride = width rounded up to 64), the last layer fp32.
+struct FcLayerDesc {
+    Split x; int x_stride, in_features;      // input planes [B, x_stride], K = in_features rounded up to 64
+    Split w; const float* bias; int out_features, out_pad;   // packed weights [out_pad][K] (pack_conv_weights with k = 1)
+    Split y; int y_stride;                    // output planes (hidden layers) ...
+    float* yf; int yf_stride;                 // ... or fp32 output (last layer)
+    int leaky;
+};
+struct FcChainDesc { FcLayerDesc layer[4]; int num_layers = 0; };
+struct FcChainPlan;
+// chains: 1 (PosePrior only) or 2 (PosePrior, ViewpointNet + the fused Rodrigues / flip / rotate epilogue: can [B,63] and uxyz [B,3]
+// are the fp32 outputs of the two chains, hand_side / rot / out are bound at launch time)
+FcChainPlan* fc_chain_plan_create(const FcChainDesc* chains, int num_chains, int B, Half16 half, const float* can, const float* uxyz,
+                                  unsigned int* counter, int* err_flag);
+void fc_chain_plan_destroy(FcChainPlan* p);
+int fc_chain_launch(const FcChainPlan* p, const float* hand_side, float* rot, float* out, cudaStream_t s);
 TcConvPlan* tc_conv_plan_create(const TcConvDesc& d);   // nullptr on failure (h3d_last_error set)
 void tc_conv_plan_destroy(TcConvPlan* p);
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t s);

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -149,6 +150,15 @@ __device__ __forceinline__ void tc_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Programmatic dependent launch: every tensor-core kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so its
+// CTAs may become resident while the previous kernel of the stream is still draining (on SMs whose CTAs have already exited, or on
+// idle SMs when the previous grid is small) and run their prologue - barrier init, TMEM allocation, tensor-map prefetch, resident
+// weights - concurrently.  pdl_launch_dependents() lets the NEXT kernel do the same with respect to this one; pdl_wait() blocks until
+// every prerequisite grid has completed and its memory is visible, and is executed by every thread before it touches activations
+// (reads: TMA producer) or output / workspace buffers (writes: epilogue; ping-pong slots make those WAR-dependent on the previous layer).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- CTA-pair (cta_group::2) variants.  Shared-window addresses of a CTA in a cluster carry the CTA rank; clearing the
 // peer bit (cute::Sm100MmaPeerBitMask) makes a TMA completion / arrive land on the EVEN CTA's barrier at the same offset.
@@ -377,6 +387,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 4) {
         // ================================ TMA producer ================================
@@ -618,6 +630,8 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    if (!(warp == 4 && lane == 0)) pdl_wait();   // the TMA producer waits after it has issued the (static) weight loads
 
     if (warp == 4) {
         // ================================ TMA producer ================================
@@ -627,6 +641,7 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                 tma_load_2d(&map_w_hi, wsm + t * W_TAP_BYTES, w_full, t * BK, n0);
                 if (PASSES == 3) tma_load_2d(&map_w_lo, wsm + t * W_TAP_BYTES + 64 * BK * 2, w_full, t * BK, n0);
             }
+            pdl_wait();
             int stage = 0; uint32_t phase = 0;
             for (int tile = cta0; tile < p.num_tiles; tile += cta_step) {
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / (p.tiles_w * p.tiles_h);
@@ -778,6 +793,8 @@ conv_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp >= 8 && warp < 12) {
         // ================================ producers: build B once, then one A tile per iteration ================================
@@ -964,6 +981,8 @@ conv_c3_tma_kernel(const float* __restrict__ x, const float* __restrict__ w, con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp >= 8 && warp < 12) {
         // ================================ producers: build B once, then one A tile per iteration ================================
@@ -1194,6 +1213,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     cluster_sync_all();          // barriers of BOTH CTAs are initialised before any remote arrive / TMA completion
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 8) {
         // ================================ TMA producer (both CTAs) ================================
@@ -1406,6 +1427,8 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    if (!(warp == 8 && lane == 0)) pdl_wait();   // the TMA producer waits after it has issued the (static) weight loads
 
     if (warp == 8) {
         // ================================ TMA producer (both CTAs) ================================
@@ -1415,6 +1438,7 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                 tma_load_2d_2sm(&map_w_hi, wsm + t * C64X2_W_TAP_BYTES, w_full, t * BK, n0 + (int)rank * 32);
                 tma_load_2d_2sm(&map_w_lo, wsm + t * C64X2_W_TAP_BYTES + 32 * BK * 2, w_full, t * BK, n0 + (int)rank * 32);
             }
+            pdl_wait();
             int stage = 0; uint32_t phase = 0;
             for (int item = item0; item < p.num_tiles; item += item_step) {
                 const int mt = 2 * item + (int)rank;
@@ -1527,6 +1551,221 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------ FC stacks as ONE kernel
+// PosePrior (2050 -> 512 -> 512 -> 63, optional 30-wide bottleneck) and ViewpointNet (4098 -> 256 -> 128 -> 3) fully connected stacks
+// (nets/ColorHandPose3DNetwork.py:262-267,297-308; nets/PosePriorNetwork.py:113-116) followed by Rodrigues / flip / rotate
+// (:239-247,311-361) in a single launch instead of 5 GEMM launches + 2 split-K FC kernels + the rotation kernel.
+//  * A fully connected layer is the 1x1 case of the implicit GEMM above: M = 128 batch rows (TMA zero-fills rows >= B), N = 64 output
+//    features per tile, K = in_features in blocks of 64, 3-pass N-stacked UMMAs (hi*hi | hi*lo in one instruction, lo*hi in a second).
+//  * One CLUSTER of 8 CTAs per chain: CTA r of the cluster owns the N tiles r, r + 8, ... of every layer, so the 4.2 MB weight matrix of
+//    the first layer streams through 8 SMs.  Hidden activations go through global memory (L2-resident, <= 128 KB) as split planes;
+//    between layers every thread fences (generic -> async proxy, the next layer reads through TMA) and the cluster synchronises.
+//  * Shared-memory ring, TMEM accumulator double-buffering and barrier phases simply continue across layers (a layer is a tile loop).
+//  * Two chains = two clusters in the same grid.  The cluster that finishes LAST (atomic ticket at device scope) applies the
+//    Rodrigues / flip / rotate epilogue to the canonical coordinates and the view-point vector of both chains: no extra launch,
+//    no waiting.
+constexpr int kFcMaxLayers = 4;
+constexpr int kFcCluster = 8;
+struct FcLayer {
+    CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo;
+    TcParams p;            // epilogue parameters (bias, outputs, n_valid, leaky); B / geometry fields unused
+    int kblocks, m_tiles, n_tiles, pad_;
+};
+struct FcChain { FcLayer layer[kFcMaxLayers]; int num_layers; int pad_[3]; };
+struct FcChainParams {
+    FcChain chain[2];
+    int num_chains, B;
+    const float* can; const float* uxyz; const float* hand_side;   // rotate epilogue (num_chains == 2)
+    float* rot; float* out;
+    unsigned int* counter;
+    int* err_flag;
+};
+
+__device__ __forceinline__ void fc_layer_sync() {
+    __threadfence();                                        // the layer's outputs: visible at device scope ...
+    asm volatile("fence.proxy.async;" ::: "memory");        // ... and to the async proxy (the next layer's TMA loads)
+    cluster_sync_all();
+}
+
+template <bool FP16>
+__global__ void __cluster_dims__(kFcCluster, 1, 1) __launch_bounds__(kThreads, 1)
+fc_chain_kernel(const __grid_constant__ FcChainParams P) {
+    constexpr int BN = 64, PASSES = 3;
+    constexpr int STAGES = num_stages(BN, PASSES);
+    constexpr int STAGE_BYTES = stage_bytes(BN, PASSES);
+    constexpr int B_TILE_BYTES = BN * BK * 2;
+    constexpr uint32_t IDESC = make_idesc(BN, FP16);
+    constexpr uint32_t IDESC_STACK = make_idesc(2 * BN, FP16);
+    constexpr int ACC_COLS = 2 * BN;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    constexpr int kChunk = 9;                              // K blocks per TMEM partial sum (as the convolution kernels)
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    __shared__ int s_last;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const FcChain& ch = P.chain[blockIdx.x / kFcCluster];
+
+    if (warp == 4 && lane == 0) {
+        for (int l = 0; l < ch.num_layers; ++l) {
+            prefetch_tmap(&ch.layer[l].map_x_hi); prefetch_tmap(&ch.layer[l].map_x_lo);
+            prefetch_tmap(&ch.layer[l].map_w_hi); prefetch_tmap(&ch.layer[l].map_w_lo);
+        }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kNumEpilogueWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    // Every warp of every CTA of the cluster runs the SAME layer loop and reaches fc_layer_sync() exactly once per layer.
+    int stage = 0; uint32_t phase = 0; int acc_it = 0;
+    for (int l = 0; l < ch.num_layers; ++l) {
+        const FcLayer& L = ch.layer[l];
+        const int items = L.m_tiles * L.n_tiles;
+        if (warp == 4) {
+            // ================================ TMA producer ================================
+            if (lane == 0) {
+                for (int item = rank; item < items; item += kFcCluster) {
+                    const int nt = item % L.n_tiles, mt = item / L.n_tiles;
+                    for (int kb = 0; kb < L.kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, P.err_flag, 1);
+                        uint8_t* st = smem + stage * STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+                        tma_load_4d(&L.map_x_hi, st, &full_bar[stage], kb * BK, 0, 0, mt * BM);
+                        tma_load_4d(&L.map_x_lo, st + A_TILE_BYTES, &full_bar[stage], kb * BK, 0, 0, mt * BM);
+                        tma_load_2d(&L.map_w_hi, st + 2 * A_TILE_BYTES, &full_bar[stage], kb * BK, nt * BN);
+                        tma_load_2d(&L.map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kb * BK, nt * BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 5) {
+            // ================================ MMA issuer ================================
+            if (lane == 0) {
+                for (int item = rank; item < items; item += kFcCluster) {
+                    for (int kb0 = 0; kb0 < L.kblocks; kb0 += kChunk, ++acc_it) {
+                        const int acc = acc_it & 1;
+                        mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, P.err_flag, 2);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                        const int kb1 = min(L.kblocks, kb0 + kChunk);
+                        for (int kb = kb0; kb < kb1; ++kb) {
+                            mbar_wait(&full_bar[stage], phase, P.err_flag, 3);
+                            tc_fence_after();
+                            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
+                            const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
+#pragma unroll
+                            for (int j = 0; j < BK / UMMA_K; ++j) {
+                                const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                                tc_mma_f16(d_tmem, a_hi + koff, b_hi + koff, IDESC_STACK, (uint32_t)((kb > kb0) | (j != 0)));
+                                tc_mma_f16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+                            }
+                            tc_commit(&empty_bar[stage]);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                        tc_commit(&tfull_bar[acc]);
+                    }
+                }
+            }
+            __syncwarp();
+        } else {
+            // ================================ epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31 = batch rows) ================================
+            for (int item = rank; item < items; item += kFcCluster) {
+                const int nt = item % L.n_tiles, mt = item / L.n_tiles;
+                const int row = mt * BM + (int)threadIdx.x;
+                const bool valid = row < P.B;
+                float racc[BN];
+                for (int kb0 = 0; kb0 < L.kblocks; kb0 += kChunk, ++acc_it) {
+                    const int acc = acc_it & 1;
+                    mbar_wait(&tfull_bar[acc], (acc_it >> 1) & 1, P.err_flag, 4);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+#pragma unroll
+                    for (int c0 = 0; c0 < BN; c0 += 32) {
+                        uint32_t v[32];
+                        tc_ld_32x32b_x32(taddr + c0, v);
+                        tc_wait_ld();
+                        if (kb0 == 0) {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) racc[c0 + q] = __uint_as_float(v[q]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) racc[c0 + q] += __uint_as_float(v[q]);
+                        }
+                        tc_ld_32x32b_x32(taddr + BN + c0, v);      // + the hi*lo products of the stacked half
+                        tc_wait_ld();
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) racc[c0 + q] += __uint_as_float(v[q]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 32) epilogue_store32<PASSES, FP16>(L.p, &racc[c0], (int64_t)row, nt * BN + c0, valid);
+            }
+        }
+        fc_layer_sync();
+    }
+
+    // ---- last cluster to finish: Rodrigues + right-hand flip + rotation of the canonical coordinates (both chains' outputs)
+    if (P.num_chains == 2 && rank == 0) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(P.counter, 1u) == 1u;
+            if (s_last) *P.counter = 0u;                    // ready for the next launch (launches are stream ordered)
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int b = warp; b < P.B; b += kThreads / 32) {
+                float R[9];
+                if (lane == 0) rodrigues_rot_mat(__ldcg(P.uxyz + 3 * b), __ldcg(P.uxyz + 3 * b + 1), __ldcg(P.uxyz + 3 * b + 2), R);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) R[i] = __shfl_sync(0xFFFFFFFFu, R[i], 0);
+                if (P.rot && lane < 9) P.rot[9 * b + lane] = R[lane];
+                const bool right = P.hand_side[2 * b + 1] > P.hand_side[2 * b];
+                float cb[63 / 32 + 1];
+                (void)cb;
+                for (int i = lane; i < 63; i += 32) {
+                    float c3[3];
+                    const int kp = i / 3;
+                    c3[0] = __ldcg(P.can + 63 * b + 3 * kp); c3[1] = __ldcg(P.can + 63 * b + 3 * kp + 1); c3[2] = __ldcg(P.can + 63 * b + 3 * kp + 2);
+                    const int j = i - kp * 3;
+                    const float cz = right ? -c3[2] : c3[2];
+                    P.out[63 * b + i] = c3[0] * R[j] + c3[1] * R[3 + j] + cz * R[6 + j];
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+    cluster_sync_all();          // no CTA of the cluster exits while a peer may still be inside a cluster barrier
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1628,6 +1867,18 @@ static int smem_opt_in(K kernel, int bytes, bool* done /*[kMaxDevices]*/) {
     return H3D_OK;
 }
 
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait above); tune.pdl = 0 gives plain stream order.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tc_tuning().pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Tuning switches (A/B experiments, forced kernel variants in the tests).  Read from the environment ONCE, when the library
 // is first used, and changeable afterwards only through tc_set_tuning() (h3d_set_tuning): nothing on a launch path calls getenv.
 TcTuning& tc_tuning() {
@@ -1647,6 +1898,8 @@ TcTuning& tc_tuning() {
         v.lift_direct = geti("H3D_LIFT_DIRECT", 0);
         v.c3_ffma = geti("H3D_C3_FFMA", 0);
         v.c3_tma = geti("H3D_C3_TMA", 1);
+        v.pdl = geti("H3D_PDL", 1);
+        v.fc_chain = geti("H3D_FC_CHAIN", 1);
         return v;
     }();
     return t;
@@ -1667,6 +1920,8 @@ int tc_set_tuning(const char* key, int value) {
     else if (k == "lift_direct") t.lift_direct = value;
     else if (k == "c3_ffma") t.c3_ffma = value;
     else if (k == "c3_tma") t.c3_tma = value;
+    else if (k == "pdl") t.pdl = value;
+    else if (k == "fc_chain") t.fc_chain = value;
     else { set_error("h3d_set_tuning: unknown key '%s'", k.c_str()); return H3D_EINVAL; }
     return H3D_OK;
 }
@@ -1677,9 +1932,8 @@ int launch_inst(const TcConvPlan* pl, cudaStream_t s) {
     constexpr int smem = num_stages(BN, PASSES) * stage_bytes(BN, PASSES) + 1024 /*align slack*/ + 256 /*barriers*/;
     static bool attr[kMaxDevices] = {};
     if (int rc = smem_opt_in(conv_tc_kernel<BN, PASSES, FP16>, smem, attr)) return rc;
-    conv_tc_kernel<BN, PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->map_x_h8,
-                                                                      pl->map_w_l8, pl->p);
-    H3D_CHECK_LAUNCH();
+    H3D_CUDA(launch_pdl(conv_tc_kernel<BN, PASSES, FP16>, dim3(pl->grid), dim3(kThreads), smem, s, pl->map_x_hi, pl->map_x_lo, pl->map_w_hi,
+                        pl->map_w_lo, pl->map_x_h8, pl->map_w_l8, pl->p));
     return H3D_OK;
 }
 }  // namespace
@@ -1690,16 +1944,16 @@ int launch_c64(const TcConvPlan* pl, cudaStream_t s) {
     constexpr int smem = c64_smem_bytes(PASSES);
     static bool attr[kMaxDevices] = {};
     if (int rc = smem_opt_in(conv_c64_kernel<PASSES, FP16>, smem, attr)) return rc;
-    conv_c64_kernel<PASSES, FP16><<<pl->grid, kThreads, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
-    H3D_CHECK_LAUNCH();
+    H3D_CUDA(launch_pdl(conv_c64_kernel<PASSES, FP16>, dim3(pl->grid), dim3(kThreads), smem, s, pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo,
+                        pl->p));
     return H3D_OK;
 }
 template <bool FP16>
 int launch_c64x2(const TcConvPlan* pl, cudaStream_t s) {
     static bool attr[kMaxDevices] = {};
     if (int rc = smem_opt_in(conv_c64x2_kernel<FP16>, C64X2_SMEM, attr)) return rc;
-    conv_c64x2_kernel<FP16><<<pl->grid, kThreads2, C64X2_SMEM, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->p);
-    H3D_CHECK_LAUNCH();
+    H3D_CUDA(launch_pdl(conv_c64x2_kernel<FP16>, dim3(pl->grid), dim3(kThreads2), (size_t)C64X2_SMEM, s, pl->map_x_hi, pl->map_x_lo, pl->map_w_hi,
+                        pl->map_w_lo, pl->p));
     return H3D_OK;
 }
 }  // namespace
@@ -1711,9 +1965,8 @@ int launch_inst2(const TcConvPlan* pl, cudaStream_t s) {
     static_assert(smem <= 227 * 1024, "conv_tc2_kernel: shared memory budget");
     static bool attr[kMaxDevices] = {};
     if (int rc = smem_opt_in(conv_tc2_kernel<BN, PASSES, FP16>, smem, attr)) return rc;
-    conv_tc2_kernel<BN, PASSES, FP16><<<pl->grid, kThreads2, smem, s>>>(pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo, pl->map_x_h8,
-                                                                        pl->map_w_l8, pl->p);
-    H3D_CHECK_LAUNCH();
+    H3D_CUDA(launch_pdl(conv_tc2_kernel<BN, PASSES, FP16>, dim3(pl->grid), dim3(kThreads2), smem, s, pl->map_x_hi, pl->map_x_lo, pl->map_w_hi,
+                        pl->map_w_lo, pl->map_x_h8, pl->map_w_l8, pl->p));
     return H3D_OK;
 }
 }  // namespace
@@ -1884,17 +2137,70 @@ int launch_conv_c3_tc(const float* x, const float* w, const float* bias, Split y
         static bool at_h[kMaxDevices] = {}, at_b[kMaxDevices] = {};
         if (int rc = smem_opt_in(conv_c3_tma_kernel<true>, C3S_SMEM, at_h)) return rc;
         if (int rc = smem_opt_in(conv_c3_tma_kernel<false>, C3S_SMEM, at_b)) return rc;
-        if (half == Half16::FP16) conv_c3_tma_kernel<true><<<grid, C3T_THREADS, C3S_SMEM, s>>>(x, w, my_hi, my_lo, p);
-        else conv_c3_tma_kernel<false><<<grid, C3T_THREADS, C3S_SMEM, s>>>(x, w, my_hi, my_lo, p);
-        H3D_CHECK_LAUNCH();
+        if (half == Half16::FP16) H3D_CUDA(launch_pdl(conv_c3_tma_kernel<true>, dim3(grid), dim3(C3T_THREADS), (size_t)C3S_SMEM, s, x, w, my_hi, my_lo, p));
+        else H3D_CUDA(launch_pdl(conv_c3_tma_kernel<false>, dim3(grid), dim3(C3T_THREADS), (size_t)C3S_SMEM, s, x, w, my_hi, my_lo, p));
         return H3D_OK;
     }
     static bool attr_h[kMaxDevices] = {}, attr_b[kMaxDevices] = {};
     if (int rc = smem_opt_in(conv_c3_tc_kernel<true>, C3T_SMEM, attr_h)) return rc;
     if (int rc = smem_opt_in(conv_c3_tc_kernel<false>, C3T_SMEM, attr_b)) return rc;
-    if (half == Half16::FP16) conv_c3_tc_kernel<true><<<grid, C3T_THREADS, C3T_SMEM, s>>>(x, w, p);
-    else conv_c3_tc_kernel<false><<<grid, C3T_THREADS, C3T_SMEM, s>>>(x, w, p);
-    H3D_CHECK_LAUNCH();
+    if (half == Half16::FP16) H3D_CUDA(launch_pdl(conv_c3_tc_kernel<true>, dim3(grid), dim3(C3T_THREADS), (size_t)C3T_SMEM, s, x, w, p));
+    else H3D_CUDA(launch_pdl(conv_c3_tc_kernel<false>, dim3(grid), dim3(C3T_THREADS), (size_t)C3T_SMEM, s, x, w, p));
+    return H3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------ FC chain: host
+struct FcChainPlan { FcChainParams P; Half16 half; int grid; };
+
+FcChainPlan* fc_chain_plan_create(const FcChainDesc* chains, int num_chains, int B, Half16 half, const float* can, const float* uxyz,
+                                  unsigned int* counter, int* err_flag) {
+    if (num_chains < 1 || num_chains > 2 || B < 1) { set_error("fc_chain: bad geometry"); return nullptr; }
+    FcChainPlan* pl = new FcChainPlan();
+    memset(&pl->P, 0, sizeof(pl->P));
+    pl->half = half; pl->grid = num_chains * kFcCluster;
+    FcChainParams& P = pl->P;
+    P.num_chains = num_chains; P.B = B; P.can = can; P.uxyz = uxyz; P.counter = counter; P.err_flag = err_flag;
+    for (int c = 0; c < num_chains; ++c) {
+        const FcChainDesc& cd = chains[c];
+        if (cd.num_layers < 1 || cd.num_layers > kFcMaxLayers) { set_error("fc_chain: 1..4 layers per chain"); delete pl; return nullptr; }
+        P.chain[c].num_layers = cd.num_layers;
+        for (int l = 0; l < cd.num_layers; ++l) {
+            const FcLayerDesc& d = cd.layer[l];
+            FcLayer& L = P.chain[c].layer[l];
+            const int Kpad = (int)align_up(d.in_features, BK);
+            if (!d.x.hi || !d.x.lo || !d.w.hi || !d.w.lo || d.out_pad % 64 || d.x_stride < Kpad || (d.y.hi && (d.y_stride % 8))) {
+                set_error("fc_chain: bad layer %d of chain %d", l, c); delete pl; return nullptr;
+            }
+            bool ok = encode_act_map(&L.map_x_hi, d.x.hi, d.x_stride, Kpad, 1, 1, B, 1, 1, BM) &&
+                      encode_act_map(&L.map_x_lo, d.x.lo, d.x_stride, Kpad, 1, 1, B, 1, 1, BM) &&
+                      encode_w_map(&L.map_w_hi, d.w.hi, Kpad, d.out_pad, 64) && encode_w_map(&L.map_w_lo, d.w.lo, Kpad, d.out_pad, 64);
+            if (!ok) { delete pl; return nullptr; }
+            L.kblocks = Kpad / BK; L.m_tiles = ceil_div(B, BM); L.n_tiles = d.out_pad / 64;
+            TcParams& p = L.p;
+            p.bias = d.bias; p.y_hi = d.y.hi; p.y_lo = d.y.lo; p.Cy_total = d.y_stride; p.cy_off = 0; p.corr_scale = 1.f;
+            p.yf = d.yf; p.Cyf_total = d.yf_stride; p.cyf_off = 0;
+            p.B = B; p.H = 1; p.W = 1; p.k = 1; p.TW = 1; p.TH = 1; p.TB = BM;
+            p.n_valid = d.out_features; p.pool = 0; p.leaky = d.leaky; p.stack = 1; p.err_flag = err_flag;
+        }
+    }
+    return pl;
+}
+
+void fc_chain_plan_destroy(FcChainPlan* p) { delete p; }
+
+int fc_chain_launch(const FcChainPlan* pl, const float* hand_side, float* rot, float* out, cudaStream_t s) {
+    FcChainParams P = pl->P;
+    P.hand_side = hand_side; P.rot = rot; P.out = out;
+    H3D_REQUIRE(P.num_chains == 1 || (hand_side && out), "fc_chain: hand_side / out are required for the rotation epilogue");
+    constexpr int smem = num_stages(64, 3) * stage_bytes(64, 3) + 1024 + 256;
+    static bool at_h[kMaxDevices] = {}, at_b[kMaxDevices] = {};
+    if (pl->half == Half16::FP16) {
+        if (int rc = smem_opt_in(fc_chain_kernel<true>, smem, at_h)) return rc;
+        H3D_CUDA(launch_pdl(fc_chain_kernel<true>, dim3(pl->grid), dim3(kThreads), (size_t)smem, s, P));
+    } else {
+        if (int rc = smem_opt_in(fc_chain_kernel<false>, smem, at_b)) return rc;
+        H3D_CUDA(launch_pdl(fc_chain_kernel<false>, dim3(pl->grid), dim3(kThreads), (size_t)smem, s, P));
+    }
     return H3D_OK;
 }
 

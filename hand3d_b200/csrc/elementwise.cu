@@ -653,36 +653,13 @@ __global__ void rotate_canonical_kernel(const float* __restrict__ can, const flo
     const int b = blockIdx.x;
     __shared__ float R[9];
     if (threadIdx.x == 0) {
-        const float ux_b = uxyz[3 * b], uy_b = uxyz[3 * b + 1], uz_b = uxyz[3 * b + 2];
-        const float n2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(ux_b, ux_b), __fmul_rn(uy_b, uy_b)), __fmul_rn(uz_b, uz_b)), 1e-8f);
-        const float theta = sqrtf(n2);
-        const float st = sinf(theta), ct = cosf(theta);
-        const float one_ct = __fsub_rn(1.0f, ct);
-        const float nf = __fdiv_rn(1.0f, theta);
-        const float ux = __fmul_rn(ux_b, nf), uy = __fmul_rn(uy_b, nf), uz = __fmul_rn(uz_b, nf);
-#define M3(a, b_, c) __fmul_rn(__fmul_rn(a, b_), c)
-        R[0] = __fadd_rn(ct, M3(ux, ux, one_ct));
-        R[1] = __fsub_rn(M3(ux, uy, one_ct), __fmul_rn(uz, st));
-        R[2] = __fadd_rn(M3(ux, uz, one_ct), __fmul_rn(uy, st));
-        R[3] = __fadd_rn(M3(uy, ux, one_ct), __fmul_rn(uz, st));
-        R[4] = __fadd_rn(ct, M3(uy, uy, one_ct));
-        R[5] = __fsub_rn(M3(uy, uz, one_ct), __fmul_rn(ux, st));
-        R[6] = __fsub_rn(M3(uz, ux, one_ct), __fmul_rn(uy, st));
-        R[7] = __fadd_rn(M3(uz, uy, one_ct), __fmul_rn(ux, st));
-        R[8] = __fadd_rn(ct, M3(uz, uz, one_ct));
-#undef M3
+        rodrigues_rot_mat(uxyz[3 * b], uxyz[3 * b + 1], uxyz[3 * b + 2], R);
         if (rot)
             for (int i = 0; i < 9; ++i) rot[9 * b + i] = R[i];
     }
     __syncthreads();
     const bool right = hand_side[2 * b + 1] > hand_side[2 * b];   // argmax(hand_side,1)==1 (ties -> index 0)
-    for (int i = threadIdx.x; i < 63; i += blockDim.x) {
-        const int kp = i / 3, j = i - kp * 3;
-        const float cx = can[63 * b + 3 * kp], cy = can[63 * b + 3 * kp + 1];
-        float cz = can[63 * b + 3 * kp + 2];
-        if (right) cz = -cz;
-        out[63 * b + i] = cx * R[j] + cy * R[3 + j] + cz * R[6 + j];
-    }
+    for (int i = threadIdx.x; i < 63; i += blockDim.x) out[63 * b + i] = rotate_canonical_point(can + 63 * b, R, i, right);
 }
 
 // =============================================================================================

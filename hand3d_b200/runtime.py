@@ -361,6 +361,18 @@ class Context:
         _lib.check(self.lib.h3d_detect_keypoints(self.h, _ptr(scoremaps), B, H, W, Cc, _ptr(uv), _stream()), "h3d_detect_keypoints")
         return uv
 
+    def upsample_detect_keypoints(self, scoremaps, out_h, out_w):
+        """Fused tf.image.resize_images + detect_keypoints for 21-channel maps -> (maps [B,out_h,out_w,21], uv [B,21,2] int32)."""
+        scoremaps = _chk_f32(scoremaps, "scoremaps", 4)
+        B, H, W, Cc = scoremaps.shape
+        if Cc != 21:
+            raise ValueError("upsample_detect_keypoints expects 21 key-point channels")
+        up = torch.empty((B, out_h, out_w, 21), dtype=torch.float32, device=scoremaps.device)
+        uv = torch.empty((B, 21, 2), dtype=torch.int32, device=scoremaps.device)
+        _lib.check(self.lib.h3d_upsample_detect_keypoints(self.h, _ptr(scoremaps), B, H, W, int(out_h), int(out_w), _ptr(up), _ptr(uv), _stream()),
+                   "h3d_upsample_detect_keypoints")
+        return up, uv
+
     def decode_records(self, records, dataset="rhd", step=1, want_aux=True):
         """records: uint8 CUDA tensor [B, record_bytes] -> dict(image fp32 NHWC, header, mask, visibility)."""
         if records.dtype != torch.uint8 or not records.is_cuda or records.dim() != 2:

@@ -192,6 +192,10 @@ H3D_API int h3d_crop_image_from_xy(h3d_ctx* ctx, const float* image, const float
  * first occurrence of the maximum in row-major order. */
 H3D_API int h3d_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int C,
                          int32_t* keypoints_uv, void* stream);
+/* tf.image.resize_images (nets/ColorHandPose3DNetwork.py:96-97) fused with detect_keypoints: 21-channel score maps [B,H,W,21] ->
+ * scoremaps_up [B,out_h,out_w,21] and keypoints_uv [B,21,2] int32 (row, col) of the up-sampled maps in one pass. */
+H3D_API int h3d_upsample_detect_keypoints(h3d_ctx* ctx, const float* scoremaps, int B, int H, int W, int out_h, int out_w,
+                                          float* scoremaps_up, int32_t* keypoints_uv, void* stream);
 /* Per-image result record: coord3d [21,3] | keypoints_uv [21,2] i32 (bit-cast) | center [2] | scale_crop [1]
  * = 108 words = 432 B.  records [B,108]. */
 H3D_API int h3d_pack_records(h3d_ctx* ctx, const float* coord3d, const int32_t* keypoints_uv, const float* center,

@@ -217,3 +217,119 @@ def test_eval_util_device_matches_reference_semantics(ctx):
         got, exp = a.get_measures(0.0, 30.0, 20), ref.get_measures(0.0, 30.0, 20)
         for x, y in zip(got, exp):
             np.testing.assert_allclose(x, y, rtol=1e-6)
+
+
+@pytest.mark.parametrize("H,W,seed", [(100, 70, 7), (512, 512, 8), (41, 500, 9)])
+def test_seg_postprocess_odd_sizes(ctx, H, W, seed):
+    """widths that are not multiples of 32, the 512 x 512 limit, a map wider than tall: the log-step / van Herk dilation handles
+    partial words, partial 21-row blocks and the image borders like the literal 21 x 21 dilation"""
+    rng = np.random.default_rng(seed)
+    sm = _smooth_logits(rng, 2, H, W, amp=3.0, bias=-1.0)
+    r = ctx.seg_postprocess(_dev(sm))
+    mask = O.single_obj_scoremap(sm, literal=False)
+    center, _, size = O.calc_center_bb(mask)
+    np.testing.assert_array_equal(r["hand_mask"].cpu().numpy(), mask[..., 0].astype(np.uint8))
+    np.testing.assert_array_equal(r["center"].cpu().numpy(), center)
+    np.testing.assert_array_equal(r["crop_size"].cpu().numpy(), size)
+
+
+@pytest.mark.parametrize("shape,out", [((3, 32, 32), (256, 256)), ((2, 30, 40), (240, 320)), ((2, 16, 16), (32, 32)), ((1, 20, 12), (60, 36))])
+def test_upsample_detect_keypoints_fused(ctx, shape, out):
+    """h3d_upsample_detect_keypoints (the row-group kernel for power-of-two factors, the per-pixel kernel otherwise) against the oracle:
+    bit-exact up-sampled map and first-occurrence indices, incl. the plateaus the edge replication creates."""
+    rng = np.random.default_rng(21)
+    B, H, W = shape
+    s = rng.normal(size=(B, H, W, 21)).astype(f32)
+    s[0, H - 1, W - 1, 4] = 50.0        # maximum in the replicated corner: a plateau whose first occurrence is its top-left pixel
+    s[0, 5, :, 2] = 7.0                 # a whole input row at the maximum
+    s[B - 1, :, :, 9] = 0.25            # constant channel -> (0, 0)
+    up, uv = ctx.upsample_detect_keypoints(_dev(s), *out)
+    ref = T.resize_bilinear_tf1(s, *out)
+    np.testing.assert_array_equal(up.cpu().numpy(), ref)
+    for b in range(B):
+        np.testing.assert_array_equal(uv.cpu().numpy()[b], O.detect_keypoints(ref[b]).astype(np.int32))
+
+
+def test_calc_center_bb_leaky_relu_flip_pack(ctx):
+    """the reference helpers that were eager torch in round 1 now run one kernel each"""
+    from hand3d_b200.utils.general import NetworkOps, calc_center_bb
+    from hand3d_b200.nets.ColorHandPose3DNetwork import ColorHandPose3DNetwork
+    from hand3d_b200.distributed import pack_records
+    rng = np.random.default_rng(22)
+    mask = (rng.uniform(size=(4, 60, 80, 1)) > 0.995).astype(f32)
+    mask[1] = 0.0                                               # empty -> fall-backs
+    mask[2, 10:30, 5:60, 0] = 1.0
+    mask[3] *= 2.0                                              # values != 1 do not count (tf.equal(mask, 1))
+    c, bb, sz = calc_center_bb(_dev(mask))
+    rc, rbb, rsz = O.calc_center_bb(mask)
+    np.testing.assert_array_equal(c.cpu().numpy(), rc)
+    np.testing.assert_array_equal(sz.cpu().numpy(), rsz)
+    assert tuple(bb.shape) == (4, 2, 2) and torch.isinf(bb[1]).all()
+    np.testing.assert_array_equal(bb[2].cpu().numpy(), [[10, 29], [5, 59]])
+    x = rng.normal(size=(3, 7, 5, 13)).astype(f32)
+    np.testing.assert_array_equal(NetworkOps.leaky_relu(_dev(x)).cpu().numpy(), T.leaky_relu(x))
+    xyz = rng.normal(size=(5, 21, 3)).astype(f32)
+    cond = np.array([True, False, True, True, False])
+    out = ColorHandPose3DNetwork._flip_right_hand(_dev(xyz), torch.from_numpy(cond).cuda().reshape(5, 1, 1).expand(5, 21, 3)).cpu().numpy()
+    ref = xyz.copy(); ref[cond, :, 2] *= -1
+    np.testing.assert_array_equal(out, ref)
+    uvk = rng.integers(0, 256, size=(5, 21, 2)).astype(np.int32)
+    cen = rng.normal(size=(5, 2)).astype(f32); scl = rng.uniform(0.5, 2, size=(5, 1)).astype(f32)
+    rec = pack_records(_dev(xyz), torch.from_numpy(uvk).cuda(), _dev(cen), _dev(scl)).cpu()
+    ref_rec = pack_records(torch.from_numpy(xyz), torch.from_numpy(uvk), torch.from_numpy(cen), torch.from_numpy(scl))
+    assert torch.equal(rec.view(torch.int32), ref_rec.view(torch.int32))
+
+
+def test_operator_entries_enqueue_only(ctx):
+    """include/hand3d_b200.h: operator entries never allocate or synchronise per call.  (1) After one warm-up round the driver's free
+    memory does not move across a second round of direct C-ABI calls; (2) the calls can be captured into a CUDA graph (stream capture
+    rejects cudaMalloc / cudaFree / synchronisation) and the replay reproduces the eager results."""
+    import ctypes as C
+    from hand3d_b200 import _lib
+    rng = np.random.default_rng(23)
+    L = ctx.lib
+    logits = _dev(_smooth_logits(rng, 2, 64, 96, amp=2.0, bias=-1.0))
+    sm = _dev(rng.normal(size=(2, 32, 32, 21)).astype(f32))
+    fx = _dev(rng.normal(size=(4, 300)).astype(f32)); fw = _dev(rng.normal(size=(300, 40)).astype(f32)); fb = _dev(rng.normal(size=40).astype(f32))
+    cx = _dev(rng.normal(size=(2, 16, 16, 64)).astype(f32))
+    wk = (rng.normal(size=(3, 3, 64, 64)) / 24).astype(f32)
+    pk = ctx.pack_conv(wk, np.zeros(64, f32), "bf16x3")
+    outs = {"mask": torch.empty((2, 64, 96), dtype=torch.uint8, device="cuda"), "loc": torch.empty((2, 2), dtype=torch.int32, device="cuda"),
+            "center": torch.empty((2, 2), device="cuda"), "size": torch.empty((2, 1), device="cuda"), "scale": torch.empty((2, 1), device="cuda"),
+            "uv": torch.empty((2, 21, 2), dtype=torch.int32, device="cuda"), "fy": torch.empty((4, 40), device="cuda"),
+            "cy": torch.empty((2, 16, 16, 64), device="cuda"), "ty": torch.empty((2, 8, 8, 64), device="cuda")}
+    p = lambda t: C.c_void_p(t.data_ptr())     # noqa: E731
+
+    def round_(stream):
+        st = C.c_void_p(stream)
+        _lib.check(L.h3d_seg_postprocess(ctx.h, p(logits), 2, 64, 96, p(outs["mask"]), p(outs["loc"]), p(outs["center"]), p(outs["size"]), p(outs["scale"]), st))
+        _lib.check(L.h3d_detect_keypoints(ctx.h, p(sm), 2, 32, 32, 21, p(outs["uv"]), st))
+        _lib.check(L.h3d_fully_connected_f32(ctx.h, p(fx), p(fw), p(fb), p(outs["fy"]), 4, 300, 40, 1, st))
+        _lib.check(L.h3d_conv2d_tc_packed(ctx.h, p(cx), pk.h, p(outs["cy"]), 2, 16, 16, 1, 1, st))
+        _lib.check(L.h3d_conv2d_f32(ctx.h, p(cx), p(_w), p(_b), p(outs["ty"]), 2, 16, 16, 64, 64, 3, 2, 1, st))
+
+    _w = _dev(wk); _b = _dev(np.zeros(64, f32))
+    cur = torch.cuda.current_stream().cuda_stream
+    round_(cur); torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(3):
+        round_(cur)
+    free1 = torch.cuda.mem_get_info()[0]
+    torch.cuda.synchronize()
+    assert free0 == free1, "an operator entry allocated device memory per call (%d -> %d bytes free)" % (free0, free1)
+    eager = {k: v.clone() for k, v in outs.items()}
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for v in outs.values():
+            v.zero_()
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(g):
+        round_(torch.cuda.current_stream().cuda_stream)
+    g.replay(); torch.cuda.synchronize()
+    for k in outs:
+        assert torch.equal(outs[k], eager[k]), k
+    ref = T.leaky_relu(T.conv2d_same(cx.cpu().numpy(), wk, np.zeros(64, f32), 1, np.float64))
+    assert np.abs(outs["cy"].cpu().numpy() - ref).max() < 5e-5
+    ctx.check_errors()
