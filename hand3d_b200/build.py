@@ -62,11 +62,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [_nvcc(), "-shared", "--cudart=static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    tmp = LIB + ".tmp"       # link next to the target and rename: a reader (or a repo snapshot) never sees a half-written library
+    cmd = [_nvcc(), "-shared", "--cudart=static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
+    os.replace(tmp, LIB)
     with open(os.path.join(HERE, "build", "nvcc.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

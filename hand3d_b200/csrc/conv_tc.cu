@@ -60,7 +60,7 @@ struct TcParams {
     int leaky;
     int stack;      // N-stacked passes (generic single-CTA kernel, 3-pass, BN <= 128); 0 = three separate UMMAs per K step
     int exp;        // timing experiments only (tc_set_tuning("tc_exp")): bit 0 drops the lo*hi UMMA (WRONG results), bit 1 issues the
-                    // UMMAs of a stage grouped by shape instead of interleaved (conv_c64x2_kernel)
+                    // UMMAs of a stage grouped by shape instead of interleaved, bit 2 disables the L2 prefetch (conv_c64x2_kernel)
     int* err_flag;
 };
 
@@ -107,6 +107,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// TMA prefetch of a tensor box into L2 (no shared-memory destination, no barrier): used to run further ahead of the shared-memory ring
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -1440,7 +1445,23 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
             }
             pdl_wait();
             int stage = 0; uint32_t phase = 0;
+            // The kernel is bound by the latency of its patch loads, not by the tensor pipe (ncu r02d: dropping a third of the UMMAs
+            // changes the run time by 3 %; three 40 KB stages in flight against ~2.7 us per stage from DRAM): the patches of the tile
+            // TWO iterations ahead are prefetched into L2 (one 18-pixel-wide box covers the three kw-shifted patches), so the
+            // shared-memory ring is filled at L2 latency.
+            auto prefetch_item = [&](int it) {
+                if (it >= p.num_tiles) return;
+                const int m2 = 2 * it + (int)rank;
+                const int tw2 = m2 % p.tiles_w, th2 = (m2 / p.tiles_w) % p.tiles_h, tb2 = m2 / (p.tiles_w * p.tiles_h);
+                if (tb2 >= p.B) return;
+                for (int kw = 0; kw < 3; kw += 2) {     // boxes at kw = 0 and kw = 2 cover pixels w0 .. w0 + 17
+                    tma_prefetch_4d(&map_x_hi, 0, tw2 * C64_TW - 1 + kw, th2 * C64_TH - 1, tb2);
+                    tma_prefetch_4d(&map_x_lo, 0, tw2 * C64_TW - 1 + kw, th2 * C64_TH - 1, tb2);
+                }
+            };
+            if (!(p.exp & 4)) { prefetch_item(item0); prefetch_item(item0 + item_step); }
             for (int item = item0; item < p.num_tiles; item += item_step) {
+                if (!(p.exp & 4)) prefetch_item(item + 2 * item_step);
                 const int mt = 2 * item + (int)rank;
                 const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
                 const int w0 = tw * C64_TW - 1, h0 = th * C64_TH - 1;

@@ -378,6 +378,7 @@ __global__ void seg_prob_kernel(const float2* __restrict__ logits, int H, int W,
 constexpr int kGrowThreads = 1024;
 constexpr int kMaxMaskWords = 512 * 16;  // H, W <= 512
 constexpr int kMaxRowWords = 16;         // W <= 512
+constexpr int kWordsPerThread = kMaxMaskWords / kGrowThreads;   // 8
 
 __global__ void __launch_bounds__(kGrowThreads, 1)
 mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ det_g, int H, int W, int Ww,
@@ -416,6 +417,17 @@ mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __r
     uint32_t* pre = sm + 3 * H * Ww;        // [H][Ww]
     uint32_t* suf = sm + 4 * H * Ww;        // [H][Ww]
     const int nblk = (H + 20) / 21;
+    // per-thread constants of the combine phase (word i = tid + q * 1024): window [a, b] = [y-10, y+10] clipped to the image; inside one
+    // 21-row block it is a prefix (mode 0: the window starts at the block's first row) or a suffix (mode 1), else suffix | prefix (mode 2)
+    int c_a[kWordsPerThread], c_b[kWordsPerThread], c_mode[kWordsPerThread];
+#pragma unroll
+    for (int q = 0; q < kWordsPerThread; ++q) {
+        const int i = tid + q * kGrowThreads;
+        const int y = i / Ww, xw = i - y * Ww;
+        const int a = max(y - 10, 0), b2 = min(y + 10, H - 1);
+        c_a[q] = a * Ww + xw; c_b[q] = b2 * Ww + xw;
+        c_mode[q] = (a / 21 == b2 / 21) ? ((a % 21 == 0) ? 0 : 1) : 2;
+    }
     for (int pass = 0; pass < num_passes; ++pass) {
         if (tid == 0) s_changed = 0;
         if (tid < H) {
@@ -441,23 +453,27 @@ mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __r
         __syncthreads();
         for (int t = tid; t < nblk * Ww; t += kGrowThreads) {
             const int k = t / Ww, xw = t - k * Ww;
-            const int y0 = 21 * k, y1 = min(y0 + 20, H - 1);
+            const int y0 = 21 * k, n = min(21, H - y0);
             uint32_t a = 0u;
-            for (int y = y0; y <= y1; ++y) { a |= hor[y * Ww + xw]; pre[y * Ww + xw] = a; }
+#pragma unroll
+            for (int q = 0; q < 21; ++q)
+                if (q < n) { a |= hor[(y0 + q) * Ww + xw]; pre[(y0 + q) * Ww + xw] = a; }
             a = 0u;
-            for (int y = y1; y >= y0; --y) { a |= hor[y * Ww + xw]; suf[y * Ww + xw] = a; }
+#pragma unroll
+            for (int q = 20; q >= 0; --q)
+                if (q < n) { a |= hor[(y0 + q) * Ww + xw]; suf[(y0 + q) * Ww + xw] = a; }
         }
         __syncthreads();
         int changed = 0;
-        for (int i = tid; i < words; i += kGrowThreads) {
-            const int y = i / Ww, xw = i - y * Ww;
-            const int a = max(y - 10, 0), b2 = min(y + 10, H - 1);
-            uint32_t r;
-            if (a / 21 == b2 / 21) r = (a % 21 == 0) ? pre[b2 * Ww + xw] : suf[a * Ww + xw];   // window inside one block: it starts at the block's first row or ends at its last
-            else r = suf[a * Ww + xw] | pre[b2 * Ww + xw];
-            r &= det[i];
-            changed |= (r != obj[i]);
-            obj[i] = r;                      // obj is not read by anybody else in this phase
+#pragma unroll
+        for (int q = 0; q < kWordsPerThread; ++q) {
+            const int i = tid + q * kGrowThreads;
+            if (i < words) {
+                uint32_t r = c_mode[q] == 0 ? pre[c_b[q]] : c_mode[q] == 1 ? suf[c_a[q]] : (suf[c_a[q]] | pre[c_b[q]]);
+                r &= det[i];
+                changed |= (r != obj[i]);
+                obj[i] = r;                  // obj is not read by anybody else in this phase
+            }
         }
         if (changed) s_changed = 1;
         __syncthreads();
@@ -538,11 +554,11 @@ int launch_seg_postprocess(const float* logits, int B, int H, int W, void* scrat
 // =============================================================================================
 __global__ void crop_image_kernel(const float* __restrict__ image, const float* __restrict__ center,
                                   const float* __restrict__ scale, float* __restrict__ out, int B, int H, int W, int C, int crop) {
-    const int64_t total = (int64_t)B * crop * crop;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % crop);
-        const int y = (int)((i / crop) % crop);
-        const int b = (int)(i / ((int64_t)crop * crop));
+    // blockIdx.y = image; the box arithmetic of utils/general.py:181-191 and of crop_and_resize_op.cc is per image: computed once per CTA
+    __shared__ float s_par[6];   // y1n * (H-1), x1n * (W-1), height scale, width scale, single-row in_y, single-col in_x
+    const int b = blockIdx.y;
+    const float hm1 = (float)(H - 1), wm1 = (float)(W - 1);
+    if (threadIdx.x == 0) {
         const float cs = (float)crop;
         const float css = __fdiv_rn(cs, scale[b]);                       // :182
         const float half = floorf(__fdiv_rn(css, 2.0f));                 // float '//' (:183,185)
@@ -550,14 +566,23 @@ __global__ void crop_image_kernel(const float* __restrict__ image, const float* 
         const float x1 = __fsub_rn(center[2 * b + 1], half), x2 = __fadd_rn(x1, css);
         const float y1n = __fdiv_rn(y1, (float)H), y2n = __fdiv_rn(y2, (float)H);   // :187-190 (H, W -- not H-1)
         const float x1n = __fdiv_rn(x1, (float)W), x2n = __fdiv_rn(x2, (float)W);
-        const float hm1 = (float)(H - 1), wm1 = (float)(W - 1);
-        const float hs = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(y2n, y1n), hm1), (float)(crop - 1)) : 0.f;
-        const float ws = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(x2n, x1n), wm1), (float)(crop - 1)) : 0.f;
-        const float in_y = crop > 1 ? __fadd_rn(__fmul_rn(y1n, hm1), __fmul_rn((float)y, hs))
-                                    : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1n, y2n)), hm1);
-        const float in_x = crop > 1 ? __fadd_rn(__fmul_rn(x1n, wm1), __fmul_rn((float)x, ws))
-                                    : __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1n, x2n)), wm1);
-        float* dst = out + i * C;
+        s_par[0] = __fmul_rn(y1n, hm1);
+        s_par[1] = __fmul_rn(x1n, wm1);
+        s_par[2] = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(y2n, y1n), hm1), (float)(crop - 1)) : 0.f;
+        s_par[3] = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(x2n, x1n), wm1), (float)(crop - 1)) : 0.f;
+        s_par[4] = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1n, y2n)), hm1);
+        s_par[5] = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1n, x2n)), wm1);
+    }
+    __syncthreads();
+    const float oy = s_par[0], ox = s_par[1], hs = s_par[2], ws = s_par[3];
+    const float* img = image + (int64_t)b * H * W * C;
+    float* ob = out + (int64_t)b * crop * crop * C;
+    const int total = crop * crop;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / crop, x = i - y * crop;
+        const float in_y = crop > 1 ? __fadd_rn(oy, __fmul_rn((float)y, hs)) : s_par[4];
+        const float in_x = crop > 1 ? __fadd_rn(ox, __fmul_rn((float)x, ws)) : s_par[5];
+        float* dst = ob + (int64_t)i * C;
         const bool valid = !(in_y < 0.f || in_y > hm1) && !(in_x < 0.f || in_x > wm1);
         if (!valid) {
             for (int c = 0; c < C; ++c) dst[c] = 0.f;
@@ -566,20 +591,28 @@ __global__ void crop_image_kernel(const float* __restrict__ image, const float* 
         const int top = (int)floorf(in_y), bot = (int)ceilf(in_y);
         const int lef = (int)floorf(in_x), rig = (int)ceilf(in_x);
         const float ly = __fsub_rn(in_y, (float)top), lx = __fsub_rn(in_x, (float)lef);
-        const float* img = image + (int64_t)b * H * W * C;
-        for (int c = 0; c < C; ++c) {
-            const float tl = __ldg(img + ((int64_t)top * W + lef) * C + c), tr = __ldg(img + ((int64_t)top * W + rig) * C + c);
-            const float bl = __ldg(img + ((int64_t)bot * W + lef) * C + c), br = __ldg(img + ((int64_t)bot * W + rig) * C + c);
-            dst[c] = lerp_tf(lerp_tf(tl, tr, lx), lerp_tf(bl, br, lx), ly);
+        const float* ptl = img + ((int64_t)top * W + lef) * C;
+        const float* ptr = img + ((int64_t)top * W + rig) * C;
+        const float* pbl = img + ((int64_t)bot * W + lef) * C;
+        const float* pbr = img + ((int64_t)bot * W + rig) * C;
+        if (C == 3) {   // the RGB image of the hot path: twelve independent loads in flight, three coalesced stores
+            const float tl0 = __ldg(ptl), tl1 = __ldg(ptl + 1), tl2 = __ldg(ptl + 2), tr0 = __ldg(ptr), tr1 = __ldg(ptr + 1), tr2 = __ldg(ptr + 2);
+            const float bl0 = __ldg(pbl), bl1 = __ldg(pbl + 1), bl2 = __ldg(pbl + 2), br0 = __ldg(pbr), br1 = __ldg(pbr + 1), br2 = __ldg(pbr + 2);
+            dst[0] = lerp_tf(lerp_tf(tl0, tr0, lx), lerp_tf(bl0, br0, lx), ly);
+            dst[1] = lerp_tf(lerp_tf(tl1, tr1, lx), lerp_tf(bl1, br1, lx), ly);
+            dst[2] = lerp_tf(lerp_tf(tl2, tr2, lx), lerp_tf(bl2, br2, lx), ly);
+        } else {
+            for (int c = 0; c < C; ++c)
+                dst[c] = lerp_tf(lerp_tf(__ldg(ptl + c), __ldg(ptr + c), lx), lerp_tf(__ldg(pbl + c), __ldg(pbr + c), lx), ly);
         }
     }
 }
 
 int launch_crop_image(const float* image, const float* center, const float* scale, float* out, int B, int H, int W, int C,
                       int crop, cudaStream_t s) {
-    const int64_t total = (int64_t)B * crop * crop;
-    crop_image_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 148 * 16), 256, 0, s>>>(image, center, scale, out, B, H,
-                                                                                             W, C, crop);
+    const int total = crop * crop;
+    dim3 grid((unsigned)std::max(1, std::min(ceil_div(total, 256), 148 * 16 / std::max(1, std::min(B, 16)))), B);
+    crop_image_kernel<<<grid, 256, 0, s>>>(image, center, scale, out, B, H, W, C, crop);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }

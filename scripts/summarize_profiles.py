@@ -40,28 +40,30 @@ def main():
             d = by_id.setdefault(r["ID"], {"name": short(r["Kernel Name"]), "grid": r["Grid Size"]})
             d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
         names = [(d["name"], d.get("gpu__time_duration.sum", 0.0) / 1e3, d["grid"], d) for d in by_id.values()]
-        ends = [i for i, (n, _, _, _) in enumerate(names) if "CatArray" in n]
+        ends = [i for i, (n, _, _, _) in enumerate(names) if "CatArray" in n or "pack_records_kernel" in n]   # last kernel of a single-GPU step
         s, e = (ends[2] + 1, ends[3] + 1) if len(ends) > 3 else (0, len(names))
         step = names[s:e]
         have_dram = any("dram__bytes_read.sum" in d for _, _, _, d in step)
         agg = collections.OrderedDict()
         for n, v, g, d in step:
-            a_ = agg.setdefault(n, [0.0, 0, 0.0, 0.0])
+            a_ = agg.setdefault(n, [0.0, 0, 0.0, 0.0, 0.0])
             a_[0] += v; a_[1] += 1
             a_[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
             a_[3] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * v
+            a_[4] += d.get("sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * v
         tot = sum(v for _, v, _, _ in step)
         with open("profiles/%s_launches.md" % a.tag, "w") as f:
             f.write("# %s: every launch of one bench step (ncu --metrics gpu__time_duration.sum[,dram__bytes_*,sm__pipe_tensor_cycles_active] --clock-control none)\n\n" % a.tag)
             f.write("Command: `ncu ... python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (B = 32, 320x320, bf16x3). "
                     "Per-launch times are cold-cache and serialised: compare SHARES.  HBM GB/s = (DRAM read + write bytes) / duration "
                     "(measured peak copy bandwidth of this pool: 6576 GB/s, MEASURED_PEAKS.json).\n\n")
-            f.write("| kernel | launches | total us | share | DRAM MB | HBM GB/s | tensor pipe active % (time-weighted) |\n|---|---:|---:|---:|---:|---:|---:|\n")
-            for n, (v, c, byt, tp) in sorted(agg.items(), key=lambda x: -x[1][0]):
-                f.write("| `%s` | %d | %.1f | %.1f %% | %s | %s | %s |\n" % (
+            f.write("| kernel | launches | total us | share | DRAM MB | HBM GB/s | tensor pipe active % (time-weighted) | tensor unit busy % (`sm__pipe_tc_cycles_active`) |\n|---|---:|---:|---:|---:|---:|---:|---:|\n")
+            for n, (v, c, byt, tp, tcb) in sorted(agg.items(), key=lambda x: -x[1][0]):
+                f.write("| `%s` | %d | %.1f | %.1f %% | %s | %s | %s | %s |\n" % (
                     n, c, v, 100 * v / tot, "%.1f" % (byt / 1e6) if have_dram else "-",
-                    "%.0f" % (byt / 1e3 / v) if have_dram and v > 0 else "-", "%.1f" % (tp / v) if have_dram and v > 0 else "-"))
-            f.write("| **sum** | %d | %.1f | 100 %% | %s | | |\n\n" % (len(step), tot, "%.1f" % (sum(x[2] for x in agg.values()) / 1e6) if have_dram else "-"))
+                    "%.0f" % (byt / 1e3 / v) if have_dram and v > 0 else "-", "%.1f" % (tp / v) if have_dram and v > 0 else "-",
+                    "%.1f" % (tcb / v) if have_dram and v > 0 else "-"))
+            f.write("| **sum** | %d | %.1f | 100 %% | %s | | | |\n\n" % (len(step), tot, "%.1f" % (sum(x[2] for x in agg.values()) / 1e6) if have_dram else "-"))
             f.write("## launch list\n\n| # | kernel | grid | us | DRAM read MB | DRAM write MB | HBM GB/s | tensor pipe % |\n|---:|---|---|---:|---:|---:|---:|---:|\n")
             for i, (n, v, g, d) in enumerate(step):
                 rd, wr = d.get("dram__bytes_read.sum", 0.0), d.get("dram__bytes_write.sum", 0.0)

@@ -258,6 +258,7 @@ def test_calc_center_bb_leaky_relu_flip_pack(ctx):
     rng = np.random.default_rng(22)
     mask = (rng.uniform(size=(4, 60, 80, 1)) > 0.995).astype(f32)
     mask[1] = 0.0                                               # empty -> fall-backs
+    mask[2] = 0.0
     mask[2, 10:30, 5:60, 0] = 1.0
     mask[3] *= 2.0                                              # values != 1 do not count (tf.equal(mask, 1))
     c, bb, sz = calc_center_bb(_dev(mask))
