@@ -59,8 +59,7 @@ struct TcParams {
     int chunk_kb;   // K blocks accumulated inside the tensor core before the epilogue folds the partial sum into fp32 registers
     int leaky;
     int stack;      // N-stacked passes (generic single-CTA kernel, 3-pass, BN <= 128); 0 = three separate UMMAs per K step
-    int exp;        // timing experiments only (tc_set_tuning("tc_exp")): bit 0 drops the lo*hi UMMA (WRONG results), bit 1 issues the
-                    // UMMAs of a stage grouped by shape instead of interleaved, bit 2 disables the L2 prefetch (conv_c64x2_kernel)
+    int exp;        // reserved for timing experiments (tc_set_tuning("tc_exp")); unused by the shipped kernels
     int* err_flag;
 };
 
@@ -164,6 +163,19 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 // (reads: TMA producer) or output / workspace buffers (writes: epilogue; ping-pong slots make those WAR-dependent on the previous layer).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// One elected lane of a converged warp.  The role warps (TMA producer, MMA issuer) run their loops with ALL 32 lanes in warp-uniform
+// control flow and wrap only the issuing instructions in `if (elect_one())`: addresses, descriptors and loop state are then
+// warp-uniform values that ptxas keeps in uniform registers, and UTCHMMA / UTMALDG / UTCBAR read their operands straight from them.
+// With `if (lane == 0)` around the whole loop (round 1) the operands were per-thread values and every tcgen05.mma was wrapped in a
+// divergence "waterfall" (ELECT + 5 R2UR.BROADCAST + BRA.U.ANY, ~20 dependent instructions): ~85 issue cycles per UMMA against 32-64
+// tensor cycles for the N = 64 / 128 instructions of the 64-channel kernels, which left their tensor pipe half idle (ncu r02f: the
+// issuer never waits on a barrier, yet the pipe computes 50 % of the time).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // ---- CTA-pair (cta_group::2) variants.  Shared-window addresses of a CTA in a cluster carry the CTA rank; clearing the
 // peer bit (cute::Sm100MmaPeerBitMask) makes a TMA completion / arrive land on the EVEN CTA's barrier at the same offset.
@@ -396,18 +408,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
     pdl_wait();
 
     if (warp == 4) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * p.TW - p.pad, h0 = th * p.TH - p.pad, b0 = tb * p.TB, n0 = nt * BN;
-                int kcol = 0;
-                for (int kh = 0; kh < p.k; ++kh) {
-                    for (int kw = 0; kw < p.k; ++kw) {
-                        for (int cc = 0; cc < p.cin_chunks; ++cc, kcol += BK) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+        // ================================ TMA producer (whole warp, one elected lane issues) ================================
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+            const int w0 = tw * p.TW - p.pad, h0 = th * p.TH - p.pad, b0 = tb * p.TB, n0 = nt * BN;
+            int kcol = 0;
+            for (int kh = 0; kh < p.k; ++kh) {
+                for (int kw = 0; kw < p.k; ++kw) {
+                    for (int cc = 0; cc < p.cin_chunks; ++cc, kcol += BK) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+                        if (elect_one()) {
                             uint8_t* st = smem + stage * STAGE_BYTES;
                             mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                             tma_load_4d(&map_x_hi, st, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
@@ -422,27 +434,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                                 tma_load_2d(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
                                 tma_load_2d(&map_w_l8, st + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES, &full_bar[stage], kcol, n0);
                             }
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 5) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            int acc_it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                for (int kb0 = 0; kb0 < kblocks; kb0 += p.chunk_kb, ++acc_it) {
-                    const int acc = acc_it & 1;
-                    mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+        // ================================ MMA issuer (whole warp, one elected lane issues) ================================
+        int stage = 0; uint32_t phase = 0;
+        int acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int kb0 = 0; kb0 < kblocks; kb0 += p.chunk_kb, ++acc_it) {
+                const int acc = acc_it & 1;
+                mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                const int kb1 = min(kblocks, kb0 + p.chunk_kb);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                    const int kb1 = min(kblocks, kb0 + p.chunk_kb);
-                    for (int kb = kb0; kb < kb1; ++kb) {
-                        mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
-                        tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                         const uint64_t a_hi = make_smem_desc(sa);
                         const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
@@ -474,9 +487,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_consta
                             }
                         }
                         tc_commit(&empty_bar[stage]);   // frees the smem stage once the MMAs above have read it
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        if (kb + 1 == kb1) tc_commit(&tfull_bar[acc]);   // partial accumulator complete -> epilogue (same thread as the MMAs)
                     }
-                    tc_commit(&tfull_bar[acc]);         // partial accumulator complete -> epilogue
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -636,47 +650,51 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
-    if (!(warp == 4 && lane == 0)) pdl_wait();   // the TMA producer waits after it has issued the (static) weight loads
+    if (warp != 4) pdl_wait();   // the TMA producer warp waits after it has issued the (static) weight loads
 
     if (warp == 4) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
+        // ================================ TMA producer (whole warp, one elected lane issues) ================================
+        if (elect_one()) {
             mbar_expect_tx(w_full, W_BYTES);
             for (int t = 0; t < 9; ++t) {
                 tma_load_2d(&map_w_hi, wsm + t * W_TAP_BYTES, w_full, t * BK, n0);
                 if (PASSES == 3) tma_load_2d(&map_w_lo, wsm + t * W_TAP_BYTES + 64 * BK * 2, w_full, t * BK, n0);
             }
-            pdl_wait();
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = cta0; tile < p.num_tiles; tile += cta_step) {
-                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * C64_TW - 1, h0 = th * C64_TH - 1;
-                for (int kw = 0; kw < 3; ++kw) {
-                    mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 1);
+        }
+        __syncwarp();
+        pdl_wait();
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = cta0; tile < p.num_tiles; tile += cta_step) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / (p.tiles_w * p.tiles_h);
+            const int w0 = tw * C64_TW - 1, h0 = th * C64_TH - 1;
+            for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 1);
+                if (elect_one()) {
                     uint8_t* st = asm_ + stage * A_STAGE_BYTES;
                     mbar_expect_tx(&a_full[stage], A_STAGE_BYTES);
                     tma_load_4d(&map_x_hi, st, &a_full[stage], 0, w0 + kw, h0, tb);
                     if (PASSES == 3) tma_load_4d(&map_x_lo, st + C64_PATCH_BYTES, &a_full[stage], 0, w0 + kw, h0, tb);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 5) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            mbar_wait(w_full, 0, p.err_flag, 5);
+        // ================================ MMA issuer (whole warp, one elected lane issues) ================================
+        mbar_wait(w_full, 0, p.err_flag, 5);
+        tc_fence_after();
+        const uint32_t wb = smem_u32(wsm);
+        int stage = 0; uint32_t phase = 0;
+        int acc_it = 0;
+        for (int tile = cta0; tile < p.num_tiles; tile += cta_step, ++acc_it) {
+            const int acc = acc_it & 1;
+            mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
             tc_fence_after();
-            const uint32_t wb = smem_u32(wsm);
-            int stage = 0; uint32_t phase = 0;
-            int acc_it = 0;
-            for (int tile = cta0; tile < p.num_tiles; tile += cta_step, ++acc_it) {
-                const int acc = acc_it & 1;
-                mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+            for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&a_full[stage], phase, p.err_flag, 3);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                for (int kw = 0; kw < 3; ++kw) {
-                    mbar_wait(&a_full[stage], phase, p.err_flag, 3);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t sa = smem_u32(asm_ + stage * A_STAGE_BYTES);
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh) {
@@ -691,9 +709,10 @@ conv_c64_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                         }
                     }
                     tc_commit(&a_empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kw == 2) tc_commit(&tfull_bar[acc]);
                 }
-                tc_commit(&tfull_bar[acc]);
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -870,15 +889,15 @@ conv_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
             if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 12) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            const uint64_t bdesc = make_smem_desc(smem_u32(bsm));
-            int stage = 0; uint32_t phase = 0; int acc_it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
-                const int acc = acc_it & 1;
-                mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
-                mbar_wait(&a_full[stage], phase, p.err_flag, 3);
-                tc_fence_after();
+        // ================================ MMA issuer (whole warp, one elected lane issues) ================================
+        const uint64_t bdesc = make_smem_desc(smem_u32(bsm));
+        int stage = 0; uint32_t phase = 0; int acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+            const int acc = acc_it & 1;
+            mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+            mbar_wait(&a_full[stage], phase, p.err_flag, 3);
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
                 const uint32_t sa = smem_u32(asm_ + stage * C3T_A_STAGE_BYTES);
                 const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
@@ -890,8 +909,9 @@ conv_c3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
                 }
                 tc_commit(&a_empty[stage]);
                 tc_commit(&tfull_bar[acc]);
-                if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
         }
     } else {
         // ================================ epilogue: warps 0-7, lane quadrant = warp % 4, channel half = warp / 4 ================================
@@ -1056,15 +1076,15 @@ conv_c3_tma_kernel(const float* __restrict__ x, const float* __restrict__ w, con
             if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 12) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            const uint64_t bdesc = make_smem_desc(smem_u32(bsm));
-            int stage = 0; uint32_t phase = 0; int acc_it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
-                const int acc = acc_it & 1;
-                mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
-                mbar_wait(&a_full[stage], phase, p.err_flag, 3);
-                tc_fence_after();
+        // ================================ MMA issuer (whole warp, one elected lane issues) ================================
+        const uint64_t bdesc = make_smem_desc(smem_u32(bsm));
+        int stage = 0; uint32_t phase = 0; int acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++acc_it) {
+            const int acc = acc_it & 1;
+            mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
+            mbar_wait(&a_full[stage], phase, p.err_flag, 3);
+            tc_fence_after();
+            if (elect_one()) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 128);
                 const uint64_t a_hi = make_smem_desc(smem_u32(asm_ + stage * C3S_A_STAGE_BYTES));
                 const uint64_t a_lo = a_hi + (uint64_t)(64 >> 4);          // bytes [64,128) of every row
@@ -1076,8 +1096,9 @@ conv_c3_tma_kernel(const float* __restrict__ x, const float* __restrict__ w, con
                 }
                 tc_commit(&a_empty[stage]);
                 tc_commit(&tfull_bar[acc]);
-                if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == C3T_STAGES) { stage = 0; phase ^= 1; }
         }
     } else {
         // ================================ epilogue: warps 0-7 (lane quadrant q, channel half ch) -> smem staging -> TMA store ================================
@@ -1092,7 +1113,7 @@ conv_c3_tma_kernel(const float* __restrict__ x, const float* __restrict__ w, con
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 128 + ch * 32);
             // the previous tile's bulk stores must have finished READING the staging buffer before it is overwritten
-            if (threadIdx.x == 0) tma_store_wait_read();
+            if (warp == 0) { if (elect_one()) tma_store_wait_read(); __syncwarp(); }   // the lane that committed the stores
             named_bar_sync(2, 256);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {           // 16 channels at a time (72-register budget at two CTAs per SM)
@@ -1124,13 +1145,16 @@ conv_c3_tma_kernel(const float* __restrict__ x, const float* __restrict__ w, con
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             fence_proxy_async_smem();
             named_bar_sync(2, 256);
-            if (threadIdx.x == 0) {
-                tma_store_4d(&map_y_hi, osm, 0, tw * C64_TW, th * C64_TH, b);
-                if (want_lo) tma_store_4d(&map_y_lo, osm + A_TILE_BYTES, 0, tw * C64_TW, th * C64_TH, b);
-                tma_store_commit();
+            if (warp == 0) {                                  // warp-uniform; lane 0 is always the elected lane of a full warp
+                if (elect_one()) {
+                    tma_store_4d(&map_y_hi, osm, 0, tw * C64_TW, th * C64_TH, b);
+                    if (want_lo) tma_store_4d(&map_y_lo, osm + A_TILE_BYTES, 0, tw * C64_TW, th * C64_TH, b);
+                    tma_store_commit();
+                }
+                __syncwarp();
             }
         }
-        if (threadIdx.x == 0) tma_store_wait_all();        // global writes complete before the CTA exits
+        if (warp == 0) { if (elect_one()) tma_store_wait_all(); __syncwarp(); }   // global writes complete before the CTA exits
     }
 
     tc_fence_before();
@@ -1222,18 +1246,18 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     pdl_wait();
 
     if (warp == 8) {
-        // ================================ TMA producer (both CTAs) ================================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
-                const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * p.TW - p.pad, h0 = th * p.TH - p.pad, b0 = tb * p.TB, n0 = nt * BN + (int)rank * (BN / 2);
-                int kcol = 0;
-                for (int kh = 0; kh < p.k; ++kh) {
-                    for (int kw = 0; kw < p.k; ++kw) {
-                        for (int cc = 0; cc < p.cin_chunks; ++cc, kcol += BK) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+        // ================================ TMA producer (both CTAs; whole warp, one elected lane issues) ================================
+        int stage = 0; uint32_t phase = 0;
+        for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
+            const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+            const int w0 = tw * p.TW - p.pad, h0 = th * p.TH - p.pad, b0 = tb * p.TB, n0 = nt * BN + (int)rank * (BN / 2);
+            int kcol = 0;
+            for (int kh = 0; kh < p.k; ++kh) {
+                for (int kw = 0; kw < p.k; ++kw) {
+                    for (int cc = 0; cc < p.cin_chunks; ++cc, kcol += BK) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, p.err_flag, 1);
+                        if (elect_one()) {
                             uint8_t* st = smem + stage * STAGE_BYTES;
                             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);   // bytes of both CTAs
                             tma_load_4d_2sm(&map_x_hi, st, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
@@ -1241,29 +1265,29 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                                 tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
                                 tma_load_2d_2sm(rank == 0 ? &map_w_hi : &map_w_lo, st + 2 * A_TILE_BYTES, &full_bar[stage], kcol, nt * BN);
                                 tma_load_2d_2sm(&map_w_l8, st + 2 * A_TILE_BYTES + Y_BYTES, &full_bar[stage], kcol, n0);
-                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                                continue;
+                            } else {
+                                tma_load_2d_2sm(&map_w_hi, st + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
+                                if (PASSES == 3) {
+                                    tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                    tma_load_2d_2sm(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
+                                }
+                                if (PASSES == 4) {
+                                    tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                    tma_load_4d_2sm(&map_x_h8, st + A_TILE_BYTES + A8_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
+                                    tma_load_2d_2sm(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
+                                    tma_load_2d_2sm(&map_w_l8, st + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES, &full_bar[stage], kcol, n0);
+                                }
                             }
-                            tma_load_2d_2sm(&map_w_hi, st + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES, &full_bar[stage], kcol, n0);
-                            if (PASSES == 3) {
-                                tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
-                                tma_load_2d_2sm(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
-                            }
-                            if (PASSES == 4) {
-                                tma_load_4d_2sm(&map_x_lo, st + A_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
-                                tma_load_4d_2sm(&map_x_h8, st + A_TILE_BYTES + A8_TILE_BYTES, &full_bar[stage], cc * BK, w0 + kw, h0 + kh, b0);
-                                tma_load_2d_2sm(&map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kcol, n0);
-                                tma_load_2d_2sm(&map_w_l8, st + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES, &full_bar[stage], kcol, n0);
-                            }
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 9) {
-        // ================================ MMA issuer (leader CTA) ================================
-        if (rank == 0 && lane == 0) {
+        // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ================================
+        if (rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc_it = 0;
             for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
@@ -1276,40 +1300,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&full_bar[stage], phase, p.err_flag, 3);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                        const uint64_t a_hi = make_smem_desc(sa);
-                        const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
-                        const uint64_t b_hi = make_smem_desc(sa + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES);
-                        const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + (STACK ? Y_BYTES : B_TILE_BYTES));
+                        if (elect_one()) {
+                            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                            const uint64_t a_hi = make_smem_desc(sa);
+                            const uint64_t a_lo = make_smem_desc(sa + A_TILE_BYTES);
+                            const uint64_t b_hi = make_smem_desc(sa + (PASSES >= 3 ? 2 : 1) * A_TILE_BYTES);
+                            const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + (STACK ? Y_BYTES : B_TILE_BYTES));
 #pragma unroll
-                        for (int j = 0; j < BK / UMMA_K; ++j) {
-                            const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
-                            if (STACK) {   // b_hi = region Y ([W_hi ; W_lo] across the pair), b_lo = region X (W_hi halves)
-                                tc_mma_f16_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC_STACK, (uint32_t)((kb > kb0) | (j != 0)));
-                                tc_mma_f16_2cta(d_tmem, a_lo + koff, b_lo + koff, IDESC, 1u);
-                                continue;
+                            for (int j = 0; j < BK / UMMA_K; ++j) {
+                                const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                                if (STACK) {   // b_hi = region Y ([W_hi ; W_lo] across the pair), b_lo = region X (W_hi halves)
+                                    tc_mma_f16_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC_STACK, (uint32_t)((kb > kb0) | (j != 0)));
+                                    tc_mma_f16_2cta(d_tmem, a_lo + koff, b_lo + koff, IDESC, 1u);
+                                } else {
+                                    tc_mma_f16_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC, (uint32_t)((kb > kb0) | (j != 0)));
+                                    if (PASSES == 3) {
+                                        tc_mma_f16_2cta(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
+                                        tc_mma_f16_2cta(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
+                                    }
+                                }
                             }
-                            tc_mma_f16_2cta(d_tmem, a_hi + koff, b_hi + koff, IDESC, (uint32_t)((kb > kb0) | (j != 0)));
-                            if (PASSES == 3) {
-                                tc_mma_f16_2cta(d_tmem, a_hi + koff, b_lo + koff, IDESC, 1u);
-                                tc_mma_f16_2cta(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
-                            }
-                        }
-                        if (PASSES == 4) {
-                            const uint64_t a_l8 = make_smem_desc64(sa + A_TILE_BYTES), a_h8 = make_smem_desc64(sa + A_TILE_BYTES + A8_TILE_BYTES);
-                            const uint64_t b_h8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
-                            const uint64_t b_l8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES);
+                            if (PASSES == 4) {
+                                const uint64_t a_l8 = make_smem_desc64(sa + A_TILE_BYTES), a_h8 = make_smem_desc64(sa + A_TILE_BYTES + A8_TILE_BYTES);
+                                const uint64_t b_h8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                                const uint64_t b_l8 = make_smem_desc64(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + B8_TILE_BYTES);
 #pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const uint64_t koff = (uint64_t)((j * 32) >> 4);
-                                tc_mma_f8_2cta(d_tmem, a_l8 + koff, b_h8 + koff, IDESC, 1u);
-                                tc_mma_f8_2cta(d_tmem, a_h8 + koff, b_l8 + koff, IDESC, 1u);
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint64_t koff = (uint64_t)((j * 32) >> 4);
+                                    tc_mma_f8_2cta(d_tmem, a_l8 + koff, b_h8 + koff, IDESC, 1u);
+                                    tc_mma_f8_2cta(d_tmem, a_h8 + koff, b_l8 + koff, IDESC, 1u);
+                                }
                             }
+                            tc_commit_2cta(&empty_bar[stage]);   // frees this smem stage in both CTAs
+                            if (kb + 1 == kb1) tc_commit_2cta(&tfull_bar[acc]);   // partial accumulator complete -> epilogues of both CTAs
                         }
-                        tc_commit_2cta(&empty_bar[stage]);   // frees this smem stage in both CTAs
+                        __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    tc_commit_2cta(&tfull_bar[acc]);         // partial accumulator complete -> epilogues of both CTAs
                 }
             }
         }
@@ -1433,51 +1460,39 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
-    if (!(warp == 8 && lane == 0)) pdl_wait();   // the TMA producer waits after it has issued the (static) weight loads
+    if (warp != 8) pdl_wait();   // the TMA producer warp waits after it has issued the (static) weight loads
 
     if (warp == 8) {
-        // ================================ TMA producer (both CTAs) ================================
-        if (lane == 0) {
+        // ================================ TMA producer (both CTAs; whole warp, one elected lane issues) ================================
+        if (elect_one()) {
             if (rank == 0) mbar_expect_tx(w_full, 2 * C64X2_W_BYTES);
             for (int t = 0; t < 9; ++t) {
                 tma_load_2d_2sm(&map_w_hi, wsm + t * C64X2_W_TAP_BYTES, w_full, t * BK, n0 + (int)rank * 32);
                 tma_load_2d_2sm(&map_w_lo, wsm + t * C64X2_W_TAP_BYTES + 32 * BK * 2, w_full, t * BK, n0 + (int)rank * 32);
             }
-            pdl_wait();
-            int stage = 0; uint32_t phase = 0;
-            // The kernel is bound by the latency of its patch loads, not by the tensor pipe (ncu r02d: dropping a third of the UMMAs
-            // changes the run time by 3 %; three 40 KB stages in flight against ~2.7 us per stage from DRAM): the patches of the tile
-            // TWO iterations ahead are prefetched into L2 (one 18-pixel-wide box covers the three kw-shifted patches), so the
-            // shared-memory ring is filled at L2 latency.
-            auto prefetch_item = [&](int it) {
-                if (it >= p.num_tiles) return;
-                const int m2 = 2 * it + (int)rank;
-                const int tw2 = m2 % p.tiles_w, th2 = (m2 / p.tiles_w) % p.tiles_h, tb2 = m2 / (p.tiles_w * p.tiles_h);
-                if (tb2 >= p.B) return;
-                for (int kw = 0; kw < 3; kw += 2) {     // boxes at kw = 0 and kw = 2 cover pixels w0 .. w0 + 17
-                    tma_prefetch_4d(&map_x_hi, 0, tw2 * C64_TW - 1 + kw, th2 * C64_TH - 1, tb2);
-                    tma_prefetch_4d(&map_x_lo, 0, tw2 * C64_TW - 1 + kw, th2 * C64_TH - 1, tb2);
-                }
-            };
-            if (!(p.exp & 4)) { prefetch_item(item0); prefetch_item(item0 + item_step); }
-            for (int item = item0; item < p.num_tiles; item += item_step) {
-                if (!(p.exp & 4)) prefetch_item(item + 2 * item_step);
-                const int mt = 2 * item + (int)rank;
-                const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
-                const int w0 = tw * C64_TW - 1, h0 = th * C64_TH - 1;
-                for (int kw = 0; kw < 3; ++kw) {
-                    mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 1);
+        }
+        __syncwarp();
+        pdl_wait();
+        int stage = 0; uint32_t phase = 0;
+        for (int item = item0; item < p.num_tiles; item += item_step) {
+            const int mt = 2 * item + (int)rank;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
+            const int w0 = tw * C64_TW - 1, h0 = th * C64_TH - 1;
+            for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&a_empty[stage], phase ^ 1, p.err_flag, 1);
+                if (elect_one()) {
                     uint8_t* st = asm_ + stage * C64X2_A_STAGE_BYTES;
                     if (rank == 0) mbar_expect_tx(&a_full[stage], 2 * C64X2_A_STAGE_BYTES);
                     tma_load_4d_2sm(&map_x_hi, st, &a_full[stage], 0, w0 + kw, h0, tb);   // tb >= B (odd tile count): zero fill
                     tma_load_4d_2sm(&map_x_lo, st + C64_PATCH_BYTES, &a_full[stage], 0, w0 + kw, h0, tb);
-                    if (++stage == C64X2_STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == C64X2_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 9) {
-        // ================================ MMA issuer (leader CTA) ================================
-        if (rank == 0 && lane == 0) {
+        // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ================================
+        if (rank == 0) {
             mbar_wait(w_full, 0, p.err_flag, 5);
             tc_fence_after();
             const uint32_t wb = smem_u32(wsm);
@@ -1491,41 +1506,27 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
                 for (int kw = 0; kw < 3; ++kw) {
                     mbar_wait(&a_full[stage], phase, p.err_flag, 3);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(asm_ + stage * C64X2_A_STAGE_BYTES);
-                    if (p.exp & 2) {   // experiment: grouped by instruction shape
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(asm_ + stage * C64X2_A_STAGE_BYTES);
 #pragma unroll
-                        for (int pass = 0; pass < 2; ++pass)
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint64_t a_hi = make_smem_desc(sa + kh * C64_ROW_BYTES);
+                            const uint64_t a_lo = make_smem_desc(sa + C64_PATCH_BYTES + kh * C64_ROW_BYTES);
+                            const uint64_t b = make_smem_desc(wb + (kh * 3 + kw) * C64X2_W_TAP_BYTES);
 #pragma unroll
-                            for (int kh = 0; kh < 3; ++kh) {
-                                const uint64_t a = make_smem_desc(sa + pass * C64_PATCH_BYTES + kh * C64_ROW_BYTES);
-                                const uint64_t b = make_smem_desc(wb + (kh * 3 + kw) * C64X2_W_TAP_BYTES);
-#pragma unroll
-                                for (int j = 0; j < BK / UMMA_K; ++j) {
-                                    const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
-                                    const uint32_t accum = (uint32_t)((kw | kh | j) != 0);
-                                    if (pass == 0) tc_mma_f16_2cta(d_tmem, a + koff, b + koff, IDESC_MAIN, accum);
-                                    else if (!(p.exp & 1)) tc_mma_f16_2cta(d_tmem + 128, a + koff, b + koff, IDESC_N64, accum);
-                                }
+                            for (int j = 0; j < BK / UMMA_K; ++j) {
+                                const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                                const uint32_t accum = (uint32_t)((kw | kh | j) != 0);
+                                tc_mma_f16_2cta(d_tmem, a_hi + koff, b + koff, IDESC_MAIN, accum);
+                                tc_mma_f16_2cta(d_tmem + 128, a_lo + koff, b + koff, IDESC_N64, accum);
                             }
-                    } else {
-#pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
-                        const uint64_t a_hi = make_smem_desc(sa + kh * C64_ROW_BYTES);
-                        const uint64_t a_lo = make_smem_desc(sa + C64_PATCH_BYTES + kh * C64_ROW_BYTES);
-                        const uint64_t b = make_smem_desc(wb + (kh * 3 + kw) * C64X2_W_TAP_BYTES);
-#pragma unroll
-                        for (int j = 0; j < BK / UMMA_K; ++j) {
-                            const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
-                            const uint32_t accum = (uint32_t)((kw | kh | j) != 0);
-                            tc_mma_f16_2cta(d_tmem, a_hi + koff, b + koff, IDESC_MAIN, accum);
-                            if (!(p.exp & 1)) tc_mma_f16_2cta(d_tmem + 128, a_lo + koff, b + koff, IDESC_N64, accum);
                         }
+                        tc_commit_2cta(&a_empty[stage]);
+                        if (kw == 2) tc_commit_2cta(&tfull_bar[acc]);
                     }
-                    }
-                    tc_commit_2cta(&a_empty[stage]);
+                    __syncwarp();
                     if (++stage == C64X2_STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit_2cta(&tfull_bar[acc]);
             }
         }
     } else {
@@ -1660,36 +1661,36 @@ fc_chain_kernel(const __grid_constant__ FcChainParams P) {
         const FcLayer& L = ch.layer[l];
         const int items = L.m_tiles * L.n_tiles;
         if (warp == 4) {
-            // ================================ TMA producer ================================
-            if (lane == 0) {
-                for (int item = rank; item < items; item += kFcCluster) {
-                    const int nt = item % L.n_tiles, mt = item / L.n_tiles;
-                    for (int kb = 0; kb < L.kblocks; ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1, P.err_flag, 1);
+            // ================================ TMA producer (whole warp, one elected lane issues) ================================
+            for (int item = rank; item < items; item += kFcCluster) {
+                const int nt = item % L.n_tiles, mt = item / L.n_tiles;
+                for (int kb = 0; kb < L.kblocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, P.err_flag, 1);
+                    if (elect_one()) {
                         uint8_t* st = smem + stage * STAGE_BYTES;
                         mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
                         tma_load_4d(&L.map_x_hi, st, &full_bar[stage], kb * BK, 0, 0, mt * BM);
                         tma_load_4d(&L.map_x_lo, st + A_TILE_BYTES, &full_bar[stage], kb * BK, 0, 0, mt * BM);
                         tma_load_2d(&L.map_w_hi, st + 2 * A_TILE_BYTES, &full_bar[stage], kb * BK, nt * BN);
                         tma_load_2d(&L.map_w_lo, st + 2 * A_TILE_BYTES + B_TILE_BYTES, &full_bar[stage], kb * BK, nt * BN);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
-            __syncwarp();
         } else if (warp == 5) {
-            // ================================ MMA issuer ================================
-            if (lane == 0) {
-                for (int item = rank; item < items; item += kFcCluster) {
-                    for (int kb0 = 0; kb0 < L.kblocks; kb0 += kChunk, ++acc_it) {
-                        const int acc = acc_it & 1;
-                        mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, P.err_flag, 2);
+            // ================================ MMA issuer (whole warp, one elected lane issues) ================================
+            for (int item = rank; item < items; item += kFcCluster) {
+                for (int kb0 = 0; kb0 < L.kblocks; kb0 += kChunk, ++acc_it) {
+                    const int acc = acc_it & 1;
+                    mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, P.err_flag, 2);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                    const int kb1 = min(L.kblocks, kb0 + kChunk);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait(&full_bar[stage], phase, P.err_flag, 3);
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                        const int kb1 = min(L.kblocks, kb0 + kChunk);
-                        for (int kb = kb0; kb < kb1; ++kb) {
-                            mbar_wait(&full_bar[stage], phase, P.err_flag, 3);
-                            tc_fence_after();
+                        if (elect_one()) {
                             const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                             const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
                             const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
@@ -1700,13 +1701,13 @@ fc_chain_kernel(const __grid_constant__ FcChainParams P) {
                                 tc_mma_f16(d_tmem, a_lo + koff, b_hi + koff, IDESC, 1u);
                             }
                             tc_commit(&empty_bar[stage]);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            if (kb + 1 == kb1) tc_commit(&tfull_bar[acc]);
                         }
-                        tc_commit(&tfull_bar[acc]);
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
-            __syncwarp();
         } else {
             // ================================ epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31 = batch rows) ================================
             for (int item = rank; item < items; item += kFcCluster) {
