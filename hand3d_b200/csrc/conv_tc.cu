@@ -2030,7 +2030,10 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if ((tune.bn == 64 || tune.bn == 128 || tune.bn == 256) && d.Cout_pad % tune.bn == 0) BN = tune.bn;
     // 64 -> 64 / 64 -> 128 channels, 3x3 (conv1_2, conv2_1, small lifting layers): weights-resident / patch-reuse kernels; on a CTA
     // pair in the 3-pass modes when the map is large enough to fill the machine with tile pairs
-    bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad <= 128 && (d.passes == 1 || d.passes == 3) && tune.c64 != 0;
+    // (3-pass, Cout = 128 = conv2_1: the N-stacked CTA-pair kernel is faster since the role warps issue from uniform registers -
+    // 227 us against 340 us for the two-group 64-channel kernel, ncu r02c - so the specialisation keeps Cout = 64 there)
+    bool c64 = d.k == 3 && d.Cin_pad == 64 && (d.passes == 1 ? d.Cout_pad <= 128 : (d.passes == 3 && (d.Cout_pad == 64 || tune.c64 == 2))) &&
+               tune.c64 != 0;
     const bool c64x2 = c64 && d.passes == 3 && tune.c64x2 != 0 && (int64_t)d.H * d.W > 256;
     if (c64) { two = false; BN = 64; }
     pl->BN = BN;

@@ -91,6 +91,23 @@ def test_conv2d_tc_single_cta_variants(ctx, case, switch, tuning):
     assert err < TOL["bf16x3"], "max abs err %.3e (tolerance %.1e)" % (err, TOL["bf16x3"])
 
 
+@pytest.mark.parametrize("pair", [1, 0])
+def test_conv2d_tc_c64_two_channel_groups(ctx, pair, tuning):
+    """64 -> 128 channels on the 64-channel kernels (two resident 64-channel weight groups, CTAs / clusters split between them):
+    no longer the policy's choice for conv2_1 in the 3-pass modes (tc_c64 = 2 forces it), still the fp16 single-pass path."""
+    tuning("tc_c64", 2)
+    tuning("tc_c64x2", pair)
+    B, H, W, Cin, Cout, k = CASES[9]
+    rng = np.random.default_rng(17)
+    x = rng.normal(size=(B, H, W, Cin)).astype(f32)
+    w = (rng.normal(size=(k, k, Cin, Cout)) / np.sqrt(k * k * Cin)).astype(f32)
+    b = rng.normal(size=Cout).astype(f32)
+    for prec in ("bf16x3", "fp16"):
+        y = ctx.conv2d_tc(torch.from_numpy(x).cuda(), w, b, leaky=True, precision=prec).cpu().numpy()
+        ref = T.leaky_relu(T.conv2d_same(x, w, b, 1, np.float64))
+        assert np.abs(y - ref).max() < TOL[prec]
+
+
 STRIDED = [  # B,H,W,Cin,Cout: the stride-2 layers of the lifting pyramids (nets/ColorHandPose3DNetwork.py:255-258,291-294)
     (2, 32, 32, 32, 32),      # conv_pose_0_2: Cin / Cout padded 32 -> 64
     (3, 16, 16, 64, 64),      # conv_pose_1_2 / conv_vp_0_2 geometry
