@@ -193,6 +193,7 @@ struct TcTuning {
     int chunk_kb = 0;      // 0 policy
     int exp = 0;           // timing experiments (wrong results allowed), see TcParams::exp
     int no_side_stream = 0, no_pool_fusion = 0, lift_direct = 0, c3_ffma = 0;
+    int c64_tma_out = 1;   // 64-channel pair kernel: bulk-tensor-store epilogue for un-pooled layers (conv2_1)
     int fc_chain = 1;      // FC stacks + rotation epilogue of the lifting stage as one kernel (0 = one launch per layer)
     int pdl = 1;           // programmatic dependent launch between the tensor-core kernels (prologue overlaps the previous kernel's tail)
     int c3_tma = 1;        // first layer: shared-memory staged epilogue + bulk tensor stores (0 = direct 16-byte global stores)

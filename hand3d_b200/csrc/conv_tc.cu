@@ -60,6 +60,7 @@ struct TcParams {
     int leaky;
     int stack;      // N-stacked passes (generic single-CTA kernel, 3-pass, BN <= 128); 0 = three separate UMMAs per K step
     int exp;        // reserved for timing experiments (tc_set_tuning("tc_exp")); unused by the shipped kernels
+    int tma_out;    // conv_c64x2_kernel: un-pooled split-plane output staged in shared memory and written by bulk tensor stores
     int* err_flag;
 };
 
@@ -1417,13 +1418,15 @@ constexpr int C64X2_W_BYTES = 9 * C64X2_W_TAP_BYTES;
 constexpr int C64X2_A_STAGE_BYTES = 2 * C64_PATCH_BYTES;
 constexpr int C64X2_STAGES = 3;
 constexpr int C64X2_ACC_COLS = 256;
-constexpr int C64X2_SMEM = C64X2_W_BYTES + C64X2_STAGES * C64X2_A_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int C64X2_OUT_BYTES = 2 * A_TILE_BYTES;        // un-pooled layers: the 128 x 64 output tile (hi, lo) is staged here and leaves by bulk tensor stores
+constexpr int C64X2_SMEM = C64X2_W_BYTES + C64X2_STAGES * C64X2_A_STAGE_BYTES + C64X2_OUT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 static_assert(C64X2_SMEM <= 227 * 1024, "conv_c64x2_kernel: shared memory budget");
 
 template <bool FP16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
-                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams p) {
+                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                  const __grid_constant__ CUtensorMap map_y_hi, const __grid_constant__ CUtensorMap map_y_lo, const TcParams p) {
     constexpr uint32_t IDESC_MAIN = make_idesc(128, FP16, 256);
     constexpr uint32_t IDESC_N64 = make_idesc(64, FP16, 256);
 
@@ -1431,7 +1434,8 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* wsm = smem;
     uint8_t* asm_ = smem + C64X2_W_BYTES;
-    uint64_t* a_full = reinterpret_cast<uint64_t*>(asm_ + C64X2_STAGES * C64X2_A_STAGE_BYTES);
+    uint8_t* osm = asm_ + C64X2_STAGES * C64X2_A_STAGE_BYTES;           // output staging [hi tile | lo tile], 1024-byte aligned
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(osm + C64X2_OUT_BYTES);
     uint64_t* a_empty = a_full + C64X2_STAGES;
     uint64_t* tfull_bar = a_empty + C64X2_STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -1561,8 +1565,44 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
             float racc[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) racc[i] = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + __uint_as_float(v2[i]);
-            epilogue_store32<3, FP16>(p, racc, pix, n0 + 32 * ch, valid);
+            if (!p.tma_out) {
+                epilogue_store32<3, FP16>(p, racc, pix, n0 + 32 * ch, valid);
+                continue;
+            }
+            // Un-pooled layer (conv2_1): 8 bytes per output value leave the SM.  Direct 16-byte st.global touches 32 different lines
+            // per warp instruction (the thread <-> pixel mapping of TMEM) and made this layer LSU bound (ncu r02d: tensor pipe 50 %
+            // with either kernel family); instead the tile is staged in the SWIZZLE_128B layout and written by one bulk tensor store
+            // per plane (full 128-byte lines, partial tiles clipped by TMA), exactly as in conv_c3_tma_kernel.
+            uint32_t hi[16], lo[16];
+            const float2* bias2 = reinterpret_cast<const float2*>(p.bias + n0 + 32 * ch);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float2 bv = __ldg(bias2 + i);
+                float f0 = racc[2 * i] + bv.x, f1 = racc[2 * i + 1] + bv.y;
+                if (p.leaky) { f0 = fmaxf(f0, kNegSlope * f0); f1 = fmaxf(f1, kNegSlope * f1); }
+                hi[i] = pack_hi2<FP16>(f0, f1);
+                const float2 r = unpack2<FP16>(hi[i]);
+                lo[i] = pack_hi2<FP16>(f0 - r.x, f1 - r.y);
+            }
+            if (warp == 0) { if (elect_one()) tma_store_wait_read(); __syncwarp(); }   // the previous tile's stores have read the staging buffer
+            named_bar_sync(2, 256);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                *reinterpret_cast<uint4*>(osm + sw128_chunk(row, 4 * ch + c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                *reinterpret_cast<uint4*>(osm + A_TILE_BYTES + sw128_chunk(row, 4 * ch + c)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(2, 256);
+            if (warp == 0) {
+                if (elect_one() && b < p.B) {                   // (an odd tile count leaves the pair's second tile outside the batch)
+                    tma_store_4d(&map_y_hi, osm, n0, tw * C64_TW, th * C64_TH, b);
+                    tma_store_4d(&map_y_lo, osm + A_TILE_BYTES, n0, tw * C64_TW, th * C64_TH, b);
+                    tma_store_commit();
+                }
+                __syncwarp();
+            }
         }
+        if (p.tma_out && warp == 0) { if (elect_one()) tma_store_wait_all(); __syncwarp(); }
     }
 
     tc_fence_before();
@@ -1860,6 +1900,7 @@ struct TcConvPlan {
 
     TcConvDesc d;
     CUtensorMap map_x_hi, map_x_lo, map_w_hi, map_w_lo, map_x_h8, map_w_l8;
+    CUtensorMap map_y_hi, map_y_lo;      // conv_c64x2_kernel with tma_out
     TcParams p;
     int BN, grid;
     int* err_flag;
@@ -1922,6 +1963,7 @@ TcTuning& tc_tuning() {
         v.c3_tma = geti("H3D_C3_TMA", 1);
         v.pdl = geti("H3D_PDL", 1);
         v.fc_chain = geti("H3D_FC_CHAIN", 1);
+        v.c64_tma_out = geti("H3D_C64_TMA_OUT", 1);
         return v;
     }();
     return t;
@@ -1944,6 +1986,7 @@ int tc_set_tuning(const char* key, int value) {
     else if (k == "c3_tma") t.c3_tma = value;
     else if (k == "pdl") t.pdl = value;
     else if (k == "fc_chain") t.fc_chain = value;
+    else if (k == "c64_tma_out") t.c64_tma_out = value;
     else { set_error("h3d_set_tuning: unknown key '%s'", k.c_str()); return H3D_EINVAL; }
     return H3D_OK;
 }
@@ -1975,7 +2018,7 @@ int launch_c64x2(const TcConvPlan* pl, cudaStream_t s) {
     static bool attr[kMaxDevices] = {};
     if (int rc = smem_opt_in(conv_c64x2_kernel<FP16>, C64X2_SMEM, attr)) return rc;
     H3D_CUDA(launch_pdl(conv_c64x2_kernel<FP16>, dim3(pl->grid), dim3(kThreads2), (size_t)C64X2_SMEM, s, pl->map_x_hi, pl->map_x_lo, pl->map_w_hi,
-                        pl->map_w_lo, pl->p));
+                        pl->map_w_lo, pl->map_y_hi, pl->map_y_lo, pl->p));
     return H3D_OK;
 }
 }  // namespace
@@ -2030,10 +2073,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if ((tune.bn == 64 || tune.bn == 128 || tune.bn == 256) && d.Cout_pad % tune.bn == 0) BN = tune.bn;
     // 64 -> 64 / 64 -> 128 channels, 3x3 (conv1_2, conv2_1, small lifting layers): weights-resident / patch-reuse kernels; on a CTA
     // pair in the 3-pass modes when the map is large enough to fill the machine with tile pairs
-    // (3-pass, Cout = 128 = conv2_1: the N-stacked CTA-pair kernel is faster since the role warps issue from uniform registers -
-    // 227 us against 340 us for the two-group 64-channel kernel, ncu r02c - so the specialisation keeps Cout = 64 there)
-    bool c64 = d.k == 3 && d.Cin_pad == 64 && (d.passes == 1 ? d.Cout_pad <= 128 : (d.passes == 3 && (d.Cout_pad == 64 || tune.c64 == 2))) &&
-               tune.c64 != 0;
+    bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad <= 128 && (d.passes == 1 || d.passes == 3) && tune.c64 != 0;
     const bool c64x2 = c64 && d.passes == 3 && tune.c64x2 != 0 && (int64_t)d.H * d.W > 256;
     if (c64) { two = false; BN = 64; }
     pl->BN = BN;
@@ -2095,6 +2135,14 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if (ok && d.passes == 1) { pl->map_x_lo = pl->map_x_hi; pl->map_w_lo = pl->map_w_hi; }
     if (ok && d.passes != 4) { pl->map_x_h8 = pl->map_x_hi; pl->map_w_l8 = pl->map_w_hi; }
     if (ok && stacked_pair) ok = encode_w_map(&pl->map_w_l8, d.w.hi, Ktot, d.Cout_pad, BN / 2);   // region X: W_hi in 64-row boxes
+    p.tma_out = 0;
+    pl->map_y_hi = pl->map_x_hi; pl->map_y_lo = pl->map_x_hi;
+    if (ok && c64x2 && d.pool == 0 && d.y.hi && d.y.lo && !d.yf && d.Cout % 64 == 0 && tune.c64_tma_out) {
+        // output planes [B,H,W,Cy_total] at channel offset cy_off: boxes of {64 channels, 16, 8, 1} at channel coordinate n0
+        ok = encode_act_map(&pl->map_y_hi, d.y.hi + d.cy_off, d.Cy_total, d.Cout_pad, d.W, d.H, d.B, C64_TW, C64_TH, 1) &&
+             encode_act_map(&pl->map_y_lo, d.y.lo + d.cy_off, d.Cy_total, d.Cout_pad, d.W, d.H, d.B, C64_TW, C64_TH, 1);
+        p.tma_out = 1;
+    }
     if (!ok) { delete pl; return nullptr; }
     return pl;
 }
