@@ -121,7 +121,18 @@ struct StagePlan {
     int cur_lane = 0;                   // lane given to steps as they are appended (see seal())
     int B = 0, H = 0, W = 0, variant = -1;
     int64_t flops = 0;
-    ~StagePlan() { for (auto* p : tc) tc_conv_plan_destroy(p); for (auto* p : fc) fc_chain_plan_destroy(p); }
+    // layer chains (conv_tc.cu "Layer chains"): per chained launch one ticket word + B per-image completion counters, zeroed by the
+    // plan's first step; chain_prev = the chained launch appended last, iff it is the plan's most recent step
+    int* sync = nullptr;
+    int sync_slots = 0;
+    TcConvPlan* chain_prev = nullptr;
+    size_t chain_prev_step = 0;
+    int* chain_prev_sig = nullptr;
+    ~StagePlan() {
+        for (auto* p : tc) tc_conv_plan_destroy(p);
+        for (auto* p : fc) fc_chain_plan_destroy(p);
+        if (sync) cudaFree(sync);
+    }
     // label every step appended since the last call with the current lane
     void seal(bool join = false) {
         const size_t first = lane.size();
@@ -414,9 +425,22 @@ static int add_direct(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, con
     return H3D_OK;
 }
 
+constexpr int kMaxChainSlots = 96;
+
+// First step of a stage plan that chains layers: zero the ticket words and completion counters (one memset node per stage call)
+static int begin_chain_sync(StagePlan* pl, int B) {
+    if (!tc_tuning().chain) return H3D_OK;
+    const size_t bytes = (size_t)kMaxChainSlots * (B + 1) * sizeof(int);
+    H3D_CUDA(cudaMalloc(&pl->sync, bytes));   // plan build time, never on a launch path
+    int* sync = pl->sync;
+    pl->steps.push_back([sync, bytes](const Ext&, cudaStream_t s) { H3D_CUDA(cudaMemsetAsync(sync, 0, bytes, s)); return H3D_OK; });
+    pl->launches.push_back(0);
+    return H3D_OK;
+}
+
 static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec& l, int B, int H, int W, Split x,
                   int Cin_total, int Cin_pad, const std::vector<int>& perm, Split y, int Cy_total, int cy_off, float* yf,
-                  int Cyf_total, int cyf_off, int pool = 0, int force_passes = 0) {
+                  int Cyf_total, int cyf_off, int pool = 0, int force_passes = 0, bool chain = false) {
     const PackedW* pw;
     int rc = get_packed(ctx, scope, l, Cin_pad, perm, &pw, force_passes);
     if (rc) return rc;
@@ -431,6 +455,21 @@ static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const L
     TcConvPlan* tp = tc_conv_plan_create(d);
     if (!tp) return H3D_ECUDA;
     pl->tc.push_back(tp);
+    if (chain && pl->sync && tc_conv_plan_chainable(tp) && pl->sync_slots < kMaxChainSlots) {
+        int* words = pl->sync + (size_t)pl->sync_slots++ * (B + 1);   // [ticket | completion counter per image]
+        const int* dep = nullptr; int target = 0;
+        if (tc_tuning().chain == 1 && pl->chain_prev && pl->chain_prev_step + 1 == pl->steps.size()) {
+            // the previous step is a chained launch: depend on it per image iff it produces ALL of this layer's input planes
+            const TcConvDesc& pd = tc_conv_plan_desc(pl->chain_prev);
+            const int ph = pd.pool ? pd.H / 2 : pd.H, pw = pd.pool ? pd.W / 2 : pd.W;
+            if (pd.y.hi == x.hi && pd.y.lo == x.lo && pd.y.l8 == x.l8 && pd.cy_off == 0 && pd.Cy_total == Cin_total && pd.Cout_pad == Cin_pad &&
+                pd.B == B && ph == H && pw == W) {
+                dep = pl->chain_prev_sig; target = tc_conv_plan_signal_target(pl->chain_prev);
+            }
+        }
+        tc_conv_plan_set_chain(tp, words, dep, target, words + 1);
+        pl->chain_prev = tp; pl->chain_prev_step = pl->steps.size(); pl->chain_prev_sig = words + 1;
+    }
     pl->steps.push_back([tp](const Ext&, cudaStream_t s) { return tc_conv_launch(tp, s); });
     pl->launches.push_back(1);
     const int64_t fl = 2ll * B * H * W * l.k * l.k * l.cin * l.cout / (pool == 2 ? 4 : 1);
@@ -460,7 +499,7 @@ static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, co
         const bool pool_after = !strcmp(l.name, "conv1_2") || !strcmp(l.name, "conv2_2") || !strcmp(l.name, "conv3_4");
         const bool fuse_pool = use_tc && pool_after && (h % 2 == 0) && (w % 2 == 0) && !tc_tuning().no_pool_fusion;
         if (use_tc) {
-            rc = add_tc(ctx, pl, scope, l, B, h, w, in.s, in.C, l.cin, {}, out.s, out.C, c_off, nullptr, 0, 0, fuse_pool ? 1 : 0);
+            rc = add_tc(ctx, pl, scope, l, B, h, w, in.s, in.C, l.cin, {}, out.s, out.C, c_off, nullptr, 0, 0, fuse_pool ? 1 : 0, 0, true);
         } else if (tc) {   // first layer (Cin = 3): CUDA-core conv writing the split planes directly
             rc = add_direct(ctx, pl, scope, l, B, h, w, in.f, i == 0 ? l.cin : in.C, 0, nullptr, 0, 0, out.s, out.C, c_off);
         } else {
@@ -489,6 +528,7 @@ static int build_handsegnet(h3d_ctx* ctx, int B, int H, int W) {
     auto pl = std::make_unique<StagePlan>();
     pl->B = B; pl->H = H; pl->W = W;
     const bool tc = is_tc(ctx->precision);
+    if (tc) { if (int rc0 = begin_chain_sync(pl.get(), B)) return rc0; }
     char* r = ctx->ws + ctx->lay.seg_off;
     const int64_t se = slot_elems_seg(B, H, W);
     char* slot0 = r; char* slot1 = r + align_up(se * 4, 1024);
@@ -499,14 +539,15 @@ static int build_handsegnet(h3d_ctx* ctx, int B, int H, int W) {
     float* low = ctx->lay.seg_low;
     if (tc) {
         Act mid = slot_view(other, (int64_t)B * h * w * 512, 512, true, passes_of(ctx->precision));
-        if ((rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.s, last.C, 128, {}, mid.s, 512, 0, nullptr, 0, 0))) return rc;
-        if ((rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[15], B, h, w, mid.s, 512, 512, {}, Split(), 0, 0, low, 2, 0))) return rc;
+        if ((rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.s, last.C, 128, {}, mid.s, 512, 0, nullptr, 0, 0, 0, 0, true))) return rc;
+        if ((rc = add_tc(ctx, pl.get(), "HandSegNet", kHandSeg[15], B, h, w, mid.s, 512, 512, {}, Split(), 0, 0, low, 2, 0, 0, 0, true))) return rc;
     } else {
         float* f512 = (float*)other;
         if ((rc = add_direct(ctx, pl.get(), "HandSegNet", kHandSeg[14], B, h, w, last.f, last.C, 0, f512, 512, 0, Split(), 0, 0))) return rc;
         if ((rc = add_direct(ctx, pl.get(), "HandSegNet", kHandSeg[15], B, h, w, f512, 512, 0, low, 2, 0, Split(), 0, 0))) return rc;
     }
-    pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return launch_resize_bilinear_tf1(low, e.out, B, h, w, 2, H, W, s); });
+    // e.out == nullptr (pipeline): the x8 up-sampling is fused into the mask post-processing (launch_seg_postprocess reads seg_low)
+    pl->steps.push_back([=](const Ext& e, cudaStream_t s) { return e.out ? launch_resize_bilinear_tf1(low, e.out, B, h, w, 2, H, W, s) : H3D_OK; });
     pl->launches.push_back(1);
     ctx->seg = std::move(pl);
     return H3D_OK;
@@ -518,6 +559,7 @@ static int build_posenet(h3d_ctx* ctx, int B, int Hc, int Wc) {
     auto pl = std::make_unique<StagePlan>();
     pl->B = B; pl->H = Hc; pl->W = Wc;
     const bool tc = is_tc(ctx->precision);
+    if (tc) { if (int rc0 = begin_chain_sync(pl.get(), B)) return rc0; }
     const int lo = passes_of(ctx->precision);
     const int h8 = Hc / 8, w8 = Wc / 8;
     const int LH = std::max(ctx->lay.H, 256), LW = std::max(ctx->lay.W, 256);
@@ -554,8 +596,8 @@ static int build_posenet(h3d_ctx* ctx, int B, int Hc, int Wc) {
         int rc2;
         if (tc) {
             Act mid = slot_view((char*)f512, pix * cin6, cin6, true, lo);
-            if ((rc2 = add_tc(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.s, in6.C, 128, {}, mid.s, cin6, 0, nullptr, 0, 0))) return rc2;
-            rc2 = add_tc(ctx, pl.get(), "PoseNet2D", l7, B, h, w, mid.s, cin6, cin6, {}, feed_back ? cb.s : Split(), 192, 128, sm_out, 21, 0);
+            if ((rc2 = add_tc(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.s, in6.C, 128, {}, mid.s, cin6, 0, nullptr, 0, 0, 0, 0, true))) return rc2;
+            rc2 = add_tc(ctx, pl.get(), "PoseNet2D", l7, B, h, w, mid.s, cin6, cin6, {}, feed_back ? cb.s : Split(), 192, 128, sm_out, 21, 0, 0, 0, true);
         } else {
             if ((rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l6, B, h, w, in6.f, in6.C, in6.f == cb.f ? 21 : 0, f512, cin6, 0, Split(), 0, 0))) return rc2;
             rc2 = add_direct(ctx, pl.get(), "PoseNet2D", l7, B, h, w, f512, cin6, 0, sm_out, 21, 0, Split(), 0, 0);
@@ -580,7 +622,7 @@ static int build_posenet(h3d_ctx* ctx, int B, int Hc, int Wc) {
         for (int i = 0; i < 5; ++i) {
             LayerSpec l{nm[i], 7, 1, i == 0 ? 149 : 128, 128, 1};
             Act out = slot_view(slots[i & 1], pix * 128, 128, tc, lo);
-            if (tc) rc = add_tc(ctx, pl.get(), "PoseNet2D", l, B, h, w, in.s, in.C, i == 0 ? 192 : 128, i == 0 ? perm : std::vector<int>(), out.s, 128, 0, nullptr, 0, 0);
+            if (tc) rc = add_tc(ctx, pl.get(), "PoseNet2D", l, B, h, w, in.s, in.C, i == 0 ? 192 : 128, i == 0 ? perm : std::vector<int>(), out.s, 128, 0, nullptr, 0, 0, 0, 0, true);
             else rc = add_direct(ctx, pl.get(), "PoseNet2D", l, B, h, w, in.f, in.C, 0, out.f, 128, 0, Split(), 0, 0);
             if (rc) return rc;
             in = out;
@@ -1129,15 +1171,22 @@ int h3d_set_workspace(h3d_ctx* ctx, void* dev_ptr, int64_t bytes) {
     return H3D_OK;
 }
 
-int h3d_handsegnet_forward(h3d_ctx* ctx, const float* image, int B, int H, int W, float* logits, void* stream) {
-    DeviceGuard guard_(ctx ? ctx->device : 0);
-    H3D_REQUIRE(ctx && image && logits && B > 0, "h3d_handsegnet_forward: bad argument");
+// logits == nullptr: stop after the low-resolution head (Layout::seg_low); the caller up-samples (fused into the mask post-processing)
+static int run_handsegnet(h3d_ctx* ctx, const float* image, int B, int H, int W, float* logits, void* stream) {
     int rc;
     if ((rc = ensure_layout_covers(ctx, B, H, W, 0, 0))) return rc;
     if (!ctx->seg || ctx->seg->B != B || ctx->seg->H != H || ctx->seg->W != W)
         if ((rc = build_handsegnet(ctx, B, H, W))) return rc;
     Ext e; e.in = image; e.out = logits;
-    return run_plan(ctx, ctx->seg.get(), e, (cudaStream_t)stream);
+    rc = run_plan(ctx, ctx->seg.get(), e, (cudaStream_t)stream);
+    if (!logits) ctx->launches -= 1;   // the skipped up-sampling step
+    return rc;
+}
+
+int h3d_handsegnet_forward(h3d_ctx* ctx, const float* image, int B, int H, int W, float* logits, void* stream) {
+    DeviceGuard guard_(ctx ? ctx->device : 0);
+    H3D_REQUIRE(ctx && image && logits && B > 0, "h3d_handsegnet_forward: bad argument");
+    return run_handsegnet(ctx, image, B, H, W, logits, stream);
 }
 
 int h3d_posenet_forward(h3d_ctx* ctx, const float* image_crop, int B, int Hc, int Wc, float* s0, float* s1, float* s2, void* stream) {
@@ -1203,10 +1252,13 @@ int h3d_pipeline_forward(h3d_ctx* ctx, const float* image, const float* hand_sid
     float* cen = center ? center : L.center;
     float* scl = scale_crop ? scale_crop : L.scale;
     // HandSegNet (nets/...:78-79)
-    if ((rc = h3d_handsegnet_forward(ctx, image, B, H, W, seg, stream))) return rc;
+    // (its x8 up-sampling, nets/...:166, is fused into the next kernel: the 0.82 MB / image hand_scoremap is written once, not re-read)
+    const bool fuse_up = !tc_tuning().no_seg_fusion;
+    if ((rc = run_handsegnet(ctx, image, B, H, W, fuse_up ? nullptr : seg, stream))) return rc;
     // single_obj_scoremap + calc_center_bb + scale (nets/...:82-85)
     int nl = 0;
-    if ((rc = launch_seg_postprocess(seg, B, H, W, L.seg_scratch, hand_mask, nullptr, cen, L.crop_size, scl, s, &nl))) return rc;
+    if ((rc = launch_seg_postprocess(seg, B, H, W, L.seg_scratch, hand_mask, nullptr, cen, L.crop_size, scl, s, &nl,
+                                     fuse_up ? L.seg_low : nullptr, H / 8, W / 8))) return rc;
     ctx->launches += nl;
     if (force_center) H3D_CUDA(cudaMemcpyAsync(cen, force_center, (size_t)B * 8, cudaMemcpyDeviceToDevice, s));
     if (force_scale) H3D_CUDA(cudaMemcpyAsync(scl, force_scale, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));

@@ -97,7 +97,7 @@ int launch_split_to_f32(Split x, float* y, int64_t rows, int C, int Cpad, Half16
 int64_t seg_scratch_bytes(int B, int H, int W);
 int launch_seg_postprocess(const float* logits, int B, int H, int W, void* scratch, uint8_t* hand_mask,
                            int32_t* max_loc, float* center, float* crop_size, float* scale_crop, cudaStream_t s,
-                           int* n_launch);
+                           int* n_launch, const float* low = nullptr, int LH = 0, int LW = 0);
 int launch_crop_image(const float* image, const float* center, const float* scale, float* out, int B, int H, int W,
                       int C, int crop, cudaStream_t s);
 int64_t argmax_scratch_bytes(int B, int C);
@@ -193,8 +193,10 @@ struct TcTuning {
     int chunk_kb = 0;      // 0 policy
     int exp = 0;           // timing experiments (wrong results allowed), see TcParams::exp
     int no_side_stream = 0, no_pool_fusion = 0, lift_direct = 0, c3_ffma = 0;
+    int no_seg_fusion = 0; // 1: HandSegNet's x8 up-sampling as its own launch (instead of fused into the mask post-processing)
     int c64_tma_out = 1;   // 64-channel pair kernel: bulk-tensor-store epilogue for un-pooled layers (conv2_1)
     int fc_chain = 1;      // FC stacks + rotation epilogue of the lifting stage as one kernel (0 = one launch per layer)
+    int chain = 1;         // layer chains: dynamic tile tickets + per-image dependencies between consecutive CTA-pair conv launches (2 = tickets only)
     int pdl = 1;           // programmatic dependent launch between the tensor-core kernels (prologue overlaps the previous kernel's tail)
     int c3_tma = 1;        // first layer: shared-memory staged epilogue + bulk tensor stores (0 = direct 16-byte global stores)
 };
@@ -219,6 +221,10 @@ void fc_chain_plan_destroy(FcChainPlan* p);
 int fc_chain_launch(const FcChainPlan* p, const float* hand_side, float* rot, float* out, cudaStream_t s);
 TcConvPlan* tc_conv_plan_create(const TcConvDesc& d);   // nullptr on failure (h3d_last_error set)
 void tc_conv_plan_destroy(TcConvPlan* p);
+bool tc_conv_plan_chainable(const TcConvPlan* p);
+int tc_conv_plan_signal_target(const TcConvPlan* p);
+const TcConvDesc& tc_conv_plan_desc(const TcConvPlan* p);
+void tc_conv_plan_set_chain(TcConvPlan* p, int* sched, const int* dep_cnt, int dep_target, int* sig_cnt);
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t s);
 int64_t tc_conv_flops(const TcConvPlan* p);
 int tc_num_sms();

@@ -62,6 +62,11 @@ struct TcParams {
     int exp;        // reserved for timing experiments (tc_set_tuning("tc_exp")); unused by the shipped kernels
     int tma_out;    // conv_c64x2_kernel: un-pooled split-plane output staged in shared memory and written by bulk tensor stores
     int* err_flag;
+    // conv_tc2_kernel, layer chains (see "Layer chains" above the kernel); all optional
+    int* sched;            // ticket counter of this launch (zeroed before the launch): dynamic tile scheduler; null = static round-robin
+    const int* dep_cnt;    // per-image completion counters of the layer that produces this layer's input; null = griddepcontrol.wait
+    int dep_target;        // arrivals per image that mean "every tile of the image has been stored"
+    int* sig_cnt;          // this layer's per-image completion counters (zeroed before the launch); null = no signalling
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -224,6 +229,51 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
         "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// 32-bit store into the shared memory of CTA `rank` of the cluster, at the offset of `p` in this CTA
+__device__ __forceinline__ void st_shared_cluster_u32(const void* p, uint32_t rank, uint32_t v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "st.shared::cluster.u32 [ra], %2;\n\t}"
+        ::"r"(smem_u32(p)), "r"(rank), "r"(v) : "memory");
+}
+// wait with cluster-scope acquire: orders shared-memory data written by the PEER CTA before its (release.cluster) arrive
+__device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+    if (mbar_try_wait_cl(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cl(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            if (err_flag) { atomicExch_system(err_flag, code); __threadfence_system(); }
+            __trap();
+        }
+    }
+}
+// Bounded wait until a device-scope counter reaches `target` (acquire): layer-chain dependencies between two resident grids
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void counter_wait(const int* cnt, int target, int* err_flag, int code) {
+    if (ld_acquire_gpu(cnt) >= target) return;
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(cnt) < target) {
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000ll) {
+            if (err_flag) { atomicExch_system(err_flag, code); __threadfence_system(); }
+            __trap();
+        }
+    }
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
@@ -1191,6 +1241,25 @@ __host__ __device__ constexpr int num_stages2(int BN, int PASSES) {
     return kSmemBudget / stage_bytes2(BN, PASSES) > 8 ? 8 : kSmemBudget / stage_bytes2(BN, PASSES);
 }
 
+// Layer chains (round 2).  A layer whose pixel tiles do not fill a whole number of waves (the 32x32 / 40x40 maps: 1.7 - 5.4 waves
+// of tile pairs on 74 SM pairs) leaves 10 - 14 % of the machine idle in its last wave, and a dependent launch cannot use that time
+// because griddepcontrol.wait blocks until the WHOLE previous grid has finished.  Three mechanisms remove the bubble:
+//   * dynamic tile scheduler: the leader's producer warp draws tile tickets from a device counter (p.sched) and hands every ticket
+//     to the MMA warp, the epilogue warps and the peer CTA through a 4-slot shared-memory ring (sfull / sempty mbarriers, the peer
+//     copy written through DSMEM) - the CTAs that become resident early simply take the first tickets; results do not depend on
+//     which CTA computes a tile, so this changes no bit of the output;
+//   * per-image completion counters: after the stores of a tile every epilogue thread fences, the eight epilogue warps meet at a
+//     named barrier and one thread bumps sig_cnt[image]; the NEXT layer's producer warps wait for dep_cnt[image] == dep_target
+//     (acquire at device scope, then fence.proxy.async because TMA reads through the async proxy) instead of griddepcontrol.wait;
+//     convolutions never read across images, so a tile may start as soon as its own images are complete;
+//   * stores stay behind griddepcontrol.wait (executed by each epilogue thread before its first store): the ping-pong slots make
+//     the output of layer i+1 alias the input of layer i, so layer i+1 may READ early but never WRITE before layer i has
+//     completed.  Completion of a kernel therefore still implies completion of all its predecessors.
+// A CTA of layer i+1 that became resident in the tail of layer i thus runs the main loop of its first tile, drains the accumulator
+// chunks into registers, and blocks only at its first store.  All waits are bounded (trap + error word).
+constexpr int kSchedSlots = 4;
+constexpr int kSchedConsumers = 18;   // MMA warp + 8 epilogue warps of the leader, producer warp + 8 epilogue warps of the peer
+
 template <int BN, int PASSES, bool FP16>
 // Register budget: 10 warps land 3 / 3 / 2 / 2 on the four SM sub-partitions of 16384 registers each, so 16384 / (3 x 32) = 170 ->
 // 168 registers per thread is the hardware limit for this block shape (a __maxnreg__(200) build compiles spill-free at 197
@@ -1213,6 +1282,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     static_assert(PASSES != 4 || FP16, "fp8-correction mode uses an fp16 main plane");
     constexpr int COLS = BN / 2;                       // accumulator columns drained by one epilogue warp
     static_assert(STAGES >= 2, "need at least a double-buffered pipeline");
+    static_assert((2 * STAGES + 4 + 2 * kSchedSlots) * 8 + kSchedSlots * 4 + 4 <= 256, "barrier area");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1220,7 +1290,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* sfull_bar = tempty_bar + 2;              // tile ring: ticket published (one per CTA, arrived by the leader's producer)
+    uint64_t* sempty_bar = sfull_bar + kSchedSlots;    // tile ring: ticket consumed (leader CTA only, kSchedConsumers arrivals)
+    int* sched_tile = reinterpret_cast<int*>(sempty_bar + kSchedSlots);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_tile + kSchedSlots);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -1233,6 +1306,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         if (PASSES == 4) { prefetch_tmap(&map_x_h8); prefetch_tmap(&map_w_l8); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
+        for (int s = 0; s < kSchedSlots; ++s) { mbar_init(&sfull_bar[s], 1); mbar_init(&sempty_bar[s], kSchedConsumers); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -1244,15 +1318,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
-    pdl_wait();
+    if (!p.dep_cnt) pdl_wait();  // chained layers: the producer waits per image, the epilogue before its first store
 
     if (warp == 8) {
         // ================================ TMA producer (both CTAs; whole warp, one elected lane issues) ================================
         int stage = 0; uint32_t phase = 0;
-        for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
+        for (int seq = 0;; ++seq) {
+            const int slot = seq & (kSchedSlots - 1);
+            const uint32_t sph = (uint32_t)(seq / kSchedSlots) & 1u;
+            int item;
+            if (rank == 0) {     // draw the next ticket and publish it to both CTAs
+                mbar_wait(&sempty_bar[slot], sph ^ 1, p.err_flag, 5);
+                int v = 0;
+                if (lane == 0) {
+                    v = p.sched ? atomicAdd(p.sched, 1) : cluster_id + seq * num_clusters;
+                    if (v >= p.num_tiles) v = -1;
+                    sched_tile[slot] = v;
+                    st_shared_cluster_u32(&sched_tile[slot], 1, (uint32_t)v);
+                    mbar_arrive(&sfull_bar[slot]);
+                    mbar_arrive_cluster(&sfull_bar[slot], 1);
+                }
+                item = __shfl_sync(0xFFFFFFFFu, v, 0);
+            } else {
+                mbar_wait_cl(&sfull_bar[slot], sph, p.err_flag, 6);
+                item = sched_tile[slot];
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&sempty_bar[slot], 0);
+            }
+            item = __reduce_max_sync(0xFFFFFFFFu, item);   // same value in every lane: keeps the TMA coordinates in uniform registers
+            if (item < 0) break;
             const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
             const int w0 = tw * p.TW - p.pad, h0 = th * p.TH - p.pad, b0 = tb * p.TB, n0 = nt * BN + (int)rank * (BN / 2);
+            if (p.dep_cnt) {     // the images of this tile are complete in the producing layer (an odd tile count leaves b0 >= B: zero fill)
+                const int bend = min(b0 + p.TB, p.B);
+                for (int b = b0; b < bend; ++b) counter_wait(p.dep_cnt + b, p.dep_target, p.err_flag, 7);
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
             int kcol = 0;
             for (int kh = 0; kh < p.k; ++kh) {
                 for (int kw = 0; kw < p.k; ++kw) {
@@ -1291,7 +1393,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         if (rank == 0) {
             int stage = 0; uint32_t phase = 0;
             int acc_it = 0;
-            for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
+            for (int seq = 0;; ++seq) {
+                const int slot = seq & (kSchedSlots - 1);
+                mbar_wait_cl(&sfull_bar[slot], (uint32_t)(seq / kSchedSlots) & 1u, p.err_flag, 6);
+                int item = sched_tile[slot];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty_bar[slot]);
+                item = __reduce_max_sync(0xFFFFFFFFu, item);
+                if (item < 0) break;
                 for (int kb0 = 0; kb0 < kblocks; kb0 += p.chunk_kb, ++acc_it) {
                     const int acc = acc_it & 1;
                     mbar_wait(&tempty_bar[acc], ((acc_it >> 1) & 1) ^ 1, p.err_flag, 2);
@@ -1347,7 +1456,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         const int row = q * 32 + lane;                       // tile row = TMEM lane
         const int w_l = row % p.TW, h_l = (row / p.TW) % p.TH, b_l = row / (p.TW * p.TH);
         int acc_it = 0;
-        for (int item = cluster_id; item < p.num_tiles; item += num_clusters) {
+        bool may_store = p.dep_cnt == nullptr;               // chained layers: griddepcontrol.wait before the first store (WAR on the slots)
+        for (int seq = 0;; ++seq) {
+            const int slot = seq & (kSchedSlots - 1);
+            mbar_wait_cl(&sfull_bar[slot], (uint32_t)(seq / kSchedSlots) & 1u, p.err_flag, 6);
+            const int item = sched_tile[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&sempty_bar[slot], 0);
+            if (item < 0) break;
             const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / (p.tiles_w * p.tiles_h);
             const int w = tw * p.TW + w_l, h = th * p.TH + h_l, b = tb * p.TB + b_l, n0 = nt * BN + ch * COLS;
@@ -1387,8 +1503,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);   // leader's barrier: 16 arrivals per phase
             }
+            if (!may_store) { pdl_wait(); may_store = true; }
 #pragma unroll
             for (int c0 = 0; c0 < COLS; c0 += 32) epilogue_store32<PASSES, FP16>(p, &racc[c0], pix, n0 + c0, valid);
+            if (p.sig_cnt) {     // this CTA's tile is stored: bump the completion counters of its images
+                __threadfence();
+                named_bar_sync(1, 32 * 8);
+                if (threadIdx.x == 0) {
+                    const int b0 = tb * p.TB, bend = min(b0 + p.TB, p.B);
+                    for (int bb = b0; bb < bend; ++bb) atomicAdd(p.sig_cnt + bb, 1);
+                }
+            }
         }
     }
 
@@ -1964,6 +2089,8 @@ TcTuning& tc_tuning() {
         v.pdl = geti("H3D_PDL", 1);
         v.fc_chain = geti("H3D_FC_CHAIN", 1);
         v.c64_tma_out = geti("H3D_C64_TMA_OUT", 1);
+        v.chain = geti("H3D_TC_CHAIN", 1);
+        v.no_seg_fusion = geti("H3D_NO_SEG_FUSION", 0);
         return v;
     }();
     return t;
@@ -1987,6 +2114,8 @@ int tc_set_tuning(const char* key, int value) {
     else if (k == "pdl") t.pdl = value;
     else if (k == "fc_chain") t.fc_chain = value;
     else if (k == "c64_tma_out") t.c64_tma_out = value;
+    else if (k == "tc_chain") t.chain = value;
+    else if (k == "no_seg_fusion") t.no_seg_fusion = value;
     else { set_error("h3d_set_tuning: unknown key '%s'", k.c_str()); return H3D_EINVAL; }
     return H3D_OK;
 }
@@ -2148,6 +2277,14 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
 }
 
 void tc_conv_plan_destroy(TcConvPlan* p) { delete p; }
+
+// Layer chains (conv_tc2_kernel): only the CTA-pair kernel draws tickets / signals / waits per image
+bool tc_conv_plan_chainable(const TcConvPlan* p) { return p->two_cta && !p->c64 && !p->c64x2; }
+int tc_conv_plan_signal_target(const TcConvPlan* p) { return p->p.tiles_w * p->p.tiles_h * p->p.n_tiles; }
+const TcConvDesc& tc_conv_plan_desc(const TcConvPlan* p) { return p->d; }
+void tc_conv_plan_set_chain(TcConvPlan* p, int* sched, const int* dep_cnt, int dep_target, int* sig_cnt) {
+    p->p.sched = sched; p->p.dep_cnt = dep_cnt; p->p.dep_target = dep_target; p->p.sig_cnt = sig_cnt;
+}
 
 int64_t tc_conv_flops(const TcConvPlan* p) {
     return 2ll * p->d.B * p->d.H * p->d.W * p->d.k * p->d.k * (int64_t)p->d.Cin_pad * p->d.Cout_pad;

@@ -331,8 +331,14 @@ int64_t seg_scratch_bytes(int B, int H, int W) {
     return align_up((int64_t)B * 8, 256) + align_up((int64_t)B * H * seg_words(W) * 4, 256);
 }
 
-__global__ void seg_prob_kernel(const float2* __restrict__ logits, int H, int W, int Ww, unsigned long long* __restrict__ key,
-                                uint32_t* __restrict__ det) {
+// UPS = false: `logits` is the full-resolution map [B,H,W,2] (operator entry h3d_seg_postprocess).
+// UPS = true (pipeline): `logits` is HandSegNet's low-resolution head output [B,LH,LW,2]; the kernel up-samples it on the fly with exactly
+// the operations of resize_bilinear_tf1_kernel<2> (nets/...:166), WRITES the full-resolution hand_scoremap to `up` and classifies the
+// values it has in registers - the 0.82 MB / image map is written once and never read back (it was: written, then re-read).
+template <bool UPS>
+__global__ void __launch_bounds__(256)
+seg_prob_kernel(const float2* __restrict__ logits, float2* __restrict__ up, int LH, int LW, float hscale, float wscale, int H, int W,
+                int Ww, unsigned long long* __restrict__ key, uint32_t* __restrict__ det) {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
@@ -344,7 +350,21 @@ __global__ void seg_prob_kernel(const float2* __restrict__ logits, int H, int W,
         bool bit = false;
         if (x < W) {
             const int idx = y * W + x;
-            const float2 l = __ldg(logits + (int64_t)b * H * W + idx);
+            float2 l;
+            if (UPS) {
+                const float in_y = __fmul_rn((float)y, hscale), in_x = __fmul_rn((float)x, wscale);
+                const int y0 = (int)floorf(in_y), x0 = (int)floorf(in_x);
+                const int y1 = min(y0 + 1, LH - 1), x1 = min(x0 + 1, LW - 1);
+                const float ly = __fsub_rn(in_y, (float)y0), lx = __fsub_rn(in_x, (float)x0);
+                const float2* r0 = logits + ((int64_t)b * LH + y0) * LW;
+                const float2* r1 = logits + ((int64_t)b * LH + y1) * LW;
+                const float2 tl = __ldg(r0 + x0), tr = __ldg(r0 + x1), bl = __ldg(r1 + x0), br = __ldg(r1 + x1);
+                l.x = lerp_tf(lerp_tf(tl.x, tr.x, lx), lerp_tf(bl.x, br.x, lx), ly);
+                l.y = lerp_tf(lerp_tf(tl.y, tr.y, lx), lerp_tf(bl.y, br.y, lx), ly);
+                up[(int64_t)b * H * W + idx] = l;
+            } else {
+                l = __ldg(logits + (int64_t)b * H * W + idx);
+            }
             const float m = fmaxf(l.x, l.y);
             const float e0 = expf(__fsub_rn(l.x, m)), e1 = expf(__fsub_rn(l.y, m));
             const float inv = __fdiv_rn(1.0f, __fadd_rn(e0, e1));
@@ -377,18 +397,25 @@ __global__ void seg_prob_kernel(const float2* __restrict__ logits, int H, int W,
 
 constexpr int kGrowThreads = 1024;
 constexpr int kMaxMaskWords = 512 * 16;  // H, W <= 512
-constexpr int kMaxRowWords = 16;         // W <= 512
-constexpr int kWordsPerThread = kMaxMaskWords / kGrowThreads;   // 8
+constexpr int kGrowRows = 8;             // rows per thread in the vertical phase
+constexpr int kGrowSeg = 4;              // words per thread in the horizontal phase
+constexpr int kGrowPadTop = 10, kGrowPadBot = 10 + kGrowRows - 1;
+__host__ __device__ inline int grow_rows_padded(int H) { return (H + kGrowRows - 1) / kGrowRows * kGrowRows; }
+// shared memory: det, obj [Hp][Ww] (Hp = H rounded up to 8, padding rows zero) and hor [10 + Hp + 17][Ww] (padding rows zero)
+__host__ __device__ inline size_t grow_smem_bytes(int H, int Ww) {
+    return (size_t)(2 * grow_rows_padded(H) + kGrowPadTop + grow_rows_padded(H) + kGrowPadBot) * Ww * sizeof(uint32_t);
+}
 
 __global__ void __launch_bounds__(kGrowThreads, 1)
 mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __restrict__ det_g, int H, int W, int Ww,
                  int num_passes, uint8_t* __restrict__ hand_mask, int32_t* __restrict__ max_loc, float* __restrict__ center,
                  float* __restrict__ crop_size, float* __restrict__ scale_crop) {
     extern __shared__ uint32_t sm[];
-    uint32_t* det = sm;                    // [H][Ww]
-    uint32_t* obj = sm + H * Ww;           // [H][Ww]
-    uint32_t* hor = sm + 2 * H * Ww;       // [H][Ww]
-    __shared__ int s_changed;
+    const int Hp = grow_rows_padded(H);
+    uint32_t* det = sm;                                   // [Hp][Ww]
+    uint32_t* obj = sm + Hp * Ww;                         // [Hp][Ww]
+    uint32_t* hor_p = sm + 2 * Hp * Ww;                   // [10 + Hp + 17][Ww]: row y of the image is row y + 10
+    uint32_t* hor = hor_p + kGrowPadTop * Ww;
     __shared__ int s_rmin, s_rmax, s_cmin, s_cmax;
     const int b = blockIdx.x;
     const int words = H * Ww;
@@ -397,10 +424,11 @@ mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __r
     const unsigned long long k = key[b];
     const int seed_idx = (int)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
     const int sy = seed_idx / W, sx = seed_idx - sy * W;
-    for (int i = tid; i < words; i += kGrowThreads) {
-        det[i] = det_g[(int64_t)b * words + i];
+    for (int i = tid; i < Hp * Ww; i += kGrowThreads) {
+        det[i] = i < words ? det_g[(int64_t)b * words + i] : 0u;
         obj[i] = 0u;
     }
+    for (int i = tid; i < (kGrowPadTop + Hp + kGrowPadBot) * Ww; i += kGrowThreads) hor_p[i] = 0u;
     if (tid == 0) {
         s_rmin = 1 << 30; s_rmax = -1; s_cmin = 1 << 30; s_cmax = -1;
         if (max_loc) { max_loc[2 * b] = sy; max_loc[2 * b + 1] = sx; }
@@ -409,77 +437,80 @@ mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __r
     if (tid == 0) obj[sy * Ww + (sx >> 5)] = 1u << (sx & 31);   // one-hot seed (utils/general.py:252-253)
     __syncthreads();
 
-    // One pass = obj <- det AND dilate21x21(obj).  The 21 x 21 box dilation is separable:
-    //  * horizontal (bits): one thread per image row keeps the row's words in registers and widens the set by -+1, -+2, -+4, -+3 pixels
-    //    (windows 3 -> 7 -> 15 -> 21 pixels: 4 multi-word shift-OR steps instead of 20);
-    //  * vertical (rows): van Herk / Gil-Werman with blocks of 21 rows: pre[y] = OR of the block's rows up to y, suf[y] = OR from y
-    //    to the block's end, window [y-10, y+10] = suf[y-10] | pre[y+10] (3 word operations per row instead of 21).
-    uint32_t* pre = sm + 3 * H * Ww;        // [H][Ww]
-    uint32_t* suf = sm + 4 * H * Ww;        // [H][Ww]
-    const int nblk = (H + 20) / 21;
-    // per-thread constants of the combine phase (word i = tid + q * 1024): window [a, b] = [y-10, y+10] clipped to the image; inside one
-    // 21-row block it is a prefix (mode 0: the window starts at the block's first row) or a suffix (mode 1), else suffix | prefix (mode 2)
-    int c_a[kWordsPerThread], c_b[kWordsPerThread], c_mode[kWordsPerThread];
+    // One pass = obj <- det AND dilate21x21(obj).  The 21 x 21 box dilation is separable; the SM is instruction-issue bound on it (one
+    // CTA per image), so both phases are organised for few instructions per word:
+    //  * horizontal (bits): one thread per run of 4 words of a row; the run plus one neighbour word on either side (6 words in registers)
+    //    is widened by -+1, -+2, -+4, -+3 pixels (windows 3 -> 7 -> 15 -> 21 pixels: 4 funnel-shift steps instead of 20); the missing
+    //    outer neighbours only corrupt the outer 10 bits of the two side words, which the 4 inner words never see;
+    //  * vertical (rows) + combine: one thread per (word column, group of 8 rows): the 28 rows [y0-10, y0+17] are read once (zero
+    //    padding rows above and below: no bounds checks), the 14 rows common to the eight windows are OR-ed once and the 7 + 7 rows at
+    //    either end enter as running prefixes; the result is AND-ed with det, compared with obj and written back (obj is only read in the
+    //    horizontal phase).
+    // Two block barriers per pass; the second one also carries the "something changed" vote (__syncthreads_or).
+    const int segs = (Ww + kGrowSeg - 1) / kGrowSeg;
+    const int h_tasks = H * segs;                          // <= 2048: at most two per thread
+    int h_base[2], h_x0[2];
 #pragma unroll
-    for (int q = 0; q < kWordsPerThread; ++q) {
-        const int i = tid + q * kGrowThreads;
-        const int y = i / Ww, xw = i - y * Ww;
-        const int a = max(y - 10, 0), b2 = min(y + 10, H - 1);
-        c_a[q] = a * Ww + xw; c_b[q] = b2 * Ww + xw;
-        c_mode[q] = (a / 21 == b2 / 21) ? ((a % 21 == 0) ? 0 : 1) : 2;
+    for (int q = 0; q < 2; ++q) {
+        const int t = tid + q * kGrowThreads;
+        const int y = t / segs, sg = t - y * segs;
+        h_x0[q] = sg * kGrowSeg;
+        h_base[q] = t < h_tasks ? y * Ww + sg * kGrowSeg : -1;
     }
+    const int groups = Hp / kGrowRows;
+    const int v_tasks = groups * Ww;                       // <= 64 * 16 = 1024: at most one per thread
+    const int v_g = tid / Ww, v_xw = tid - v_g * Ww;
+    const int v_base = v_g * kGrowRows * Ww + v_xw;        // word of (row y0, column xw); rows advance by Ww words
     for (int pass = 0; pass < num_passes; ++pass) {
-        if (tid == 0) s_changed = 0;
-        if (tid < H) {
-            uint32_t w[kMaxRowWords];
 #pragma unroll
-            for (int i = 0; i < kMaxRowWords; ++i) w[i] = i < Ww ? obj[tid * Ww + i] : 0u;
+        for (int q = 0; q < 2; ++q) {
+            if (h_base[q] >= 0) {
+                const int base = h_base[q], x0 = h_x0[q];
+                uint32_t w[kGrowSeg + 2];
 #pragma unroll
-            for (int step = 0; step < 4; ++step) {
-                const int sft = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 3;
-                uint32_t r[kMaxRowWords];
-#pragma unroll
-                for (int i = 0; i < kMaxRowWords; ++i) {
-                    const uint32_t prev = i > 0 ? w[i - 1] : 0u, next = i + 1 < kMaxRowWords ? w[i + 1] : 0u;
-                    r[i] = w[i] | __funnelshift_l(prev, w[i], sft) | __funnelshift_r(w[i], next, sft);
+                for (int i = 0; i < kGrowSeg + 2; ++i) {
+                    const int xw = x0 - 1 + i;
+                    w[i] = (xw >= 0 && xw < Ww) ? obj[base - 1 + i] : 0u;
                 }
 #pragma unroll
-                for (int i = 0; i < kMaxRowWords; ++i) w[i] = r[i];
+                for (int step = 0; step < 4; ++step) {
+                    const int sft = step == 0 ? 1 : step == 1 ? 2 : step == 2 ? 4 : 3;
+                    uint32_t r[kGrowSeg + 2];
+#pragma unroll
+                    for (int i = 0; i < kGrowSeg + 2; ++i) {
+                        const uint32_t lo = i > 0 ? w[i - 1] : 0u, hi = i + 1 < kGrowSeg + 2 ? w[i + 1] : 0u;
+                        r[i] = w[i] | __funnelshift_l(lo, w[i], sft) | __funnelshift_r(w[i], hi, sft);
+                    }
+#pragma unroll
+                    for (int i = 0; i < kGrowSeg + 2; ++i) w[i] = r[i];
+                }
+#pragma unroll
+                for (int i = 0; i < kGrowSeg; ++i)
+                    if (x0 + i < Ww) hor[base + i] = w[i + 1];      // bits beyond W in the last word are masked by det below
             }
-#pragma unroll
-            for (int i = 0; i < kMaxRowWords; ++i)
-                if (i < Ww) hor[tid * Ww + i] = w[i];      // bits beyond W in the last word are masked by det below
-        }
-        __syncthreads();
-        for (int t = tid; t < nblk * Ww; t += kGrowThreads) {
-            const int k = t / Ww, xw = t - k * Ww;
-            const int y0 = 21 * k, n = min(21, H - y0);
-            uint32_t a = 0u;
-#pragma unroll
-            for (int q = 0; q < 21; ++q)
-                if (q < n) { a |= hor[(y0 + q) * Ww + xw]; pre[(y0 + q) * Ww + xw] = a; }
-            a = 0u;
-#pragma unroll
-            for (int q = 20; q >= 0; --q)
-                if (q < n) { a |= hor[(y0 + q) * Ww + xw]; suf[(y0 + q) * Ww + xw] = a; }
         }
         __syncthreads();
         int changed = 0;
+        if (tid < v_tasks) {
+            uint32_t v[kGrowRows + 20];
 #pragma unroll
-        for (int q = 0; q < kWordsPerThread; ++q) {
-            const int i = tid + q * kGrowThreads;
-            if (i < words) {
-                uint32_t r = c_mode[q] == 0 ? pre[c_b[q]] : c_mode[q] == 1 ? suf[c_a[q]] : (suf[c_a[q]] | pre[c_b[q]]);
-                r &= det[i];
+            for (int i = 0; i < kGrowRows + 20; ++i) v[i] = hor_p[v_base + i * Ww];   // rows y0 - 10 .. y0 + 17
+            uint32_t core = v[kGrowRows - 1];
+#pragma unroll
+            for (int i = kGrowRows; i <= 20; ++i) core |= v[i];                       // rows common to the windows of y0 .. y0 + 7
+            uint32_t lo[kGrowRows], hi[kGrowRows];                                     // lo[k] = v[7-k .. 6], hi[k] = v[21 .. 20+k]; [0] = 0
+            lo[0] = 0u; hi[0] = 0u;
+#pragma unroll
+            for (int kk = 1; kk < kGrowRows; ++kk) { lo[kk] = lo[kk - 1] | v[kGrowRows - 1 - kk]; hi[kk] = hi[kk - 1] | v[20 + kk]; }
+#pragma unroll
+            for (int j = 0; j < kGrowRows; ++j) {
+                const int i = v_base + j * Ww;                                         // padding rows: det = 0 -> obj stays 0
+                const uint32_t r = (core | lo[kGrowRows - 1 - j] | hi[j]) & det[i];
                 changed |= (r != obj[i]);
-                obj[i] = r;                  // obj is not read by anybody else in this phase
+                obj[i] = r;
             }
         }
-        if (changed) s_changed = 1;
-        __syncthreads();
-        const int any = s_changed;
-        __syncthreads();
-        if (!any) break;   // fixed point: remaining passes are no-ops
+        if (!__syncthreads_or(changed)) break;   // fixed point: remaining passes are no-ops
     }
 
     // bounding box (utils/general.py:294-300): X = row index, Y = column index
@@ -521,23 +552,30 @@ mask_grow_kernel(const unsigned long long* __restrict__ key, const uint32_t* __r
     }
 }
 
+// low != nullptr: fused form for the pipeline - `low` [B,LH,LW,2] is up-sampled to `logits` [B,H,W,2] (written) and classified in one pass
 int launch_seg_postprocess(const float* logits, int B, int H, int W, void* scratch, uint8_t* hand_mask, int32_t* max_loc,
-                           float* center, float* crop_size, float* scale_crop, cudaStream_t s, int* n_launch) {
+                           float* center, float* crop_size, float* scale_crop, cudaStream_t s, int* n_launch, const float* low, int LH,
+                           int LW) {
     H3D_REQUIRE(H <= 512 && W <= 512 && H > 0 && W > 0, "seg_postprocess: H, W must be in [1, 512]");
     const int Ww = seg_words(W);
     unsigned long long* key = (unsigned long long*)scratch;
     uint32_t* det = (uint32_t*)((char*)scratch + align_up((int64_t)B * 8, 256));
     H3D_CUDA(cudaMemsetAsync(key, 0, (size_t)B * 8, s));
     const int words = H * Ww;
-    dim3 grid(std::min(ceil_div(words, 8), 64), B);
-    seg_prob_kernel<<<grid, 256, 0, s>>>((const float2*)logits, H, W, Ww, key, det);
+    // about one resident wave of 256-thread CTAs (148 SMs x 8), split over the images
+    dim3 grid(std::max(1, std::min(ceil_div(words, 8), ceil_div(148 * 8, B))), B);
+    if (low && !(LH == H && LW == W))
+        seg_prob_kernel<true><<<grid, 256, 0, s>>>((const float2*)low, (float2*)const_cast<float*>(logits), LH, LW, (float)LH / (float)H,
+                                                   (float)LW / (float)W, H, W, Ww, key, det);
+    else
+        seg_prob_kernel<false><<<grid, 256, 0, s>>>((const float2*)(low ? low : logits), nullptr, 0, 0, 0.f, 0.f, H, W, Ww, key, det);
     H3D_CHECK_LAUNCH();
-    const size_t smem = (size_t)5 * words * sizeof(uint32_t);    // det, obj, hor, pre, suf
+    const size_t smem = grow_smem_bytes(H, Ww);    // det, obj, hor (+ zero padding rows)
     static bool attr_set[64] = {};   // per device (one process may drive several GPUs)
     int dev = 0;
     H3D_CUDA(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        H3D_CUDA(cudaFuncSetAttribute(mask_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kMaxMaskWords * 4));
+        H3D_CUDA(cudaFuncSetAttribute(mask_grow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grow_smem_bytes(512, 16)));
         attr_set[dev & 63] = true;
     }
     const int num_passes = std::max(H, W) / (21 / 2);   // utils/general.py:256
@@ -550,38 +588,47 @@ int launch_seg_postprocess(const float* logits, int B, int H, int W, void* scrat
 
 // =============================================================================================
 // crop_image_from_xy (utils/general.py:163-196) = box arithmetic + tf.image.crop_and_resize
-// (bilinear, extrapolation 0).  One thread per output pixel (all C channels, C <= 4).
+// (bilinear, extrapolation 0).
 // =============================================================================================
-__global__ void crop_image_kernel(const float* __restrict__ image, const float* __restrict__ center,
-                                  const float* __restrict__ scale, float* __restrict__ out, int B, int H, int W, int C, int crop) {
-    // blockIdx.y = image; the box arithmetic of utils/general.py:181-191 and of crop_and_resize_op.cc is per image: computed once per CTA
-    __shared__ float s_par[6];   // y1n * (H-1), x1n * (W-1), height scale, width scale, single-row in_y, single-col in_x
+struct CropBox { float oy, ox, hs, ws, cy, cx; };
+// the box arithmetic of utils/general.py:181-191 and of crop_and_resize_op.cc (per image; every thread evaluates it: ~10 flops on three
+// cached scalars cost less than a block barrier at the head of a 20 us kernel)
+__device__ __forceinline__ CropBox crop_box(const float* __restrict__ center, const float* __restrict__ scale, int b, int H, int W, int crop) {
+    const float hm1 = (float)(H - 1), wm1 = (float)(W - 1);
+    const float cs = (float)crop;
+    const float css = __fdiv_rn(cs, __ldg(scale + b));               // :182
+    const float half = floorf(__fdiv_rn(css, 2.0f));                 // float '//' (:183,185)
+    const float y1 = __fsub_rn(__ldg(center + 2 * b), half), y2 = __fadd_rn(y1, css);
+    const float x1 = __fsub_rn(__ldg(center + 2 * b + 1), half), x2 = __fadd_rn(x1, css);
+    const float y1n = __fdiv_rn(y1, (float)H), y2n = __fdiv_rn(y2, (float)H);   // :187-190 (H, W -- not H-1)
+    const float x1n = __fdiv_rn(x1, (float)W), x2n = __fdiv_rn(x2, (float)W);
+    CropBox c;
+    c.oy = __fmul_rn(y1n, hm1);
+    c.ox = __fmul_rn(x1n, wm1);
+    c.hs = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(y2n, y1n), hm1), (float)(crop - 1)) : 0.f;
+    c.ws = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(x2n, x1n), wm1), (float)(crop - 1)) : 0.f;
+    c.cy = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1n, y2n)), hm1);     // single-row / single-column crops sample the box centre
+    c.cx = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1n, x2n)), wm1);
+    return c;
+}
+
+// One thread per output pixel (all C channels, C <= 4); a CTA owns whole output rows of one image (blockIdx.y), so that the 2 input
+// rows a row of the crop touches are shared through L1 by its threads; the loop is unrolled by two for loads in flight.
+__global__ void __launch_bounds__(256)
+crop_image_kernel(const float* __restrict__ image, const float* __restrict__ center, const float* __restrict__ scale,
+                  float* __restrict__ out, int B, int H, int W, int C, int crop) {
     const int b = blockIdx.y;
     const float hm1 = (float)(H - 1), wm1 = (float)(W - 1);
-    if (threadIdx.x == 0) {
-        const float cs = (float)crop;
-        const float css = __fdiv_rn(cs, scale[b]);                       // :182
-        const float half = floorf(__fdiv_rn(css, 2.0f));                 // float '//' (:183,185)
-        const float y1 = __fsub_rn(center[2 * b], half), y2 = __fadd_rn(y1, css);
-        const float x1 = __fsub_rn(center[2 * b + 1], half), x2 = __fadd_rn(x1, css);
-        const float y1n = __fdiv_rn(y1, (float)H), y2n = __fdiv_rn(y2, (float)H);   // :187-190 (H, W -- not H-1)
-        const float x1n = __fdiv_rn(x1, (float)W), x2n = __fdiv_rn(x2, (float)W);
-        s_par[0] = __fmul_rn(y1n, hm1);
-        s_par[1] = __fmul_rn(x1n, wm1);
-        s_par[2] = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(y2n, y1n), hm1), (float)(crop - 1)) : 0.f;
-        s_par[3] = crop > 1 ? __fdiv_rn(__fmul_rn(__fsub_rn(x2n, x1n), wm1), (float)(crop - 1)) : 0.f;
-        s_par[4] = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(y1n, y2n)), hm1);
-        s_par[5] = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(x1n, x2n)), wm1);
-    }
-    __syncthreads();
-    const float oy = s_par[0], ox = s_par[1], hs = s_par[2], ws = s_par[3];
+    const CropBox bx = crop_box(center, scale, b, H, W, crop);
     const float* img = image + (int64_t)b * H * W * C;
     float* ob = out + (int64_t)b * crop * crop * C;
     const int total = crop * crop;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int stride = gridDim.x * blockDim.x;
+#pragma unroll 2
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int y = i / crop, x = i - y * crop;
-        const float in_y = crop > 1 ? __fadd_rn(oy, __fmul_rn((float)y, hs)) : s_par[4];
-        const float in_x = crop > 1 ? __fadd_rn(ox, __fmul_rn((float)x, ws)) : s_par[5];
+        const float in_y = crop > 1 ? __fadd_rn(bx.oy, __fmul_rn((float)y, bx.hs)) : bx.cy;
+        const float in_x = crop > 1 ? __fadd_rn(bx.ox, __fmul_rn((float)x, bx.ws)) : bx.cx;
         float* dst = ob + (int64_t)i * C;
         const bool valid = !(in_y < 0.f || in_y > hm1) && !(in_x < 0.f || in_x > wm1);
         if (!valid) {
@@ -611,8 +658,9 @@ __global__ void crop_image_kernel(const float* __restrict__ image, const float* 
 int launch_crop_image(const float* image, const float* center, const float* scale, float* out, int B, int H, int W, int C,
                       int crop, cudaStream_t s) {
     const int total = crop * crop;
-    dim3 grid((unsigned)std::max(1, std::min(ceil_div(total, 256), 148 * 16 / std::max(1, std::min(B, 16)))), B);
-    crop_image_kernel<<<grid, 256, 0, s>>>(image, center, scale, out, B, H, W, C, crop);
+    // about one resident wave: 148 SMs x 8 CTAs of 256 threads, split over the images (at least 1, at most one CTA per 256 pixels)
+    const int per_image = std::max(1, std::min(ceil_div(total, 256), ceil_div(148 * 8, std::max(1, B))));
+    crop_image_kernel<<<dim3((unsigned)per_image, B), 256, 0, s>>>(image, center, scale, out, B, H, W, C, crop);
     H3D_CHECK_LAUNCH();
     return H3D_OK;
 }

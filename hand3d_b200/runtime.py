@@ -58,13 +58,23 @@ class Context:
             pass
 
     # ---- configuration -------------------------------------------------------------------
+    def _no_live_graphs(self, what):
+        # captured graphs bake in plan-owned device pointers (tile-ticket / completion counters, packed operands): rebuilding the
+        # plans under a live graph would make its replay touch freed memory
+        if getattr(self, "_graphs_captured", 0):
+            raise RuntimeError("%s rebuilds the stage plans, which captured CUDA graphs still point into; drop the graphs and call "
+                               "release_graphs() first" % what)
+
     def set_precision(self, precision):
         p = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        if p != getattr(self, "precision", None):
+            self._no_live_graphs("set_precision()")
         _lib.check(self.lib.h3d_set_precision(self.h, p), "h3d_set_precision")
         self.precision = p
 
     def set_tuning(self, key, value):
         """Kernel-selection switch (process-wide, see include/hand3d_b200.h: h3d_set_tuning); drops this context's plans."""
+        self._no_live_graphs("set_tuning()")
         _lib.check(self.lib.h3d_set_tuning(self.h, key.encode(), int(value)), "h3d_set_tuning(%s)" % key)
 
     @property

@@ -93,11 +93,41 @@ def test_cuda_graph_replay_matches_eager(ctx):
     hs = Wt.synthetic_hand_side(B, seed=33)
     ti, th = torch.from_numpy(imgs[0]).cuda(), torch.from_numpy(hs).cuda()
     replay, res = ctx.capture_pipeline(ti, th, True, outputs="keypoints")
-    for img in imgs[::-1] + imgs:
-        ti.copy_(torch.from_numpy(img))
-        replay()
+    try:
+        for img in imgs[::-1] + imgs:
+            ti.copy_(torch.from_numpy(img))
+            replay()
+            torch.cuda.synchronize()
+            got = {k: v.clone() for k, v in res.items() if v is not None}
+            ref = ctx.pipeline(ti, th, True, outputs="keypoints")
+            for k in ("keypoints_uv", "keypoint_coord3d", "center", "scale_crop"):
+                assert torch.equal(got[k], ref[k]), k
+        with pytest.raises(RuntimeError, match="release_graphs"):     # plans (and what graphs point into) are frozen while a graph lives
+            ctx.set_tuning("tc_chain", 0)
+    finally:
+        del replay
         torch.cuda.synchronize()
-        got = {k: v.clone() for k, v in res.items() if v is not None}
-        ref = ctx.pipeline(ti, th, True, outputs="keypoints")
-        for k in ("keypoints_uv", "keypoint_coord3d", "center", "scale_crop"):
-            assert torch.equal(got[k], ref[k]), k
+        ctx.release_graphs()      # later tests may grow the workspace / switch precision again
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16"])
+def test_layer_chains_change_no_bit(ctx, prec):
+    """Layer chains (dynamic tile tickets + per-image dependencies between consecutive CTA-pair conv launches, conv_tc.cu) only
+    re-order WHEN a tile is computed: chain = 1 (default), 2 (tickets only) and 0 (static round-robin, griddepcontrol.wait) must
+    give bit-identical outputs, repeatedly (B = 32 and a ragged B = 7, back-to-back calls so that consecutive steps overlap too)."""
+    ctx.set_precision(prec)
+    try:
+        for B in (32, 7):
+            img = Wt.synthetic_images(B, 320, 320, seed=41)
+            hs = Wt.synthetic_hand_side(B, seed=42)
+            ctx.set_tuning("tc_chain", 0)
+            base = _run(ctx, img, hs)
+            for mode in (1, 2, 1):
+                ctx.set_tuning("tc_chain", mode)
+                for rep in range(3):
+                    r = _run(ctx, img, hs)
+                    for k in base:
+                        np.testing.assert_array_equal(r[k], base[k], err_msg="%s (chain %d, rep %d, B %d)" % (k, mode, rep, B))
+    finally:
+        ctx.set_tuning("tc_chain", 1)
+        ctx.set_precision("bf16x3")
