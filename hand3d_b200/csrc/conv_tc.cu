@@ -2090,6 +2090,7 @@ TcTuning& tc_tuning() {
         v.fc_chain = geti("H3D_FC_CHAIN", 1);
         v.c64_tma_out = geti("H3D_C64_TMA_OUT", 1);
         v.chain = geti("H3D_TC_CHAIN", 1);
+        v.small_batch_split = geti("H3D_TC_SMALL_SPLIT", 1);
         v.no_seg_fusion = geti("H3D_NO_SEG_FUSION", 0);
         return v;
     }();
@@ -2115,6 +2116,7 @@ int tc_set_tuning(const char* key, int value) {
     else if (k == "fc_chain") t.fc_chain = value;
     else if (k == "c64_tma_out") t.c64_tma_out = value;
     else if (k == "tc_chain") t.chain = value;
+    else if (k == "tc_small_split") t.small_batch_split = value;
     else if (k == "no_seg_fusion") t.no_seg_fusion = value;
     else { set_error("h3d_set_tuning: unknown key '%s'", k.c_str()); return H3D_EINVAL; }
     return H3D_OK;
@@ -2205,16 +2207,34 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad <= 128 && (d.passes == 1 || d.passes == 3) && tune.c64 != 0;
     const bool c64x2 = c64 && d.passes == 3 && tune.c64x2 != 0 && (int64_t)d.H * d.W > 256;
     if (c64) { two = false; BN = 64; }
+    int TW, TH, TB;
+    if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool / stride 2 needs even H and W"); delete pl; return nullptr; }
+    choose_tile(d.B, d.H, d.W, &TW, &TH, &TB, d.pool == 1);
+    if (c64) { TW = C64_TW; TH = C64_TH; TB = 1; }
+    // Few pixel tiles (small batches: run.py's single image, BASELINE config 1): a layer is then as slow as ONE of its work items, and the
+    // CTA pair's 256 x 256 items are the longest there are (72 K blocks x 1536 tensor cycles = 60 us for conv4_x) while most SMs idle.
+    // When the pair kernel would occupy at most half of the machine, the same layer runs as N = 64 (else N = 128) tiles on single CTAs -
+    // 4x (2x) shorter items on 4x (2x) more SMs.  The instruction ORDER per output element is kept (N-stacked iff the pair kernel would
+    // have been N-stacked, same K chunks), so the result is bit-identical to the pair kernel's and still independent of the batch size
+    // (tests/test_gpu_properties.py: a batch of 32 equals its shards of 1 + 1 + 30 bit for bit).
+    bool stack_single = tune.stack != 0;
+    if (two && !c64 && tune.two_cta < 0 && tune.bn == 0 && tune.small_batch_split) {
+        const int tiles = ceil_div(d.W, TW) * ceil_div(d.H, TH) * ceil_div(d.B, TB);
+        const int sms = tc_num_sms();
+        const int pair_items = ceil_div(tiles, 2) * (d.Cout_pad / BN);
+        if (4 * pair_items <= sms) {
+            const bool pair_stacked = stack2(BN, d.passes);
+            int bn1 = 0;
+            if (tiles * (d.Cout_pad / 64) <= sms) bn1 = 64;
+            else if (d.Cout_pad % 128 == 0 && tiles * (d.Cout_pad / 128) <= sms) bn1 = 128;
+            if (bn1) { two = false; BN = bn1; stack_single = pair_stacked; }
+        }
+    }
     pl->BN = BN;
     pl->two_cta = two;
     pl->c64 = c64;
     pl->c64x2 = c64x2;
     pl->device = current_device();
-
-    int TW, TH, TB;
-    if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool / stride 2 needs even H and W"); delete pl; return nullptr; }
-    choose_tile(d.B, d.H, d.W, &TW, &TH, &TB, d.pool == 1);
-    if (c64) { TW = C64_TW; TH = C64_TH; TB = 1; }
     TcParams& p = pl->p;
     p.bias = d.bias;
     p.y_hi = d.y.hi; p.y_lo = d.y.lo; p.y_l8 = d.y.l8; p.y_h8 = d.y.h8; p.Cy_total = d.Cy_total; p.cy_off = d.cy_off;
@@ -2230,7 +2250,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     p.leaky = d.leaky;
     p.n_valid = d.Cout;
     p.pool = d.pool;
-    p.stack = tune.stack != 0;
+    p.stack = stack_single;
     p.exp = tune.exp;
     p.err_flag = d.err_flag;
     // <= ~108 accumulating MMAs per TMEM partial sum (9 K blocks x 4 K steps x 3 passes); BN = 256 keeps everything in
