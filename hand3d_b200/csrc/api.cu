@@ -440,7 +440,7 @@ static int begin_chain_sync(StagePlan* pl, int B) {
 
 static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const LayerSpec& l, int B, int H, int W, Split x,
                   int Cin_total, int Cin_pad, const std::vector<int>& perm, Split y, int Cy_total, int cy_off, float* yf,
-                  int Cyf_total, int cyf_off, int pool = 0, int force_passes = 0, bool chain = false) {
+                  int Cyf_total, int cyf_off, int pool = 0, int force_passes = 0, bool chain = false, const LayerSpec* first = nullptr) {
     const PackedW* pw;
     int rc = get_packed(ctx, scope, l, Cin_pad, perm, &pw, force_passes);
     if (rc) return rc;
@@ -452,6 +452,11 @@ static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const L
     d.corr_scale = pw->corr_scale;
     d.pool = pool;
     d.err_flag = ctx->err_flag;
+    if (first) {   // conv1_1 (fp32 image -> 64 channels) is computed inside this layer's kernel; its input comes from Ext.in at launch
+        if ((rc = dev_weight(ctx, scope + "/" + first->name + "/weights", &d.c1_w))) return rc;
+        if ((rc = dev_weight(ctx, scope + "/" + first->name + "/biases", &d.c1_bias))) return rc;
+        d.c1_leaky = first->leaky;
+    }
     TcConvPlan* tp = tc_conv_plan_create(d);
     if (!tp) return H3D_ECUDA;
     pl->tc.push_back(tp);
@@ -470,9 +475,11 @@ static int add_tc(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, const L
         tc_conv_plan_set_chain(tp, words, dep, target, words + 1);
         pl->chain_prev = tp; pl->chain_prev_step = pl->steps.size(); pl->chain_prev_sig = words + 1;
     }
-    pl->steps.push_back([tp](const Ext&, cudaStream_t s) { return tc_conv_launch(tp, s); });
+    if (first) pl->steps.push_back([tp](const Ext& e, cudaStream_t s) { return tc_conv_launch_image(tp, e.in, s); });
+    else pl->steps.push_back([tp](const Ext&, cudaStream_t s) { return tc_conv_launch(tp, s); });
     pl->launches.push_back(1);
-    const int64_t fl = 2ll * B * H * W * l.k * l.k * l.cin * l.cout / (pool == 2 ? 4 : 1);
+    const int64_t fl = 2ll * B * H * W * l.k * l.k * l.cin * l.cout / (pool == 2 ? 4 : 1) +
+                       (first ? 2ll * B * H * W * first->k * first->k * first->cin * first->cout : 0);
     pl->flops += fl;
     tag(pl, KIND_TC, fl);
     return H3D_OK;
@@ -488,6 +495,7 @@ static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, co
     const Half16 half = half_of(ctx->precision);
     char* slots[2] = {slot0, slot1};
     int cur = 0;
+    const LayerSpec* fused_first = nullptr;
     Act in;   // empty -> external fp32 input
     int h = H, w = W, rc;
     for (int i = 0; i < n; ++i) {
@@ -498,7 +506,17 @@ static int build_trunk(h3d_ctx* ctx, StagePlan* pl, const std::string& scope, co
         const int c_off = last_layer ? final_c_off : 0;
         const bool pool_after = !strcmp(l.name, "conv1_2") || !strcmp(l.name, "conv2_2") || !strcmp(l.name, "conv3_4");
         const bool fuse_pool = use_tc && pool_after && (h % 2 == 0) && (w % 2 == 0) && !tc_tuning().no_pool_fusion;
-        if (use_tc) {
+        // conv1_1 + conv1_2 as one launch (conv_c1f_kernel): layer 0 is skipped here and handed to layer 1
+        if (tc && i == 0 && n > 1 && l.cin == 3 && l.cout == 64 && l.k == 3 && l.stride == 1 &&
+            !strcmp(layers[1].name, "conv1_2") && (h % 2 == 0) && (w % 2 == 0) && !tc_tuning().no_pool_fusion &&
+            tc_conv_can_fuse_first(h, w, layers[1].cin, layers[1].cout, layers[1].k, lo, 1)) {
+            fused_first = &layers[0];
+            continue;
+        }
+        if (use_tc && fused_first) {
+            rc = add_tc(ctx, pl, scope, l, B, h, w, Split(), 64, l.cin, {}, out.s, out.C, c_off, nullptr, 0, 0, fuse_pool ? 1 : 0, 0, true, fused_first);
+            fused_first = nullptr;
+        } else if (use_tc) {
             rc = add_tc(ctx, pl, scope, l, B, h, w, in.s, in.C, l.cin, {}, out.s, out.C, c_off, nullptr, 0, 0, fuse_pool ? 1 : 0, 0, true);
         } else if (tc) {   // first layer (Cin = 3): CUDA-core conv writing the split planes directly
             rc = add_direct(ctx, pl, scope, l, B, h, w, in.f, i == 0 ? l.cin : in.C, 0, nullptr, 0, 0, out.s, out.C, c_off);

@@ -184,6 +184,9 @@ struct TcConvDesc {
     Half16 half;
     int pool = 0;  // 1: fuse the following 2x2/2 max-pool; 2: stride-2 'SAME' convolution (even H, W); outputs are [B, H/2, W/2, C]
     int* err_flag = nullptr;   // device int: a barrier wait that times out stores its code here before trapping (h3d_ctx owns it)
+    // conv1_1 fused into this layer (conv1_2: 64 -> 64, 3x3, pooled, 3-pass): the first layer's device fp32 weights HWIO [3,3,3,64] and
+    // bias [64]; x is then unused and the fp32 image [B,H,W,3] is passed at launch (tc_conv_launch_image)
+    const float* c1_w = nullptr; const float* c1_bias = nullptr; int c1_leaky = 0;
 };
 // Tuning switches: initialised from the environment once (H3D_TC_2CTA, H3D_TC_BN, ...), changed only through tc_set_tuning().
 struct TcTuning {
@@ -196,6 +199,7 @@ struct TcTuning {
     int no_seg_fusion = 0; // 1: HandSegNet's x8 up-sampling as its own launch (instead of fused into the mask post-processing)
     int c64_tma_out = 1;   // 64-channel pair kernel: bulk-tensor-store epilogue for un-pooled layers (conv2_1)
     int fc_chain = 1;      // FC stacks + rotation epilogue of the lifting stage as one kernel (0 = one launch per layer)
+    int fuse_c1 = 1;       // conv1_1 computed inside conv1_2's kernel (conv_c1f_kernel) instead of its own launch
     int small_batch_split = 1;   // few pixel tiles: narrow single-CTA tiles instead of CTA-pair items (same arithmetic, shorter critical path)
     int chain = 1;         // layer chains: dynamic tile tickets + per-image dependencies between consecutive CTA-pair conv launches (2 = tickets only)
     int pdl = 1;           // programmatic dependent launch between the tensor-core kernels (prologue overlaps the previous kernel's tail)
@@ -227,6 +231,8 @@ int tc_conv_plan_signal_target(const TcConvPlan* p);
 const TcConvDesc& tc_conv_plan_desc(const TcConvPlan* p);
 void tc_conv_plan_set_chain(TcConvPlan* p, int* sched, const int* dep_cnt, int dep_target, int* sig_cnt);
 int tc_conv_launch(const TcConvPlan* p, cudaStream_t s);
+int tc_conv_launch_image(const TcConvPlan* p, const float* image, cudaStream_t s);   // plans created with TcConvDesc::c1_w
+bool tc_conv_can_fuse_first(int H, int W, int Cin, int Cout, int k, int passes, int pool);
 int64_t tc_conv_flops(const TcConvPlan* p);
 int tc_num_sms();
 

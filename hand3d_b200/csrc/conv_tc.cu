@@ -67,6 +67,8 @@ struct TcParams {
     const int* dep_cnt;    // per-image completion counters of the layer that produces this layer's input; null = griddepcontrol.wait
     int dep_target;        // arrivals per image that mean "every tile of the image has been stored"
     int* sig_cnt;          // this layer's per-image completion counters (zeroed before the launch); null = no signalling
+    // conv_c1f_kernel (conv1_1 fused into conv1_2): the first layer's fp32 HWIO weights [3,3,3,64], bias [64] and activation
+    const float* w1; const float* bias1; int leaky1;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -1738,6 +1740,345 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------ conv1_1 fused into conv1_2 (CTA pair)
+// conv1_1 (3 -> 64 channels) writes 8 bytes per output value that conv1_2 reads straight back: 1.3 GB written and 1.3 GB read per
+// 32-image step, 0.33 ms of HBM-bound launches (conv_c3_tma_kernel).  This kernel is conv_c64x2_kernel for conv1_2 whose activation
+// patches are not fetched by TMA but COMPUTED in place, by a second (tiny) tensor-core GEMM:
+//   * a pixel tile of conv1_2 (16 x 8) needs conv1_1's output on the 18 x 10 patch around it = 180 patch pixels; they are the rows of
+//     the conv1_1 GEMM (two blocks of 128 rows per CTA), K = 27 -> 32, N = 64;
+//   * four BUILDER warps stage the 20 x 12 x 3 fp32 image patch (the loads of the next tile are in flight while this one is
+//     converted) and write the im2col rows [A_hi 64 B | A_lo 64 B] into ONE 16 KB operand buffer, block after block;
+//   * the MMA warp of the leader interleaves the conv1_1 instructions of tile t + 1 (cta_group::2, M = 256 = this block of both CTAs,
+//     N = 64, three passes into one accumulator: 12 UMMAs per tile) between the kw groups of conv1_2's tile t; their accumulators use
+//     the 2 x 64 TMEM columns the conv1_2 accumulator stages leave free ([192,256) and [448,512));
+//   * the eight epilogue warps run a MID-epilogue per tile: TMEM -> + bias, leaky ReLU, ZERO outside the image (conv1_2's 'SAME' padding
+//     applies to conv1_1's OUTPUT) -> hi / lo split kept in registers -> written into the three kw-shifted patch stages of the
+//     conv_c64 scheme (canonical SWIZZLE_128B rows, generic-proxy stores + fence.proxy.async + mbarrier arrive) as the stages are
+//     released by conv1_2's MMAs of the previous tile; then the usual final epilogue (bias, leaky ReLU, 2 x 2 max-pool, split) of the
+//     previous tile.
+// Barriers (leader's instance counts both CTAs): a1_full 8 builder warps -> MMA, a1_empty commit -> builders, t1_full commit -> mid-
+// epilogue, t1_empty 16 warps -> MMA (values are in registers: the columns may be overwritten), a_full[kw] 16 warps -> MMA, a_empty[kw]
+// commit -> mid-epilogue, tfull / tempty as before.  Stage index = kw, parity = tile iteration.  All waits bounded.
+constexpr int C1F_THREADS = 32 * 14;                       // warps 0-7 epilogue, 8 weight loader, 9 MMA issuer, 10-13 builders
+constexpr int C1F_PPX = C64_TW + 2, C1F_PPY = C64_TH + 2;  // conv1_1 output patch 18 x 10
+constexpr int C1F_PP = C1F_PPX * C1F_PPY;                  // 180 patch pixels = GEMM rows (2 blocks of 128)
+constexpr int C1F_IPX = C1F_PPX + 2, C1F_IPY = C1F_PPY + 2;
+constexpr int C1F_IMG_FLOATS = C1F_IPY * C1F_IPX * 3;      // 720: image patch 12 x 20 x 3
+constexpr int C1F_A1_BYTES = A_TILE_BYTES;                 // 128 rows x [A_hi 64 B | A_lo 64 B]
+constexpr int C1F_W1_BYTES = 64 * BK * 2;                  // 64 rows x 128 B (first 64 B used): W_hi[32 r ..) rows 0-31, W_lo rows 32-63
+constexpr int C1F_SMEM = C64X2_W_BYTES + C64X2_STAGES * C64X2_A_STAGE_BYTES + C1F_A1_BYTES + C1F_W1_BYTES + 2 * C1F_IMG_FLOATS * 4 +
+                         1024 /*align slack*/ + 256 /*barriers*/;
+static_assert(C1F_SMEM <= 227 * 1024, "conv_c1f_kernel: shared memory budget");
+
+template <bool FP16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C1F_THREADS, 1)
+conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                const TcParams p) {
+    constexpr uint32_t IDESC_MAIN = make_idesc(128, FP16, 256);
+    constexpr uint32_t IDESC_N64 = make_idesc(64, FP16, 256);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* wsm = smem;                                              // conv1_2 weights, resident (as conv_c64x2_kernel)
+    uint8_t* asm_ = smem + C64X2_W_BYTES;                             // three kw patch stages [hi 20 KB | lo 20 KB]
+    uint8_t* a1sm = asm_ + C64X2_STAGES * C64X2_A_STAGE_BYTES;        // conv1_1 A operand, one 128-row block
+    uint8_t* w1sm = a1sm + C1F_A1_BYTES;                              // conv1_1 B operand halves of this CTA
+    float* imgsm = reinterpret_cast<float*>(w1sm + C1F_W1_BYTES);     // [2][720] image patch
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(imgsm + 2 * C1F_IMG_FLOATS);
+    uint64_t* a_empty = a_full + 3;
+    uint64_t* tfull_bar = a_empty + 3;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* w_full = tempty_bar + 2;
+    uint64_t* a1_full = w_full + 1;
+    uint64_t* a1_empty = a1_full + 1;
+    uint64_t* t1_full = a1_empty + 1;
+    uint64_t* t1_empty = t1_full + 1;
+    uint64_t* w1_full = t1_empty + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w1_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 8 && lane == 0) {
+        prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
+        for (int s = 0; s < 3; ++s) { mbar_init(&a_full[s], 16); mbar_init(&a_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
+        mbar_init(w_full, 1);
+        mbar_init(a1_full, 8); mbar_init(a1_empty, 1); mbar_init(t1_full, 1); mbar_init(t1_empty, 16); mbar_init(w1_full, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * C64X2_ACC_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    if (warp != 8) pdl_wait();   // the loader warp waits after it has issued the (static) weight loads
+
+    if (warp == 8) {
+        // ================================ conv1_2 weights: resident, loaded once ================================
+        if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(w_full, 2 * C64X2_W_BYTES);
+            for (int t = 0; t < 9; ++t) {
+                tma_load_2d_2sm(&map_w_hi, wsm + t * C64X2_W_TAP_BYTES, w_full, t * BK, (int)rank * 32);
+                tma_load_2d_2sm(&map_w_lo, wsm + t * C64X2_W_TAP_BYTES + 32 * BK * 2, w_full, t * BK, (int)rank * 32);
+            }
+        }
+        __syncwarp();
+        pdl_wait();
+    } else if (warp >= 10) {
+        // ================================ builders: conv1_1 weights once, then the im2col rows of every tile ================================
+        const int t = threadIdx.x - 320;                   // 0 .. 127
+        if (t < 64) {                                      // row t: plane t >> 5 (0 hi, 1 lo) of output channel 32 rank + (t & 31)
+            const int co = 32 * (int)rank + (t & 31);
+            uint32_t pk[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                float v0 = 0.f, v1 = 0.f;
+                if (2 * k2 < 27) v0 = __ldg(p.w1 + (2 * k2) * 64 + co);
+                if (2 * k2 + 1 < 27) v1 = __ldg(p.w1 + (2 * k2 + 1) * 64 + co);
+                const uint32_t h = pack_hi2<FP16>(v0, v1);
+                if (t < 32) pk[k2] = h;
+                else { const float2 r = unpack2<FP16>(h); pk[k2] = pack_hi2<FP16>(v0 - r.x, v1 - r.y); }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(w1sm + sw128_chunk(t, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(w1_full, 0);
+        constexpr int PRE = (C1F_IMG_FLOATS + 127) / 128;  // 6
+        float pre[PRE];
+        auto load_img = [&](int item) {
+            const int mt = 2 * item + (int)rank;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
+            const int x0 = tw * C64_TW - 2, y0 = th * C64_TH - 2;
+            const float* xb = x + (int64_t)b * p.H * p.W * 3;
+#pragma unroll
+            for (int j = 0; j < PRE; ++j) {
+                const int i = t + j * 128;
+                const int r = i / (C1F_IPX * 3), rem = i - r * (C1F_IPX * 3);
+                const int gy = y0 + r, gx = x0 + rem / 3;
+                float v = 0.f;
+                if (i < C1F_IMG_FLOATS && b < p.B && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) v = __ldg(xb + ((int64_t)gy * p.W + x0) * 3 + rem);
+                pre[j] = v;
+            }
+        };
+        int fills = 0, it = 0;
+        if (cluster_id < p.num_tiles) load_img(cluster_id);
+        for (int item = cluster_id; item < p.num_tiles; item += num_clusters, ++it) {
+            float* pb = imgsm + (it & 1) * C1F_IMG_FLOATS;
+#pragma unroll
+            for (int j = 0; j < PRE; ++j)
+                if (t + j * 128 < C1F_IMG_FLOATS) pb[t + j * 128] = pre[j];
+            named_bar_sync(1, 128);
+            if (item + num_clusters < p.num_tiles) load_img(item + num_clusters);
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk, ++fills) {
+                const int pp = blk * 128 + t;              // patch pixel of this row
+                const int py = pp / C1F_PPX, px = pp - py * C1F_PPX;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    float v0 = 0.f, v1 = 0.f;
+                    if (pp < C1F_PP) {
+                        if (2 * k2 < 27) { const int k = 2 * k2; v0 = pb[(py + k / 9) * (C1F_IPX * 3) + px * 3 + (k % 9)]; }
+                        if (2 * k2 + 1 < 27) { const int k = 2 * k2 + 1; v1 = pb[(py + k / 9) * (C1F_IPX * 3) + px * 3 + (k % 9)]; }
+                    }
+                    hi[k2] = pack_hi2<FP16>(v0, v1);
+                    const float2 r = unpack2<FP16>(hi[k2]);
+                    lo[k2] = pack_hi2<FP16>(v0 - r.x, v1 - r.y);
+                }
+                mbar_wait(a1_empty, ((uint32_t)fills & 1u) ^ 1u, p.err_flag, 11);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    *reinterpret_cast<uint4*>(a1sm + sw128_chunk(t, c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(a1sm + sw128_chunk(t, 4 + c)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(a1_full, 0);
+            }
+        }
+    } else if (warp == 9) {
+        // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ================================
+        if (rank == 0) {
+            mbar_wait(w_full, 0, p.err_flag, 5);
+            mbar_wait_cl(w1_full, 0, p.err_flag, 12);
+            tc_fence_after();
+            const uint32_t wb = smem_u32(wsm);
+            const uint64_t a1_hi = make_smem_desc(smem_u32(a1sm));
+            const uint64_t a1_lo = a1_hi + (uint64_t)(64 >> 4);                     // bytes [64,128) of every row
+            const uint64_t b1_hi = make_smem_desc(smem_u32(w1sm));
+            const uint64_t b1_lo = make_smem_desc(smem_u32(w1sm) + 32 * 128);       // rows 32-63
+            int fills = 0;
+            // conv1_1 of block blk of the NEXT tile: 6 UMMAs (2 K steps x hi*hi, hi*lo, lo*hi) into columns [blk * 256 + 192, + 64)
+            auto conv1_block = [&](int blk, bool last) {
+                mbar_wait_cl(a1_full, (uint32_t)fills & 1u, p.err_flag, 13);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d = tmem_base + (uint32_t)(blk * C64X2_ACC_COLS + 192);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                        tc_mma_f16_2cta(d, a1_hi + koff, b1_hi + koff, IDESC_N64, (uint32_t)(j != 0));
+                        tc_mma_f16_2cta(d, a1_hi + koff, b1_lo + koff, IDESC_N64, 1u);
+                        tc_mma_f16_2cta(d, a1_lo + koff, b1_hi + koff, IDESC_N64, 1u);
+                    }
+                    tc_commit_2cta(a1_empty);
+                    if (last) tc_commit_2cta(t1_full);
+                }
+                __syncwarp();
+                ++fills;
+            };
+            int it = 0;
+            if (cluster_id < p.num_tiles) { conv1_block(0, false); conv1_block(1, true); }
+            for (int item = cluster_id; item < p.num_tiles; item += num_clusters, ++it) {
+                const int acc = it & 1;
+                const bool more = item + num_clusters < p.num_tiles;
+                mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1, p.err_flag, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C64X2_ACC_COLS);
+                for (int kw = 0; kw < 3; ++kw) {
+                    mbar_wait_cl(&a_full[kw], (uint32_t)it & 1u, p.err_flag, 3);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = smem_u32(asm_ + kw * C64X2_A_STAGE_BYTES);
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint64_t a_hi = make_smem_desc(sa + kh * C64_ROW_BYTES);
+                            const uint64_t a_lo = make_smem_desc(sa + C64_PATCH_BYTES + kh * C64_ROW_BYTES);
+                            const uint64_t b = make_smem_desc(wb + (kh * 3 + kw) * C64X2_W_TAP_BYTES);
+#pragma unroll
+                            for (int j = 0; j < BK / UMMA_K; ++j) {
+                                const uint64_t koff = (uint64_t)((j * UMMA_K * 2) >> 4);
+                                const uint32_t accum = (uint32_t)((kw | kh | j) != 0);
+                                tc_mma_f16_2cta(d_tmem, a_hi + koff, b + koff, IDESC_MAIN, accum);
+                                tc_mma_f16_2cta(d_tmem + 128, a_lo + koff, b + koff, IDESC_N64, accum);
+                            }
+                        }
+                        tc_commit_2cta(&a_empty[kw]);
+                        if (kw == 2) tc_commit_2cta(&tfull_bar[acc]);
+                    }
+                    __syncwarp();
+                    if (more && kw < 2) {
+                        // the mid-epilogue of THIS tile has read the conv1_1 accumulators (its patches are complete, else a_full[kw] above
+                        // could not have completed); t1_empty makes that explicit for the tensor-memory proxy
+                        if (kw == 0) { mbar_wait_cl(t1_empty, (uint32_t)it & 1u, p.err_flag, 14); tc_fence_after(); }
+                        conv1_block(kw, kw == 1);
+                    }
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue warps: mid-epilogue of tile it, then final epilogue of tile it - 1 ================================
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        const int w_l = row % C64_TW, h_l = row / C64_TW;
+        const float2* bias1 = reinterpret_cast<const float2*>(p.bias1 + 32 * ch);
+        auto final_epilogue = [&](int item, int fit) {
+            const int mt = 2 * item + (int)rank;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
+            const int w = tw * C64_TW + w_l, h = th * C64_TH + h_l;
+            bool valid = (w < p.W) && (h < p.H) && (b < p.B);
+            int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
+            if (p.pool) {
+                const int par = p.pool == 2 ? 1 : 0;
+                valid = valid && ((w & 1) == par) && ((h & 1) == par);
+                pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+            }
+            const int acc = fit & 1;
+            mbar_wait(&tfull_bar[acc], (fit >> 1) & 1, p.err_flag, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C64X2_ACC_COLS);
+            uint32_t v0[32], v1[32], v2[32];
+            tc_ld_32x32b_x32(taddr + 64 * ch, v0);          // hi*hi
+            tc_ld_32x32b_x32(taddr + 64 * ch + 32, v1);     // hi*lo
+            tc_ld_32x32b_x32(taddr + 128 + 32 * ch, v2);    // lo*hi
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+            float racc[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) racc[i] = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + __uint_as_float(v2[i]);
+            epilogue_store32<3, FP16>(p, racc, pix, 32 * ch, valid);
+        };
+        int it = 0, prev_item = -1;
+        for (int item = cluster_id; item < p.num_tiles; item += num_clusters, ++it) {
+            // ---- mid-epilogue: conv1_1 accumulators of this tile -> the three kw patch stages
+            const int mt = 2 * item + (int)rank;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
+            mbar_wait(t1_full, (uint32_t)it & 1u, p.err_flag, 15);
+            tc_fence_after();
+            uint32_t hi[2][16], lo[2][16];
+            int ppy[2], ppx[2]; bool in_patch[2];
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+                const int pp = blk * 128 + row;
+                ppy[blk] = pp / C1F_PPX; ppx[blk] = pp - ppy[blk] * C1F_PPX;
+                in_patch[blk] = pp < C1F_PP;
+                const int gy = th * C64_TH - 1 + ppy[blk], gx = tw * C64_TW - 1 + ppx[blk];
+                const bool inside = in_patch[blk] && b < p.B && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+                uint32_t v[32];
+                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * C64X2_ACC_COLS + 192 + 32 * ch), v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float2 bv = __ldg(bias1 + i);
+                    float f0 = __uint_as_float(v[2 * i]) + bv.x, f1 = __uint_as_float(v[2 * i + 1]) + bv.y;
+                    if (p.leaky1) { f0 = fmaxf(f0, kNegSlope * f0); f1 = fmaxf(f1, kNegSlope * f1); }
+                    if (!inside) { f0 = 0.f; f1 = 0.f; }   // conv1_2's zero padding / pixels of no image
+                    hi[blk][i] = pack_hi2<FP16>(f0, f1);
+                    const float2 r = unpack2<FP16>(hi[blk][i]);
+                    lo[blk][i] = pack_hi2<FP16>(f0 - r.x, f1 - r.y);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(t1_empty, 0);
+#pragma unroll 1
+            for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&a_empty[kw], ((uint32_t)it & 1u) ^ 1u, p.err_flag, 1);
+                uint8_t* st = asm_ + kw * C64X2_A_STAGE_BYTES;
+#pragma unroll
+                for (int blk = 0; blk < 2; ++blk) {
+                    const int j = ppx[blk] - kw;
+                    if (in_patch[blk] && j >= 0 && j < C64_TW) {
+                        const int r = ppy[blk] * C64_TW + j;       // row of the {64 ch, 16 px, 10 rows} patch
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            *reinterpret_cast<uint4*>(st + sw128_chunk(r, 4 * ch + c)) =
+                                make_uint4(hi[blk][4 * c], hi[blk][4 * c + 1], hi[blk][4 * c + 2], hi[blk][4 * c + 3]);
+                            *reinterpret_cast<uint4*>(st + C64_PATCH_BYTES + sw128_chunk(r, 4 * ch + c)) =
+                                make_uint4(lo[blk][4 * c], lo[blk][4 * c + 1], lo[blk][4 * c + 2], lo[blk][4 * c + 3]);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&a_full[kw], 0);
+            }
+            // ---- final epilogue of the previous tile (its MMAs completed before stage 2 was released)
+            if (prev_item >= 0) final_epilogue(prev_item, it - 1);
+            prev_item = item;
+        }
+        if (prev_item >= 0) final_epilogue(prev_item, it - 1);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * C64X2_ACC_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------ FC stacks as ONE kernel
 // PosePrior (2050 -> 512 -> 512 -> 63, optional 30-wide bottleneck) and ViewpointNet (4098 -> 256 -> 128 -> 3) fully connected stacks
 // (nets/ColorHandPose3DNetwork.py:262-267,297-308; nets/PosePriorNetwork.py:113-116) followed by Rodrigues / flip / rotate
@@ -2021,6 +2362,7 @@ struct TcConvPlan {
     bool two_cta = false;
     bool c64 = false;      // 64 -> 64 channel 3x3 specialisation (conv_c64_kernel)
     bool c64x2 = false;    // ... on a CTA pair (conv_c64x2_kernel)
+    bool c1f = false;      // ... with conv1_1 fused in (conv_c1f_kernel; implies c64x2 geometry)
     int device = 0;
 
     TcConvDesc d;
@@ -2091,6 +2433,7 @@ TcTuning& tc_tuning() {
         v.c64_tma_out = geti("H3D_C64_TMA_OUT", 1);
         v.chain = geti("H3D_TC_CHAIN", 1);
         v.small_batch_split = geti("H3D_TC_SMALL_SPLIT", 1);
+        v.fuse_c1 = geti("H3D_FUSE_C1", 1);
         v.no_seg_fusion = geti("H3D_NO_SEG_FUSION", 0);
         return v;
     }();
@@ -2117,6 +2460,7 @@ int tc_set_tuning(const char* key, int value) {
     else if (k == "c64_tma_out") t.c64_tma_out = value;
     else if (k == "tc_chain") t.chain = value;
     else if (k == "tc_small_split") t.small_batch_split = value;
+    else if (k == "fuse_c1") t.fuse_c1 = value;
     else if (k == "no_seg_fusion") t.no_seg_fusion = value;
     else { set_error("h3d_set_tuning: unknown key '%s'", k.c_str()); return H3D_EINVAL; }
     return H3D_OK;
@@ -2142,6 +2486,13 @@ int launch_c64(const TcConvPlan* pl, cudaStream_t s) {
     if (int rc = smem_opt_in(conv_c64_kernel<PASSES, FP16>, smem, attr)) return rc;
     H3D_CUDA(launch_pdl(conv_c64_kernel<PASSES, FP16>, dim3(pl->grid), dim3(kThreads), smem, s, pl->map_x_hi, pl->map_x_lo, pl->map_w_hi, pl->map_w_lo,
                         pl->p));
+    return H3D_OK;
+}
+template <bool FP16>
+int launch_c1f(const TcConvPlan* pl, const float* image, cudaStream_t s) {
+    static bool attr[kMaxDevices] = {};
+    if (int rc = smem_opt_in(conv_c1f_kernel<FP16>, C1F_SMEM, attr)) return rc;
+    H3D_CUDA(launch_pdl(conv_c1f_kernel<FP16>, dim3(pl->grid), dim3(C1F_THREADS), (size_t)C1F_SMEM, s, image, pl->map_w_hi, pl->map_w_lo, pl->p));
     return H3D_OK;
 }
 template <bool FP16>
@@ -2206,6 +2557,11 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     // pair in the 3-pass modes when the map is large enough to fill the machine with tile pairs
     bool c64 = d.k == 3 && d.Cin_pad == 64 && d.Cout_pad <= 128 && (d.passes == 1 || d.passes == 3) && tune.c64 != 0;
     const bool c64x2 = c64 && d.passes == 3 && tune.c64x2 != 0 && (int64_t)d.H * d.W > 256;
+    const bool c1f = d.c1_w != nullptr;
+    if (c1f && !(c64x2 && tc_conv_can_fuse_first(d.H, d.W, d.Cin_pad, d.Cout_pad, d.k, d.passes, d.pool) && d.c1_bias && d.y.hi && d.y.lo && !d.yf)) {
+        set_error("tc_conv: conv1_1 can only be fused into a pooled 64 -> 64 channel 3x3 layer of a 3-pass mode on a map larger than 16x16");
+        delete pl; return nullptr;
+    }
     if (c64) { two = false; BN = 64; }
     int TW, TH, TB;
     if (d.pool && ((d.H | d.W) & 1)) { set_error("tc_conv: fused max-pool / stride 2 needs even H and W"); delete pl; return nullptr; }
@@ -2234,6 +2590,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     pl->two_cta = two;
     pl->c64 = c64;
     pl->c64x2 = c64x2;
+    pl->c1f = c1f;
     pl->device = current_device();
     TcParams& p = pl->p;
     p.bias = d.bias;
@@ -2253,6 +2610,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     p.stack = stack_single;
     p.exp = tune.exp;
     p.err_flag = d.err_flag;
+    p.w1 = d.c1_w; p.bias1 = d.c1_bias; p.leaky1 = d.c1_leaky;
     // <= ~108 accumulating MMAs per TMEM partial sum (9 K blocks x 4 K steps x 3 passes); BN = 256 keeps everything in
     // TMEM (its 256 fp32 partial sums per thread would not fit the register file)
     p.chunk_kb = d.passes >= 3 ? 9 : 27;
@@ -2271,11 +2629,17 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     const int w_box_rows = c64x2 ? 32 : stacked_pair ? BN : two ? BN / 2 : BN;
     const int Ktot = d.k * d.k * d.Cin_pad;
     const int box_h = c64 ? C64_PH : TH;   // the 64 -> 64 kernel fetches the tile rows plus the halo rows in one box
-    bool ok = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, box_h, TB) &&
-              encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, w_box_rows);
-    if (ok && d.passes == 3)
-        ok = encode_act_map(&pl->map_x_lo, d.x.lo, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, box_h, TB) &&
-             encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, w_box_rows);
+    bool ok;
+    if (c1f) {   // the activation patches are computed in the kernel: weight maps only
+        ok = encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, w_box_rows) && encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, w_box_rows);
+        pl->map_x_hi = pl->map_w_hi; pl->map_x_lo = pl->map_w_lo;
+    } else {
+        ok = encode_act_map(&pl->map_x_hi, d.x.hi, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, box_h, TB) &&
+             encode_w_map(&pl->map_w_hi, d.w.hi, Ktot, d.Cout_pad, w_box_rows);
+        if (ok && d.passes == 3)
+            ok = encode_act_map(&pl->map_x_lo, d.x.lo, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, box_h, TB) &&
+                 encode_w_map(&pl->map_w_lo, d.w.lo, Ktot, d.Cout_pad, w_box_rows);
+    }
     if (ok && d.passes == 4)   // e4m3 planes: x residual (slot "lo"), x coarse, w coarse (slot "lo"), w residual
         ok = encode_act_map(&pl->map_x_lo, d.x.l8, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB, 1) &&
              encode_act_map(&pl->map_x_h8, d.x.h8, d.Cin_total, d.Cin_pad, d.W, d.H, d.B, TW, TH, TB, 1) &&
@@ -2310,8 +2674,20 @@ int64_t tc_conv_flops(const TcConvPlan* p) {
     return 2ll * p->d.B * p->d.H * p->d.W * p->d.k * p->d.k * (int64_t)p->d.Cin_pad * p->d.Cout_pad;
 }
 
+bool tc_conv_can_fuse_first(int H, int W, int Cin, int Cout, int k, int passes, int pool) {
+    const TcTuning& t = tc_tuning();
+    return t.fuse_c1 && t.c64 && t.c64x2 && t.two_cta < 0 && t.bn == 0 && k == 3 && Cin == 64 && Cout == 64 && passes == 3 && pool == 1 &&
+           (int64_t)H * W > 256 && (H % 2) == 0 && (W % 2) == 0;
+}
+
+int tc_conv_launch_image(const TcConvPlan* pl, const float* image, cudaStream_t s) {
+    H3D_REQUIRE(pl->c1f && image, "tc_conv_launch_image: the plan has no fused first layer");
+    return pl->d.half == Half16::FP16 ? launch_c1f<true>(pl, image, s) : launch_c1f<false>(pl, image, s);
+}
+
 int tc_conv_launch(const TcConvPlan* pl, cudaStream_t s) {
     const bool fp16 = pl->d.half == Half16::FP16;
+    H3D_REQUIRE(!pl->c1f, "tc_conv_launch: the plan fuses the first layer, launch it with the image (tc_conv_launch_image)");
     const int key = pl->BN * 10 + pl->d.passes;
     if (pl->c64x2) return fp16 ? launch_c64x2<true>(pl, s) : launch_c64x2<false>(pl, s);
     if (pl->c64) {

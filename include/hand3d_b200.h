@@ -73,11 +73,15 @@ H3D_API int h3d_get_precision(const h3d_ctx* ctx);
 /* Kernel-selection switches for A/B measurements and forced-variant tests (process-wide; initialised ONCE from the H3D_*
  * environment variables when the library is first used, never read on a launch path).  Keys: "tc_2cta" (-1 policy / 0 / 1),
  * "tc_bn" (0 policy / 64 / 128 / 256), "tc_c64", "tc_c64x2", "tc_pair128", "tc_stack", "tc_chunk_kb", "no_side_stream",
- * "no_pool_fusion", "lift_direct", "c3_ffma".  ctx may be NULL; when given, its cached layer plans are dropped. */
+ * "no_pool_fusion", "lift_direct", "c3_ffma", "c3_tma", "pdl", "fc_chain", "c64_tma_out", "tc_chain" (layer chains: 0 off / 1 tile
+ * tickets + per-image dependencies / 2 tickets only), "tc_small_split" (narrow tiles for small batches), "fuse_c1" (conv1_1 inside
+ * conv1_2's kernel), "no_seg_fusion".  ctx may be NULL; when given, its cached layer plans are dropped (never while a CUDA graph
+ * captured from this context is alive: graphs hold plan-owned pointers). */
 H3D_API int h3d_set_tuning(h3d_ctx* ctx, const char* key, int value);
 /* Device-side error word (pinned host memory, survives a trapped kernel): 0 = none; 1-5 = a bounded mbarrier wait of a tcgen05
  * convolution kernel timed out (1 TMA producer / free stage, 2 MMA issuer / drained accumulator, 3 MMA issuer / TMA stage,
- * 4 epilogue / finished accumulator, 5 MMA issuer / resident weights) and the kernel trapped; 100 + r = h3d_gather_records_p2p
+ * 4 epilogue / finished accumulator, 5 MMA issuer / resident weights or tile-ticket ring, 6 ticket ring consumer, 7 per-image
+ * dependency of a chained layer, 11-15 fused first-layer pipeline) and the kernel trapped; 100 + r = h3d_gather_records_p2p
  * never saw peer rank r's records.  Returns H3D_OK or H3D_ECUDA (message in h3d_last_error); *code (optional) = the word. */
 H3D_API int h3d_check_errors(h3d_ctx* ctx, int* code);
 /* Number of kernels this library launched through `ctx` since creation (bench "gpu_launches"). */

@@ -55,17 +55,35 @@ def test_handsegnet_stage(net, ctx, seg_ref, prec):
     assert err < TOL[prec], "HandSegNet %s: max abs err %.3e" % (prec, err)
 
 
-@pytest.mark.parametrize("switch", ["c3_tma", "c3_ffma"])
-def test_first_layer_kernel_variants(net, ctx, seg_ref, switch):
-    """conv1_1 has three kernels: tensor cores with bulk-tensor-store epilogue (default), tensor cores with direct global stores
-    (c3_tma = 0) and the register-tiled FFMA kernel (c3_ffma = 1); all must give the HandSegNet parity."""
+@pytest.mark.parametrize("knobs", [{"fuse_c1": 0}, {"fuse_c1": 0, "c3_tma": 0}, {"fuse_c1": 0, "c3_ffma": 1}], ids=["c3_tma", "c3_tc", "c3_ffma"])
+def test_first_layer_kernel_variants(net, ctx, seg_ref, knobs):
+    """conv1_1 has four implementations: fused into conv1_2's kernel (default, covered by every other test), and as its own launch on
+    tensor cores with bulk-tensor-store epilogue (fuse_c1 = 0), with direct global stores (c3_tma = 0) or as the register-tiled FFMA
+    kernel (c3_ffma = 1); all must give the HandSegNet parity."""
     img, ref = seg_ref
     ctx.set_precision("bf16x3")
-    ctx.set_tuning(switch, 0 if switch == "c3_tma" else 1)
+    default = {"fuse_c1": 1, "c3_tma": 1, "c3_ffma": 0}
+    for k, v in knobs.items():
+        ctx.set_tuning(k, v)
     try:
         out = net.inference_detection(_dev(img))[0].cpu().numpy()
     finally:
-        ctx.set_tuning(switch, 1 if switch == "c3_tma" else 0)
+        for k in knobs:
+            ctx.set_tuning(k, default[k])
+    assert np.abs(out - ref).max() < 1e-3
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+@pytest.mark.parametrize("shape", [(3, 40, 40), (1, 24, 56), (2, 72, 48)])
+def test_handsegnet_small_odd_maps(net, ctx, wd, shape, prec):
+    """Maps that are no multiple of the 16 x 8 pixel tile, odd numbers of tiles (the CTA pair's second tile falls outside the batch) and
+    tiles that lie entirely in conv1_2's zero padding: exercises the fused conv1_1 + conv1_2 kernel's masking."""
+    B, H, W = shape
+    img = Wt.synthetic_images(B, H, W, seed=17)
+    ctx.set_precision(prec)
+    out = net.inference_detection(_dev(img))[0].cpu().numpy()
+    ref = O.inference_detection(img, wd)[-1]
+    assert out.shape == (B, H, W, 2)
     assert np.abs(out - ref).max() < 1e-3
 
 
