@@ -83,13 +83,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Suspend-time hint of mbarrier.try_wait: a waiting thread sleeps in hardware (it wakes as soon as the phase completes) instead of
+// re-issuing the poll + time-out check every ~20 cycles; ncu r02g: 43 % of the instructions a warp-specialised kernel issued were polls.
+constexpr uint32_t kTryWaitHintNs = 20000u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(kTryWaitHintNs) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
@@ -224,8 +227,20 @@ __device__ __forceinline__ void tc_commit_2cta(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
+// arrive on the barrier at the same offset in CTA `rank` of the cluster.  Default semantics (release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive(cta_id): what these arrivals publish is either nothing in memory (a drained TMEM accumulator, a consumed ring
+// slot) or this CTA's OWN shared memory, already made visible to the async proxy by fence.proxy.async, which the tensor core reads on
+// behalf of the leader's UMMA.  A `.release.cluster` arrive compiles to MEMBAR.ALL.GPU, which waits for every outstanding global store
+// of the thread - the previous tile's output on its way to HBM - and was the top stall of the epilogue warps (ncu r02g: stall_membar).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// ... with release at CLUSTER scope: the arrival publishes data this thread stored into the PEER's shared memory (tile-ticket ring)
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
@@ -245,9 +260,9 @@ __device__ __forceinline__ bool mbar_try_wait_cl(uint64_t* bar, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(kTryWaitHintNs) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
@@ -1338,7 +1353,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
                     sched_tile[slot] = v;
                     st_shared_cluster_u32(&sched_tile[slot], 1, (uint32_t)v);
                     mbar_arrive(&sfull_bar[slot]);
-                    mbar_arrive_cluster(&sfull_bar[slot], 1);
+                    mbar_arrive_cluster_release(&sfull_bar[slot], 1);
                 }
                 item = __shfl_sync(0xFFFFFFFFu, v, 0);
             } else {
@@ -1397,7 +1412,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
             int acc_it = 0;
             for (int seq = 0;; ++seq) {
                 const int slot = seq & (kSchedSlots - 1);
-                mbar_wait_cl(&sfull_bar[slot], (uint32_t)(seq / kSchedSlots) & 1u, p.err_flag, 6);
+                mbar_wait(&sfull_bar[slot], (uint32_t)(seq / kSchedSlots) & 1u, p.err_flag, 6);   // written by this CTA's producer
                 int item = sched_tile[slot];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sempty_bar[slot]);
@@ -1461,7 +1476,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_const
         bool may_store = p.dep_cnt == nullptr;               // chained layers: griddepcontrol.wait before the first store (WAR on the slots)
         for (int seq = 0;; ++seq) {
             const int slot = seq & (kSchedSlots - 1);
-            mbar_wait_cl(&sfull_bar[slot], (uint32_t)(seq / kSchedSlots) & 1u, p.err_flag, 6);
+            // the peer's copy of the ticket was stored through DSMEM by the leader: acquire at cluster scope there (it invalidates L1)
+            if (rank == 0) mbar_wait(&sfull_bar[slot], (uint32_t)(seq / kSchedSlots) & 1u, p.err_flag, 6);
+            else mbar_wait_cl(&sfull_bar[slot], (uint32_t)(seq / kSchedSlots) & 1u, p.err_flag, 6);
             const int item = sched_tile[slot];
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&sempty_bar[slot], 0);
@@ -1746,6 +1763,8 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
 // patches are not fetched by TMA but COMPUTED in place, by a second (tiny) tensor-core GEMM:
 //   * a pixel tile of conv1_2 (16 x 8) needs conv1_1's output on the 18 x 10 patch around it = 180 patch pixels; they are the rows of
 //     the conv1_1 GEMM (two blocks of 128 rows per CTA), K = 27 -> 32, N = 64;
+//   * the bias of conv1_1 is K index 27 of the GEMM (a constant-1 column of A times a bias row of W, both hi / lo split), so the
+//     mid-epilogue has no bias loads or adds;
 //   * four BUILDER warps stage the 20 x 12 x 3 fp32 image patch (the loads of the next tile are in flight while this one is
 //     converted) and write the im2col rows [A_hi 64 B | A_lo 64 B] into ONE 16 KB operand buffer, block after block;
 //   * the MMA warp of the leader interleaves the conv1_1 instructions of tile t + 1 (cta_group::2, M = 256 = this block of both CTAs,
@@ -1841,6 +1860,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                 float v0 = 0.f, v1 = 0.f;
                 if (2 * k2 < 27) v0 = __ldg(p.w1 + (2 * k2) * 64 + co);
                 if (2 * k2 + 1 < 27) v1 = __ldg(p.w1 + (2 * k2 + 1) * 64 + co);
+                if (2 * k2 + 1 == 27) v1 = __ldg(p.bias1 + co);      // K index 27: the bias, multiplied by the constant-1 column of A
                 const uint32_t h = pack_hi2<FP16>(v0, v1);
                 if (t < 32) pk[k2] = h;
                 else { const float2 r = unpack2<FP16>(h); pk[k2] = pack_hi2<FP16>(v0 - r.x, v1 - r.y); }
@@ -1889,6 +1909,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                     if (pp < C1F_PP) {
                         if (2 * k2 < 27) { const int k = 2 * k2; v0 = pb[(py + k / 9) * (C1F_IPX * 3) + px * 3 + (k % 9)]; }
                         if (2 * k2 + 1 < 27) { const int k = 2 * k2 + 1; v1 = pb[(py + k / 9) * (C1F_IPX * 3) + px * 3 + (k % 9)]; }
+                        if (2 * k2 + 1 == 27) v1 = 1.0f;             // constant-1 column: the bias comes out of the GEMM
                     }
                     hi[k2] = pack_hi2<FP16>(v0, v1);
                     const float2 r = unpack2<FP16>(hi[k2]);
@@ -1909,7 +1930,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
         // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ================================
         if (rank == 0) {
             mbar_wait(w_full, 0, p.err_flag, 5);
-            mbar_wait_cl(w1_full, 0, p.err_flag, 12);
+            mbar_wait(w1_full, 0, p.err_flag, 12);
             tc_fence_after();
             const uint32_t wb = smem_u32(wsm);
             const uint64_t a1_hi = make_smem_desc(smem_u32(a1sm));
@@ -1919,7 +1940,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
             int fills = 0;
             // conv1_1 of block blk of the NEXT tile: 6 UMMAs (2 K steps x hi*hi, hi*lo, lo*hi) into columns [blk * 256 + 192, + 64)
             auto conv1_block = [&](int blk, bool last) {
-                mbar_wait_cl(a1_full, (uint32_t)fills & 1u, p.err_flag, 13);
+                mbar_wait(a1_full, (uint32_t)fills & 1u, p.err_flag, 13);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t d = tmem_base + (uint32_t)(blk * C64X2_ACC_COLS + 192);
@@ -1941,11 +1962,19 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
             for (int item = cluster_id; item < p.num_tiles; item += num_clusters, ++it) {
                 const int acc = it & 1;
                 const bool more = item + num_clusters < p.num_tiles;
+                // conv1_1 of the NEXT tile goes in as early as possible - block 0 before this tile's first conv1_2 group, block 1 right
+                // after it - so that its accumulators are complete one kw group (2300 tensor cycles) into the tile and the mid-epilogue has
+                // the remaining two groups to convert them.  t1_empty: the mid-epilogue of THIS tile holds its values in registers.
+                if (more) {
+                    mbar_wait(t1_empty, (uint32_t)it & 1u, p.err_flag, 14);
+                    tc_fence_after();
+                    conv1_block(0, false);
+                }
                 mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1, p.err_flag, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C64X2_ACC_COLS);
                 for (int kw = 0; kw < 3; ++kw) {
-                    mbar_wait_cl(&a_full[kw], (uint32_t)it & 1u, p.err_flag, 3);
+                    mbar_wait(&a_full[kw], (uint32_t)it & 1u, p.err_flag, 3);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t sa = smem_u32(asm_ + kw * C64X2_A_STAGE_BYTES);
@@ -1966,12 +1995,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                         if (kw == 2) tc_commit_2cta(&tfull_bar[acc]);
                     }
                     __syncwarp();
-                    if (more && kw < 2) {
-                        // the mid-epilogue of THIS tile has read the conv1_1 accumulators (its patches are complete, else a_full[kw] above
-                        // could not have completed); t1_empty makes that explicit for the tensor-memory proxy
-                        if (kw == 0) { mbar_wait_cl(t1_empty, (uint32_t)it & 1u, p.err_flag, 14); tc_fence_after(); }
-                        conv1_block(kw, kw == 1);
-                    }
+                    if (more && kw == 0) conv1_block(1, true);
                 }
             }
         }
@@ -1980,7 +2004,6 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
         const int q = warp & 3, ch = warp >> 2;
         const int row = q * 32 + lane;
         const int w_l = row % C64_TW, h_l = row / C64_TW;
-        const float2* bias1 = reinterpret_cast<const float2*>(p.bias1 + 32 * ch);
         auto final_epilogue = [&](int item, int fit) {
             const int mt = 2 * item + (int)rank;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
@@ -2018,25 +2041,30 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
             tc_fence_after();
             uint32_t hi[2][16], lo[2][16];
             int ppy[2], ppx[2]; bool in_patch[2];
+            uint32_t v[2][32];
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk)    // both loads in flight before the first conversion
+                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * C64X2_ACC_COLS + 192 + 32 * ch), v[blk]);
+            tc_wait_ld();
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk) {
                 const int pp = blk * 128 + row;
                 ppy[blk] = pp / C1F_PPX; ppx[blk] = pp - ppy[blk] * C1F_PPX;
                 in_patch[blk] = pp < C1F_PP;
                 const int gy = th * C64_TH - 1 + ppy[blk], gx = tw * C64_TW - 1 + ppx[blk];
-                const bool inside = in_patch[blk] && b < p.B && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-                uint32_t v[32];
-                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * C64X2_ACC_COLS + 192 + 32 * ch), v);
-                tc_wait_ld();
+                const bool inside = in_patch[blk] && b < p.B && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && !(p.exp == 1 && blk == 1);
+                if (inside) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float2 bv = __ldg(bias1 + i);
-                    float f0 = __uint_as_float(v[2 * i]) + bv.x, f1 = __uint_as_float(v[2 * i + 1]) + bv.y;
-                    if (p.leaky1) { f0 = fmaxf(f0, kNegSlope * f0); f1 = fmaxf(f1, kNegSlope * f1); }
-                    if (!inside) { f0 = 0.f; f1 = 0.f; }   // conv1_2's zero padding / pixels of no image
-                    hi[blk][i] = pack_hi2<FP16>(f0, f1);
-                    const float2 r = unpack2<FP16>(hi[blk][i]);
-                    lo[blk][i] = pack_hi2<FP16>(f0 - r.x, f1 - r.y);
+                    for (int i = 0; i < 16; ++i) {
+                        float f0 = __uint_as_float(v[blk][2 * i]), f1 = __uint_as_float(v[blk][2 * i + 1]);   // bias included (K index 27)
+                        if (p.leaky1) { f0 = fmaxf(f0, kNegSlope * f0); f1 = fmaxf(f1, kNegSlope * f1); }
+                        hi[blk][i] = pack_hi2<FP16>(f0, f1);
+                        const float2 r = unpack2<FP16>(hi[blk][i]);
+                        lo[blk][i] = pack_hi2<FP16>(f0 - r.x, f1 - r.y);
+                    }
+                } else {                          // conv1_2's zero padding, pixels of no image, rows beyond the patch
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { hi[blk][i] = 0u; lo[blk][i] = 0u; }
                 }
             }
             tc_fence_before();
@@ -2529,7 +2557,7 @@ TcConvPlan* tc_conv_plan_create(const TcConvDesc& d) {
     if (padded_out && d.pool == 1) { set_error("tc_conv: fused pooling needs Cout %% 32 == 0"); return nullptr; }
     if (d.pool < 0 || d.pool > 2) { set_error("tc_conv: pool mode must be 0 (none), 1 (max-pool) or 2 (stride 2)"); return nullptr; }
     if (d.pool == 2 && d.k < 3) { set_error("tc_conv: stride 2 needs k >= 3 (for k = 1 TF's 'SAME' samples the even pixels, not the odd ones)"); return nullptr; }
-    if (d.passes == 3 && (!d.x.lo || !d.w.lo)) { set_error("tc_conv: 3-pass mode needs lo planes"); return nullptr; }
+    if (d.passes == 3 && ((!d.x.lo && !d.c1_w) || !d.w.lo)) { set_error("tc_conv: 3-pass mode needs lo planes"); return nullptr; }
     if (d.passes == 4 && (!d.x.l8 || !d.x.h8 || !d.w.l8 || !d.w.h8 || d.half != Half16::FP16 || d.corr_scale <= 0.f)) {
         set_error("tc_conv: fp8-correction mode needs fp16 + e4m3 l8/h8 planes for activations and weights and a correction scale");
         return nullptr;
