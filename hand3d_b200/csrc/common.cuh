@@ -199,7 +199,7 @@ struct TcTuning {
     int no_seg_fusion = 0; // 1: HandSegNet's x8 up-sampling as its own launch (instead of fused into the mask post-processing)
     int c64_tma_out = 1;   // 64-channel pair kernel: bulk-tensor-store epilogue for un-pooled layers (conv2_1)
     int fc_chain = 1;      // FC stacks + rotation epilogue of the lifting stage as one kernel (0 = one launch per layer)
-    int fuse_c1 = 0;       // 1: conv1_1 computed inside conv1_2's kernel (conv_c1f_kernel: 30 % less DRAM traffic, same step time - DESIGN 4.10)
+    int fuse_c1 = 1;       // conv1_1 computed inside conv1_2's kernel (conv_c1f_kernel); 0 = conv_c3_tma_kernel + conv_c64x2_kernel
     int small_batch_split = 1;   // few pixel tiles: narrow single-CTA tiles instead of CTA-pair items (same arithmetic, shorter critical path)
     int chain = 1;         // layer chains: dynamic tile tickets + per-image dependencies between consecutive CTA-pair conv launches (2 = tickets only)
     int pdl = 1;           // programmatic dependent launch between the tensor-core kernels (prologue overlaps the previous kernel's tail)

@@ -1771,7 +1771,7 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
 
 // ------------------------------------------------------------------------------------------ conv1_1 fused into conv1_2 (CTA pair)
 // conv1_1 (3 -> 64 channels) writes 8 bytes per output value that conv1_2 reads straight back: 1.3 GB written and 1.3 GB read per
-// 32-image step, 0.33 ms of HBM-bound launches (conv_c3_tma_kernel).  This kernel is conv_c64x2_kernel for conv1_2 whose activation
+// 32-image step, 0.3 ms of HBM-bound launches (conv_c3_tma_kernel).  This kernel is conv_c64x2_kernel for conv1_2 whose activation
 // patches are not fetched by TMA but COMPUTED in place, by a second (tiny) tensor-core GEMM:
 //   * a pixel tile of conv1_2 (16 x 8) needs conv1_1's output on the 18 x 10 patch around it = 180 patch pixels; they are the rows of
 //     the conv1_1 GEMM (two blocks of 128 rows per CTA), K = 27 -> 32, N = 64;
@@ -1780,17 +1780,20 @@ conv_c64x2_kernel(const __grid_constant__ CUtensorMap map_x_hi, const __grid_con
 //   * four BUILDER warps stage the 20 x 12 x 3 fp32 image patch (the loads of the next tile are in flight while this one is
 //     converted) and write the im2col rows [A_hi 64 B | A_lo 64 B] into ONE 16 KB operand buffer, block after block;
 //   * the MMA warp of the leader interleaves the conv1_1 instructions of tile t + 1 (cta_group::2, M = 256 = this block of both CTAs,
-//     N = 64, three passes into one accumulator: 12 UMMAs per tile) between the kw groups of conv1_2's tile t; their accumulators use
-//     the 2 x 64 TMEM columns the conv1_2 accumulator stages leave free ([192,256) and [448,512));
-//   * the eight epilogue warps run a MID-epilogue per tile: TMEM -> + bias, leaky ReLU, ZERO outside the image (conv1_2's 'SAME' padding
-//     applies to conv1_1's OUTPUT) -> hi / lo split kept in registers -> written into the three kw-shifted patch stages of the
-//     conv_c64 scheme (canonical SWIZZLE_128B rows, generic-proxy stores + fence.proxy.async + mbarrier arrive) as the stages are
-//     released by conv1_2's MMAs of the previous tile; then the usual final epilogue (bias, leaky ReLU, 2 x 2 max-pool, split) of the
-//     previous tile.
+//     N = 64, three passes into one accumulator: 12 UMMAs per tile) with the kw groups of conv1_2's tile t - block 0 before the first
+//     group, block 1 after it; their accumulators use the 2 x 64 TMEM columns the conv1_2 accumulator stages leave free ([192,256) and
+//     [448,512));
+//   * eight MID-epilogue warps: TMEM -> leaky ReLU, ZERO outside the image (conv1_2's 'SAME' padding applies to conv1_1's OUTPUT) ->
+//     hi / lo split kept in registers -> written into the three kw-shifted patch stages of the conv_c64 scheme (canonical SWIZZLE_128B
+//     rows, st.shared + fence.proxy.async + mbarrier arrive) as the stages are released by conv1_2's MMAs of the previous tile;
+//   * eight FINAL-epilogue warps: bias, leaky ReLU, 2 x 2 max-pool, split, store - as in conv_c64x2_kernel.  Mid- and final epilogue
+//     are separate warps because each is a ~3000-cycle serial chain per tile against 3840 tensor cycles per tile: on the same warps
+//     (first version of this kernel) the tile period was their SUM (profiles/r02g_c1f_sampling.md).
 // Barriers (leader's instance counts both CTAs): a1_full 8 builder warps -> MMA, a1_empty commit -> builders, t1_full commit -> mid-
 // epilogue, t1_empty 16 warps -> MMA (values are in registers: the columns may be overwritten), a_full[kw] 16 warps -> MMA, a_empty[kw]
 // commit -> mid-epilogue, tfull / tempty as before.  Stage index = kw, parity = tile iteration.  All waits bounded.
-constexpr int C1F_THREADS = 32 * 14;                       // warps 0-7 epilogue, 8 weight loader, 9 MMA issuer, 10-13 builders
+constexpr int C1F_THREADS = 32 * 21;                       // warps 0-7 final epilogue, 8-15 mid-epilogue, 16-19 builders, 20 MMA issuer
+constexpr int C1F_BUILDERS = 128;                          // (two builder warps are not enough: they become the critical path, ncu r02i)
 constexpr int C1F_PPX = C64_TW + 2, C1F_PPY = C64_TH + 2;  // conv1_1 output patch 18 x 10
 constexpr int C1F_PP = C1F_PPX * C1F_PPY;                  // 180 patch pixels = GEMM rows (2 blocks of 128)
 constexpr int C1F_IPX = C1F_PPX + 2, C1F_IPY = C1F_PPY + 2;
@@ -1831,7 +1834,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
-    if (warp == 8 && lane == 0) {
+    if (warp == 20 && lane == 0) {
         prefetch_tmap(&map_w_hi); prefetch_tmap(&map_w_lo);
         for (int s = 0; s < 3; ++s) { mbar_init(&a_full[s], 16); mbar_init(&a_empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
@@ -1839,7 +1842,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
         mbar_init(a1_full, 8); mbar_init(a1_empty, 1); mbar_init(t1_full, 1); mbar_init(t1_empty, 16); mbar_init(w1_full, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 9) {
+    if (warp == 19) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * C64X2_ACC_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
@@ -1848,22 +1851,11 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
-    if (warp != 8) pdl_wait();   // the loader warp waits after it has issued the (static) weight loads
+    if (warp != 20) pdl_wait();   // the MMA warp waits after it has issued the (static) weight loads
 
-    if (warp == 8) {
-        // ================================ conv1_2 weights: resident, loaded once ================================
-        if (elect_one()) {
-            if (rank == 0) mbar_expect_tx(w_full, 2 * C64X2_W_BYTES);
-            for (int t = 0; t < 9; ++t) {
-                tma_load_2d_2sm(&map_w_hi, wsm + t * C64X2_W_TAP_BYTES, w_full, t * BK, (int)rank * 32);
-                tma_load_2d_2sm(&map_w_lo, wsm + t * C64X2_W_TAP_BYTES + 32 * BK * 2, w_full, t * BK, (int)rank * 32);
-            }
-        }
-        __syncwarp();
-        pdl_wait();
-    } else if (warp >= 10) {
+    if (warp >= 16 && warp < 20) {
         // ================================ builders: conv1_1 weights once, then the im2col rows of every tile ================================
-        const int t = threadIdx.x - 320;                   // 0 .. 127
+        const int t = threadIdx.x - 512;                   // 0 .. 127
         if (t < 64) {                                      // row t: plane t >> 5 (0 hi, 1 lo) of output channel 32 rank + (t & 31)
             const int co = 32 * (int)rank + (t & 31);
             uint32_t pk[16];
@@ -1877,14 +1869,14 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                 if (t < 32) pk[k2] = h;
                 else { const float2 r = unpack2<FP16>(h); pk[k2] = pack_hi2<FP16>(v0 - r.x, v1 - r.y); }
             }
+            const uint32_t w1a = smem_u32(w1sm);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(w1sm + sw128_chunk(t, c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            for (int c = 0; c < 4; ++c) sts_v4(w1a + sw128_chunk(t, c), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(w1_full, 0);
-        constexpr int PRE = (C1F_IMG_FLOATS + 127) / 128;  // 6
+        constexpr int PRE = (C1F_IMG_FLOATS + C1F_BUILDERS - 1) / C1F_BUILDERS;  // 6
         float pre[PRE];
         auto load_img = [&](int item) {
             const int mt = 2 * item + (int)rank;
@@ -1893,7 +1885,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
             const float* xb = x + (int64_t)b * p.H * p.W * 3;
 #pragma unroll
             for (int j = 0; j < PRE; ++j) {
-                const int i = t + j * 128;
+                const int i = t + j * C1F_BUILDERS;
                 const int r = i / (C1F_IPX * 3), rem = i - r * (C1F_IPX * 3);
                 const int gy = y0 + r, gx = x0 + rem / 3;
                 float v = 0.f;
@@ -1901,14 +1893,15 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                 pre[j] = v;
             }
         };
+        const uint32_t a1a = smem_u32(a1sm);
         int fills = 0, it = 0;
         if (cluster_id < p.num_tiles) load_img(cluster_id);
         for (int item = cluster_id; item < p.num_tiles; item += num_clusters, ++it) {
-            float* pb = imgsm + (it & 1) * C1F_IMG_FLOATS;
+            const uint32_t pb = smem_u32(imgsm + (it & 1) * C1F_IMG_FLOATS);
 #pragma unroll
             for (int j = 0; j < PRE; ++j)
-                if (t + j * 128 < C1F_IMG_FLOATS) pb[t + j * 128] = pre[j];
-            named_bar_sync(1, 128);
+                if (t + j * C1F_BUILDERS < C1F_IMG_FLOATS) sts_f32(pb + 4u * (uint32_t)(t + j * C1F_BUILDERS), pre[j]);
+            named_bar_sync(1, C1F_BUILDERS);
             if (item + num_clusters < p.num_tiles) load_img(item + num_clusters);
 #pragma unroll 1
             for (int blk = 0; blk < 2; ++blk, ++fills) {
@@ -1919,8 +1912,8 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                 for (int k2 = 0; k2 < 16; ++k2) {
                     float v0 = 0.f, v1 = 0.f;
                     if (pp < C1F_PP) {
-                        if (2 * k2 < 27) { const int k = 2 * k2; v0 = pb[(py + k / 9) * (C1F_IPX * 3) + px * 3 + (k % 9)]; }
-                        if (2 * k2 + 1 < 27) { const int k = 2 * k2 + 1; v1 = pb[(py + k / 9) * (C1F_IPX * 3) + px * 3 + (k % 9)]; }
+                        if (2 * k2 < 27) { const int k = 2 * k2; v0 = lds_f32(pb + 4u * (uint32_t)((py + k / 9) * (C1F_IPX * 3) + px * 3 + (k % 9))); }
+                        if (2 * k2 + 1 < 27) { const int k = 2 * k2 + 1; v1 = lds_f32(pb + 4u * (uint32_t)((py + k / 9) * (C1F_IPX * 3) + px * 3 + (k % 9))); }
                         if (2 * k2 + 1 == 27) v1 = 1.0f;             // constant-1 column: the bias comes out of the GEMM
                     }
                     hi[k2] = pack_hi2<FP16>(v0, v1);
@@ -1930,16 +1923,25 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                 mbar_wait(a1_empty, ((uint32_t)fills & 1u) ^ 1u, p.err_flag, 11);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    *reinterpret_cast<uint4*>(a1sm + sw128_chunk(t, c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                    *reinterpret_cast<uint4*>(a1sm + sw128_chunk(t, 4 + c)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                    sts_v4(a1a + sw128_chunk(t, c), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                    sts_v4(a1a + sw128_chunk(t, 4 + c), lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(a1_full, 0);
             }
         }
-    } else if (warp == 9) {
-        // ================================ MMA issuer (leader CTA; whole warp, one elected lane issues) ================================
+    } else if (warp == 20) {
+        // ================================ conv1_2 weights (resident, loaded once) + MMA issuer (leader CTA) ================================
+        if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(w_full, 2 * C64X2_W_BYTES);
+            for (int t = 0; t < 9; ++t) {
+                tma_load_2d_2sm(&map_w_hi, wsm + t * C64X2_W_TAP_BYTES, w_full, t * BK, (int)rank * 32);
+                tma_load_2d_2sm(&map_w_lo, wsm + t * C64X2_W_TAP_BYTES + 32 * BK * 2, w_full, t * BK, (int)rank * 32);
+            }
+        }
+        __syncwarp();
+        pdl_wait();
         if (rank == 0) {
             mbar_wait(w_full, 0, p.err_flag, 5);
             mbar_wait(w1_full, 0, p.err_flag, 12);
@@ -1975,7 +1977,7 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                 const int acc = it & 1;
                 const bool more = item + num_clusters < p.num_tiles;
                 // conv1_1 of the NEXT tile goes in as early as possible - block 0 before this tile's first conv1_2 group, block 1 right
-                // after it - so that its accumulators are complete one kw group (2300 tensor cycles) into the tile and the mid-epilogue has
+                // after it - so that its accumulators are complete one kw group (1150 tensor cycles) into the tile and the mid-epilogue has
                 // the remaining two groups to convert them.  t1_empty: the mid-epilogue of THIS tile holds its values in registers.
                 if (more) {
                     mbar_wait(t1_empty, (uint32_t)it & 1u, p.err_flag, 14);
@@ -2011,72 +2013,42 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                 }
             }
         }
-    } else {
-        // ================================ epilogue warps: mid-epilogue of tile it, then final epilogue of tile it - 1 ================================
-        const int q = warp & 3, ch = warp >> 2;
+    } else if (warp >= 8) {
+        // ================================ mid-epilogue (8 warps: lane quadrant q, 32-channel half ch) ================================
+        const int q = warp & 3, ch = (warp - 8) >> 2;
         const int row = q * 32 + lane;
-        const int w_l = row % C64_TW, h_l = row / C64_TW;
-        auto final_epilogue = [&](int item, int fit) {
-            const int mt = 2 * item + (int)rank;
-            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
-            const int w = tw * C64_TW + w_l, h = th * C64_TH + h_l;
-            bool valid = (w < p.W) && (h < p.H) && (b < p.B);
-            int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
-            if (p.pool) {
-                const int par = p.pool == 2 ? 1 : 0;
-                valid = valid && ((w & 1) == par) && ((h & 1) == par);
-                pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
-            }
-            const int acc = fit & 1;
-            mbar_wait(&tfull_bar[acc], (fit >> 1) & 1, p.err_flag, 4);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C64X2_ACC_COLS);
-            uint32_t v0[32], v1[32], v2[32];
-            tc_ld_32x32b_x32(taddr + 64 * ch, v0);          // hi*hi
-            tc_ld_32x32b_x32(taddr + 64 * ch + 32, v1);     // hi*lo
-            tc_ld_32x32b_x32(taddr + 128 + 32 * ch, v2);    // lo*hi
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
-            float racc[32];
+        int ppy[2], ppx[2]; bool in_patch[2];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) racc[i] = (__uint_as_float(v0[i]) + __uint_as_float(v1[i])) + __uint_as_float(v2[i]);
-            epilogue_store32<3, FP16>(p, racc, pix, 32 * ch, valid);
-        };
-        int it = 0, prev_item = -1;
+        for (int blk = 0; blk < 2; ++blk) {
+            const int pp = blk * 128 + row;
+            ppy[blk] = pp / C1F_PPX; ppx[blk] = pp - ppy[blk] * C1F_PPX;
+            in_patch[blk] = pp < C1F_PP;
+        }
+        int it = 0;
         for (int item = cluster_id; item < p.num_tiles; item += num_clusters, ++it) {
-            // ---- mid-epilogue: conv1_1 accumulators of this tile -> the three kw patch stages
             const int mt = 2 * item + (int)rank;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
             mbar_wait(t1_full, (uint32_t)it & 1u, p.err_flag, 15);
             tc_fence_after();
             uint32_t hi[2][16], lo[2][16];
-            int ppy[2], ppx[2]; bool in_patch[2];
-            uint32_t v[2][32];
-#pragma unroll
-            for (int blk = 0; blk < 2; ++blk)    // both loads in flight before the first conversion
-                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * C64X2_ACC_COLS + 192 + 32 * ch), v[blk]);
-            tc_wait_ld();
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk) {
-                const int pp = blk * 128 + row;
-                ppy[blk] = pp / C1F_PPX; ppx[blk] = pp - ppy[blk] * C1F_PPX;
-                in_patch[blk] = pp < C1F_PP;
                 const int gy = th * C64_TH - 1 + ppy[blk], gx = tw * C64_TW - 1 + ppx[blk];
                 const bool inside = in_patch[blk] && b < p.B && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-                if (inside) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float f0 = __uint_as_float(v[blk][2 * i]), f1 = __uint_as_float(v[blk][2 * i + 1]);   // bias included (K index 27)
+                for (int h = 0; h < 2; ++h) {              // 16 channels at a time (register budget of the 19-warp block)
+                    uint32_t v[16];
+                    tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * C64X2_ACC_COLS + 192 + 32 * ch + 16 * h), v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float f0 = __uint_as_float(v[2 * i]), f1 = __uint_as_float(v[2 * i + 1]);   // bias included (K index 27)
                         if (p.leaky1) { f0 = fmaxf(f0, kNegSlope * f0); f1 = fmaxf(f1, kNegSlope * f1); }
-                        hi[blk][i] = pack_hi2<FP16>(f0, f1);
-                        const float2 r = unpack2<FP16>(hi[blk][i]);
-                        lo[blk][i] = pack_hi2<FP16>(f0 - r.x, f1 - r.y);
+                        if (!inside) { f0 = 0.f; f1 = 0.f; }         // conv1_2's zero padding, pixels of no image, rows beyond the patch
+                        hi[blk][8 * h + i] = pack_hi2<FP16>(f0, f1);
+                        const float2 r = unpack2<FP16>(hi[blk][8 * h + i]);
+                        lo[blk][8 * h + i] = pack_hi2<FP16>(f0 - r.x, f1 - r.y);
                     }
-                } else {                          // conv1_2's zero padding, pixels of no image, rows beyond the patch
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) { hi[blk][i] = 0u; lo[blk][i] = 0u; }
                 }
             }
             tc_fence_before();
@@ -2102,16 +2074,54 @@ conv_c1f_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(&a_full[kw], 0);
             }
-            // ---- final epilogue of the previous tile (its MMAs completed before stage 2 was released)
-            if (prev_item >= 0) final_epilogue(prev_item, it - 1);
-            prev_item = item;
         }
-        if (prev_item >= 0) final_epilogue(prev_item, it - 1);
+    } else {
+        // ================================ final epilogue (8 warps: lane quadrant q, 32-channel half ch), as conv_c64x2_kernel ================================
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        const int w_l = row % C64_TW, h_l = row / C64_TW;
+        int it = 0;
+        for (int item = cluster_id; item < p.num_tiles; item += num_clusters, ++it) {
+            const int mt = 2 * item + (int)rank;
+            const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, b = mt / (p.tiles_w * p.tiles_h);
+            const int w = tw * C64_TW + w_l, h = th * C64_TH + h_l;
+            bool valid = (w < p.W) && (h < p.H) && (b < p.B);
+            int64_t pix = ((int64_t)b * p.H + h) * p.W + w;
+            if (p.pool) {
+                const int par = p.pool == 2 ? 1 : 0;
+                valid = valid && ((w & 1) == par) && ((h & 1) == par);
+                pix = ((int64_t)b * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+            }
+            const int acc = it & 1;
+            mbar_wait(&tfull_bar[acc], (it >> 1) & 1, p.err_flag, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C64X2_ACC_COLS);
+            float racc[32];
+            {   // three column groups summed one after the other (register budget), in the order of conv_c64x2_kernel: (hh + hl) + lh
+                uint32_t v[32];
+                tc_ld_32x32b_x32(taddr + 64 * ch, v);           // hi*hi
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) racc[i] = __uint_as_float(v[i]);
+                tc_ld_32x32b_x32(taddr + 64 * ch + 32, v);      // hi*lo
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) racc[i] += __uint_as_float(v[i]);
+                tc_ld_32x32b_x32(taddr + 128 + 32 * ch, v);     // lo*hi
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) racc[i] += __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+            epilogue_store32<3, FP16>(p, racc, pix, 32 * ch, valid);
+        }
     }
 
     tc_fence_before();
     cluster_sync_all();
-    if (warp == 9) {
+    if (warp == 19) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * C64X2_ACC_COLS) : "memory");
     }
@@ -2471,7 +2481,7 @@ TcTuning& tc_tuning() {
         v.c64_tma_out = geti("H3D_C64_TMA_OUT", 1);
         v.chain = geti("H3D_TC_CHAIN", 1);
         v.small_batch_split = geti("H3D_TC_SMALL_SPLIT", 1);
-        v.fuse_c1 = geti("H3D_FUSE_C1", 0);
+        v.fuse_c1 = geti("H3D_FUSE_C1", 1);
         v.no_seg_fusion = geti("H3D_NO_SEG_FUSION", 0);
         return v;
     }();

@@ -55,14 +55,14 @@ def test_handsegnet_stage(net, ctx, seg_ref, prec):
     assert err < TOL[prec], "HandSegNet %s: max abs err %.3e" % (prec, err)
 
 
-@pytest.mark.parametrize("knobs", [{"fuse_c1": 1}, {"c3_tma": 0}, {"c3_ffma": 1}], ids=["fused_c1f", "c3_tc", "c3_ffma"])
+@pytest.mark.parametrize("knobs", [{"fuse_c1": 0}, {"fuse_c1": 0, "c3_tma": 0}, {"fuse_c1": 0, "c3_ffma": 1}], ids=["c3_tma", "c3_tc", "c3_ffma"])
 def test_first_layer_kernel_variants(net, ctx, seg_ref, knobs):
-    """conv1_1 has four implementations: its own launch on tensor cores with bulk-tensor-store epilogue (default, covered by every
-    other test), the same with direct global stores (c3_tma = 0), the register-tiled FFMA kernel (c3_ffma = 1), and fused into
-    conv1_2's kernel (fuse_c1 = 1, conv_c1f_kernel); all must give the HandSegNet parity."""
+    """conv1_1 has four implementations: fused into conv1_2's kernel (conv_c1f_kernel: default, covered by every other test), and as
+    its own launch on tensor cores with bulk-tensor-store epilogue (fuse_c1 = 0), with direct global stores (c3_tma = 0) or as the
+    register-tiled FFMA kernel (c3_ffma = 1); all must give the HandSegNet parity."""
     img, ref = seg_ref
     ctx.set_precision("bf16x3")
-    default = {"fuse_c1": 0, "c3_tma": 1, "c3_ffma": 0}
+    default = {"fuse_c1": 1, "c3_tma": 1, "c3_ffma": 0}
     for k, v in knobs.items():
         ctx.set_tuning(k, v)
     try:
@@ -87,24 +87,24 @@ def test_handsegnet_small_odd_maps(net, ctx, wd, shape, prec, fused):
     try:
         out = net.inference_detection(_dev(img))[0].cpu().numpy()
     finally:
-        ctx.set_tuning("fuse_c1", 0)
+        ctx.set_tuning("fuse_c1", 1)
     ref = O.inference_detection(img, wd)[-1]
     assert out.shape == (B, H, W, 2)
     assert np.abs(out - ref).max() < 1e-3
 
 
 def test_fused_first_layers_full_pipeline(net, ctx, wd):
-    """The opt-in fused conv1_1 + conv1_2 kernel through the whole pipeline: same discrete decisions and 1e-3 maps as the default path."""
+    """The fused conv1_1 + conv1_2 kernel (default) against the two separate kernels through the whole pipeline: 1e-3 maps, identical crops."""
     B = 4
     img = np.concatenate([Wt.synthetic_images(2, 320, 320, seed=51), Wt.synthetic_blob_images(2, 320, 320, seed=52)], 0)
     hs = Wt.synthetic_hand_side(B, seed=53)
     ctx.set_precision("bf16x3")
     base = ctx.pipeline(_dev(img), _dev(hs), True)
-    ctx.set_tuning("fuse_c1", 1)
+    ctx.set_tuning("fuse_c1", 0)
     try:
         r = ctx.pipeline(_dev(img), _dev(hs), True, force_center=base["center"], force_scale=base["scale_crop"])
     finally:
-        ctx.set_tuning("fuse_c1", 0)
+        ctx.set_tuning("fuse_c1", 1)
     for k in ("hand_scoremap", "keypoints_scoremap", "keypoint_coord3d"):
         assert (r[k] - base[k]).abs().max().item() < 1e-3, k
     assert torch.equal(r["image_crop"], base["image_crop"])
