@@ -490,7 +490,7 @@ def run_ours(args):
         peak = peaks["tflops_sustained"] if dominant == "tc_conv" else 75.0
         tr = measured_traffic(args.precision) if (dominant == "tc_conv" and args.precision in ("bf16x3", "fp16_f8c") and full and B == 32) else None
         passes = 3 if args.precision in ("bf16x3", "fp16x3") else (2 if args.precision == "fp16_f8c" else 1)
-        roof = {"bound": "tensor", "kernel": "conv_tc2_kernel / conv_tc_kernel / conv_c64x2_kernel / conv_c64_kernel (tcgen05 implicit GEMM: all conv layers with Cin >= 21 and the FC stacks)" if dominant == "tc_conv" else "conv_direct_kernel (fp32 FFMA)",
+        roof = {"bound": "tensor", "kernel": "conv_tc2_kernel / conv_tc_kernel / conv_c64x2_kernel / conv_c64_kernel / conv_c1f_kernel (tcgen05 implicit GEMM: every conv layer - conv1_1 fused into conv1_2 - and the FC stacks)" if dominant == "tc_conv" else "conv_direct_kernel (fp32 FFMA)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": tr[1]["dram_bytes_per_launch"] if tr else None,
                 "traffic_source": ("ncu dram__bytes_read+write per launch, B=32, profiles/%s" % tr[0]) if tr else None,

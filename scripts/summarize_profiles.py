@@ -73,14 +73,14 @@ def main():
                     "%.1f" % d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) if have_dram else "-"))
         out["launches"] = {"step_us": tot, "by_kernel_us": {n: x[0] for n, x in agg.items()}}
         if have_dram:
-            tc = [(n, v, d) for n, v, _, d in step if re.match(r"conv_(tc|c64)", n)]
+            tc = [(n, v, d) for n, v, _, d in step if re.match(r"conv_(tc|c64|c1f)", n)]
             byt = sum(d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0) for _, _, d in tc)
             t = sum(v for _, v, _ in tc)
             tw = sum(d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0.0) * v for _, v, d in tc) / max(t, 1e-9)
             out["tc_conv"] = {"launches_per_step": len(tc), "dram_bytes_per_step": byt, "dram_bytes_per_launch": byt / max(len(tc), 1),
                               "time_us_per_step": t, "tensor_pipe_active_pct_time_weighted": tw}
             out["hbm_kernels"] = {n: {"us": x[0], "dram_mb": x[2] / 1e6, "gb_per_s": x[2] / 1e3 / x[0] if x[0] > 0 else 0.0}
-                                  for n, x in agg.items() if not re.match(r"conv_(tc|c64)", n)}
+                                  for n, x in agg.items() if not re.match(r"conv_(tc|c64|c1f)", n)}
     if os.path.exists(a.dram) and "tc_conv" not in out:
         rows = read_ncu_csv(a.dram)
         by = collections.OrderedDict()
